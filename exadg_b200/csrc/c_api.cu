@@ -1,0 +1,678 @@
+// C ABI (include/exadg_b200.h) and the host-side operator object behind it.
+#include <dlfcn.h>
+
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "../../include/exadg_b200.h"
+#include "operator.cuh"
+#include "vector_ops.cuh"
+
+using namespace exadg_b200;
+
+namespace
+{
+thread_local std::string g_last_error;
+
+// ---- NCCL, resolved at run time (the process usually already holds torch's libnccl.so.2) ----
+struct NcclApi
+{
+  void * lib = nullptr;
+  int (*GetUniqueId)(void *) = nullptr;
+  int (*CommInitRank)(void **, int, char[128], int) = nullptr; // ncclUniqueId passed by value (128 bytes)
+  int (*CommDestroy)(void *) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  bool ok = false;
+};
+struct NcclId { char bytes[128]; };
+
+NcclApi & nccl()
+{
+  static NcclApi api;
+  if (api.lib) return api;
+  const char * names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char * nm : names) { api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
+  if (!api.lib) return api;
+  api.GetUniqueId = (int (*)(void *))dlsym(api.lib, "ncclGetUniqueId");
+  api.CommInitRank = (int (*)(void **, int, char[128], int))dlsym(api.lib, "ncclCommInitRank");
+  api.CommDestroy = (int (*)(void *))dlsym(api.lib, "ncclCommDestroy");
+  api.GroupStart = (int (*)())dlsym(api.lib, "ncclGroupStart");
+  api.GroupEnd = (int (*)())dlsym(api.lib, "ncclGroupEnd");
+  api.Send = (int (*)(const void *, size_t, int, int, void *, cudaStream_t))dlsym(api.lib, "ncclSend");
+  api.Recv = (int (*)(void *, size_t, int, int, void *, cudaStream_t))dlsym(api.lib, "ncclRecv");
+  api.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(api.lib, "ncclAllReduce");
+  api.ok = api.GetUniqueId && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Send && api.Recv && api.AllReduce;
+  return api;
+}
+constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+
+__global__ void pack_cells_kernel(const double * __restrict__ src, const int32_t * __restrict__ cells, int64_t n_cells, int n3, double * __restrict__ out)
+{
+  const int64_t total = n_cells * n3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i / n3; const int k = (int)(i % n3);
+    out[i] = src[(int64_t)cells[c] * n3 + k];
+  }
+}
+
+// closed-form diagonal on the uniform periodic Cartesian box: A = sum_d c_d (M x M x L_d)  =>
+// A_ii = sum_d c_d M_aa M_bb (L_d)_cc, identical for every cell
+__global__ void cartesian_diagonal_kernel(double * __restrict__ diag, int64_t n_dofs, int n, const double * __restrict__ cell_diag, int add)
+{
+  const int n3 = n * n * n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_dofs; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = cell_diag[i % n3];
+    diag[i] = add ? diag[i] + v : v;
+  }
+}
+} // namespace
+
+struct exadg_b200_operator
+{
+  DeviceOperator dev;
+  HostMesh mesh; // connectivity kept for the halo plan (mapping points dropped after setup)
+  cudaStream_t stream = nullptr, comm_stream = nullptr;
+  bool own_stream = true;
+  cudaEvent_t ev_packed = nullptr, ev_halo = nullptr;
+  Reducer red;
+  int64_t launches = 0;
+  int64_t n_local = 0; // locally owned DoFs
+  // halo
+  void * comm = nullptr; bool own_comm = false;
+  std::vector<int32_t *> d_send_lists; std::vector<double *> d_send_bufs;
+  int32_t * d_interior = nullptr, * d_boundary = nullptr; int64_t n_interior = 0, n_boundary = 0;
+  // work vectors
+  double * w[4] = {nullptr, nullptr, nullptr, nullptr};
+  double * d_cell_diag = nullptr;
+  double * d_stage_src = nullptr, * d_stage_dst = nullptr;
+
+  double * work(int i)
+  {
+    if (!w[i]) { CUDA_CHECK(cudaMalloc(&w[i], (size_t)std::max<int64_t>(n_local, 1) * sizeof(double))); }
+    return w[i];
+  }
+};
+
+struct exadg_b200_chebyshev
+{
+  exadg_b200_operator * op = nullptr;
+  int degree = 5; double smoothing_range = 20; int eig_cg_n_iterations = 20;
+  double lambda_min_est = 0, lambda_max_est = 0, theta = 1, delta = 0;
+  double * inv_diag = nullptr, * xold = nullptr, * r = nullptr;
+};
+
+namespace
+{
+template<typename F>
+int guarded(F && f)
+{
+  try { return f(); }
+  catch (const std::invalid_argument & e) { g_last_error = e.what(); return EXADG_B200_ERR_ARG; }
+  catch (const std::exception & e) { g_last_error = e.what(); return std::string(e.what()).find("CUDA") != std::string::npos ? EXADG_B200_ERR_CUDA : EXADG_B200_ERR_UNSUPPORTED; }
+}
+
+void check_ptr(const void * p, const char * name)
+{
+  if (!p) throw std::invalid_argument(std::string(name) + " is null");
+  if ((reinterpret_cast<uintptr_t>(p) & 15) != 0) throw std::invalid_argument(std::string(name) + " must be 16-byte aligned");
+}
+
+void allreduce(exadg_b200_operator * op, double * dev_scalars, int count)
+{
+  if (op->mesh.world <= 1) return;
+  if (!op->comm) throw std::runtime_error("world > 1 requires a communicator (exadg_b200_set_nccl_comm / exadg_b200_nccl_init)");
+  if (nccl().AllReduce(dev_scalars, dev_scalars, (size_t)count, NCCL_FLOAT64, NCCL_SUM, op->comm, op->stream) != 0) throw std::runtime_error("ncclAllReduce failed");
+}
+
+void finish_setup(exadg_b200_operator * op, double ip_factor, bool force_general)
+{
+  HostMesh & M = op->mesh;
+  DeviceOperator & D = op->dev;
+  if (!M.standard_orientation()) throw std::runtime_error("only meshes in standard orientation are supported");
+  D.n = D.degree + 1;
+  D.n_owned = M.n_owned; D.n_ghost = M.n_ghost; D.n_faces = M.n_faces;
+  const int64_t n3 = (int64_t)D.n * D.n * D.n;
+  D.n_global_dofs = M.n_global_cells * n3;
+  op->n_local = M.n_owned * n3;
+  for (int e = 0; e < 3; ++e) D.h[e] = M.h[e];
+  D.cartesian = M.cartesian_uniform && M.all_interior() && !force_general && cartesian_supported(D.n);
+  if (D.cartesian) {
+    // tau_hat is needed by the kernel tables: uniform box => tau_K = sum_d 1/h_d (interior_penalty_parameter.h:68-98)
+    double tk = 0.0;
+    for (int e = 0; e < 3; ++e) tk += 1.0 / M.h[e];
+    D.tau_hat = tk * ip_factor * (D.degree + 1.0) * (D.degree + 1.0);
+    if (cartesian_plan_create(D, M) == 0) D.cartesian = false;
+  }
+  CUDA_CHECK(cudaStreamCreateWithFlags(&op->stream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaStreamCreateWithFlags(&op->comm_stream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaEventCreateWithFlags(&op->ev_packed, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventCreateWithFlags(&op->ev_halo, cudaEventDisableTiming));
+  reducer_init(op->red);
+  setup_geometry(D, M, ip_factor, op->stream);
+  // halo plan on the device + interior/boundary split for overlap
+  if (M.world > 1) {
+    for (auto & p : M.peers) {
+      int32_t * l = nullptr; double * b = nullptr;
+      CUDA_CHECK(cudaMalloc(&l, p.send_cells.size() * sizeof(int32_t)));
+      CUDA_CHECK(cudaMemcpy(l, p.send_cells.data(), p.send_cells.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaMalloc(&b, p.send_cells.size() * n3 * sizeof(double)));
+      op->d_send_lists.push_back(l); op->d_send_bufs.push_back(b);
+    }
+    std::vector<int32_t> interior, boundary;
+    for (int64_t c = 0; c < M.n_owned; ++c) {
+      bool touches = false;
+      for (int f = 0; f < 6; ++f) touches |= (M.nb[c * 6 + f] >= M.n_owned);
+      (touches ? boundary : interior).push_back((int32_t)c);
+    }
+    op->n_interior = (int64_t)interior.size(); op->n_boundary = (int64_t)boundary.size();
+    if (!interior.empty()) { CUDA_CHECK(cudaMalloc(&op->d_interior, interior.size() * 4)); CUDA_CHECK(cudaMemcpy(op->d_interior, interior.data(), interior.size() * 4, cudaMemcpyHostToDevice)); }
+    if (!boundary.empty()) { CUDA_CHECK(cudaMalloc(&op->d_boundary, boundary.size() * 4)); CUDA_CHECK(cudaMemcpy(op->d_boundary, boundary.data(), boundary.size() * 4, cudaMemcpyHostToDevice)); }
+  }
+  // free the big host arrays that are no longer needed
+  std::vector<double>().swap(M.xmap);
+}
+
+// which: 0 all owned cells, 1 cells (batches) that touch no ghost, 2 those that do
+void launch_vmult(exadg_b200_operator * op, double * dst, const double * src, bool add, int which)
+{
+  if (op->dev.cartesian) launch_vmult_cartesian_part(op->dev, dst, src, add, which, op->stream);
+  else if (which == 0) launch_vmult_general(op->dev, dst, src, add, nullptr, 0, op->stream);
+  else {
+    const int64_t nc = which == 1 ? op->n_interior : op->n_boundary;
+    if (nc == 0) return;
+    launch_vmult_general(op->dev, dst, src, add, which == 1 ? op->d_interior : op->d_boundary, nc, op->stream);
+  }
+  op->launches++;
+}
+
+// dst (+)= A src including the ghost import of src (MatrixFree::loop's update_ghost_values, overlapped
+// with the cells that touch no ghost)
+void apply(exadg_b200_operator * op, double * dst, const double * src, bool add)
+{
+  check_ptr(dst, "dst"); check_ptr(src, "src");
+  if (dst == src) throw std::invalid_argument("dst and src must not alias");
+  HostMesh & M = op->mesh;
+  if (M.world <= 1 || M.peers.empty()) { launch_vmult(op, dst, src, add, 0); return; }
+  if (!op->comm) throw std::runtime_error("world > 1 requires a communicator (exadg_b200_set_nccl_comm / exadg_b200_nccl_init)");
+  const int n3 = op->dev.n * op->dev.n * op->dev.n;
+  for (size_t i = 0; i < M.peers.size(); ++i) {
+    const int64_t nc = (int64_t)M.peers[i].send_cells.size();
+    const int64_t total = nc * n3;
+    pack_cells_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 148 * 8), 256, 0, op->stream>>>(src, op->d_send_lists[i], nc, n3, op->d_send_bufs[i]);
+    op->launches++;
+  }
+  CUDA_CHECK(cudaEventRecord(op->ev_packed, op->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(op->comm_stream, op->ev_packed, 0));
+  NcclApi & api = nccl();
+  api.GroupStart();
+  for (size_t i = 0; i < M.peers.size(); ++i) {
+    const PeerPlan & p = M.peers[i];
+    api.Send(op->d_send_bufs[i], p.send_cells.size() * (size_t)n3, NCCL_FLOAT64, p.rank, op->comm, op->comm_stream);
+    api.Recv(op->dev.ghost + p.recv_begin * n3, (size_t)p.recv_count * n3, NCCL_FLOAT64, p.rank, op->comm, op->comm_stream);
+  }
+  if (api.GroupEnd() != 0) throw std::runtime_error("NCCL halo exchange failed");
+  CUDA_CHECK(cudaEventRecord(op->ev_halo, op->comm_stream));
+  launch_vmult(op, dst, src, add, 1);
+  CUDA_CHECK(cudaStreamWaitEvent(op->stream, op->ev_halo, 0));
+  launch_vmult(op, dst, src, add, 2);
+}
+
+void diagonal(exadg_b200_operator * op, double * diag, bool add)
+{
+  check_ptr(diag, "diagonal");
+  DeviceOperator & D = op->dev;
+  if (D.cartesian) {
+    const int n = D.n, n3 = n * n * n;
+    if (!op->d_cell_diag) {
+      // 1-D own-side operator L_d = K/h_d-scaled + face terms; see vmult_cartesian.cu for the derivation
+      Tables1D tab(D.degree);
+      std::vector<double> cd(n3, 0.0);
+      for (int d = 0; d < 3; ++d) {
+        const int e = (d + 1) % 3, f = (d + 2) % 3;
+        const double cdir = D.h[e] * D.h[f] / D.h[d];
+        const real_t tau_hat = (real_t)D.tau_hat * D.h[d];
+        std::vector<real_t> Ld(n);
+        for (int i = 0; i < n; ++i) {
+          real_t v = tab.K[i * n + i];
+          for (int s = 0; s < 2; ++s) {
+            const real_t sig = s ? 1 : -1;
+            const real_t es = (i == (s ? n - 1 : 0)) ? 1 : 0;
+            v += -sig * tab.fd[s][i] * es + tau_hat * es * es; // -1/2 sig (d e^T + e d^T)_ii + tau e e^T
+          }
+          Ld[i] = v;
+        }
+        for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+          const int idx[3] = {i, j, k};
+          cd[i + n * (j + n * k)] += (double)(cdir * Ld[idx[d]] * tab.M[idx[e] * n + idx[e]] * tab.M[idx[f] * n + idx[f]]);
+        }
+      }
+      CUDA_CHECK(cudaMalloc(&op->d_cell_diag, n3 * sizeof(double)));
+      CUDA_CHECK(cudaMemcpy(op->d_cell_diag, cd.data(), n3 * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    cartesian_diagonal_kernel<<<148 * 8, 256, 0, op->stream>>>(diag, op->n_local, n, op->d_cell_diag, add ? 1 : 0);
+    op->launches++;
+  } else {
+    launch_diagonal_general(D, diag, add, op->stream);
+    op->launches++;
+  }
+  CUDA_CHECK(cudaGetLastError());
+}
+
+double read_scalar(exadg_b200_operator * op, int slot)
+{
+  CUDA_CHECK(cudaMemcpyAsync(op->red.host + slot, op->red.result + slot, sizeof(double), cudaMemcpyDeviceToHost, op->stream));
+  CUDA_CHECK(cudaStreamSynchronize(op->stream));
+  return op->red.host[slot];
+}
+
+void cheb_run(exadg_b200_chebyshev * ch, double * x, const double * b, bool zero_start);
+
+void precondition(exadg_b200_operator * op, int precond, const double * inv_diag, exadg_b200_chebyshev * cheb, int slot, double * z, const double * g)
+{
+  const int64_t n = op->n_local;
+  if (precond == EXADG_B200_PRECOND_POINT_JACOBI) { jacobi_dot(op->red, slot, z, inv_diag, g, n, op->stream); op->launches++; }
+  else { cheb_run(cheb, z, g, true); dot(op->red, slot, g, z, n, op->stream); op->launches++; }
+  allreduce(op, op->red.result + slot, 1);
+}
+
+// dealii::SolverCG restated; scalars alpha/beta never leave the device, the host
+// only reads the residual norm once per iteration for ReductionControl::check.
+int cg(exadg_b200_operator * op, double * x, const double * b, int precond, const double * inv_diag, exadg_b200_chebyshev * cheb,
+       double abs_tol, double rel_tol, int max_iter, int * n_iter, double * residuals, std::vector<double> * alphas, std::vector<double> * betas)
+{
+  const int64_t n = op->n_local;
+  cudaStream_t s = op->stream;
+  double * g = op->work(0), * d = op->work(1), * h = op->work(2);
+  int S_GH = 0, S_DH = 1, S_NEW = 2, S_RES = 3;
+  // g = A x - b
+  apply(op, g, x, false);
+  axpby(-1.0, b, 1.0, g, n, s); op->launches++;
+  dot(op->red, S_RES, g, g, n, s); op->launches++;
+  allreduce(op, op->red.result + S_RES, 1);
+  double res = std::sqrt(read_scalar(op, S_RES));
+  const double res0 = res, reduced_tol = rel_tol * res0;
+  if (residuals) residuals[0] = res;
+  int it = 0, state = 0;
+  auto check = [&](int step, double r) {
+    if (r < reduced_tol) return 1;   // ReductionControl::check (strict)
+    if (r <= abs_tol) return 1;      // SolverControl::check
+    if (step >= max_iter || std::isnan(r)) return 2;
+    return 0;
+  };
+  state = check(0, res);
+  if (state == 0) {
+    if (precond != EXADG_B200_PRECOND_NONE) { precondition(op, precond, inv_diag, cheb, S_GH, h, g); scale_copy(-1.0, h, d, n, s); op->launches++; }
+    else { scale_copy(-1.0, g, d, n, s); op->launches++; std::swap(S_GH, S_RES); }
+  }
+  while (state == 0) {
+    ++it;
+    apply(op, h, d, false);
+    dot(op->red, S_DH, d, h, n, s); op->launches++;
+    allreduce(op, op->red.result + S_DH, 1);
+    cg_update_x_g(op->red, S_RES, S_GH, S_DH, x, d, g, h, n, s); op->launches++;
+    allreduce(op, op->red.result + S_RES, 1);
+    res = std::sqrt(read_scalar(op, S_RES));
+    if (residuals) residuals[it] = res;
+    if (alphas) { // Lanczos coefficients for the eigenvalue estimate
+      CUDA_CHECK(cudaMemcpy(op->red.host, op->red.result, 8 * sizeof(double), cudaMemcpyDeviceToHost));
+      alphas->push_back(op->red.host[S_GH] / op->red.host[S_DH]);
+    }
+    state = check(it, res);
+    if (state != 0) break;
+    if (precond != EXADG_B200_PRECOND_NONE) {
+      precondition(op, precond, inv_diag, cheb, S_NEW, h, g);
+      cg_update_d(op->red, S_NEW, S_GH, d, h, n, s); op->launches++;
+      if (betas) { CUDA_CHECK(cudaMemcpy(op->red.host, op->red.result, 8 * sizeof(double), cudaMemcpyDeviceToHost)); betas->push_back(op->red.host[S_NEW] / op->red.host[S_GH]); }
+      std::swap(S_GH, S_NEW);
+    } else {
+      cg_update_d(op->red, S_RES, S_GH, d, g, n, s); op->launches++;
+      if (betas) { CUDA_CHECK(cudaMemcpy(op->red.host, op->red.result, 8 * sizeof(double), cudaMemcpyDeviceToHost)); betas->push_back(op->red.host[S_RES] / op->red.host[S_GH]); }
+      std::swap(S_GH, S_RES);
+    }
+  }
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  if (n_iter) *n_iter = it;
+  return state == 1 ? EXADG_B200_OK : EXADG_B200_ERR_NOT_CONVERGED;
+}
+
+void tridiag_extreme_eigs(const std::vector<double> & a, const std::vector<double> & b, double & emin, double & emax)
+{
+  const int n = (int)a.size();
+  double lo = a[0], hi = a[0];
+  for (int i = 0; i < n; ++i) {
+    const double r = (i > 0 ? std::fabs(b[i - 1]) : 0.0) + (i < n - 1 ? std::fabs(b[i]) : 0.0);
+    lo = std::min(lo, a[i] - r); hi = std::max(hi, a[i] + r);
+  }
+  for (int which = 0; which < 2; ++which) {
+    const int target = which == 0 ? 1 : n;
+    double l = lo, u = hi;
+    for (int it = 0; it < 200; ++it) {
+      const double x = 0.5 * (l + u);
+      int cnt = 0; double q = 1.0;
+      for (int i = 0; i < n; ++i) {
+        q = a[i] - x - (i > 0 ? b[i - 1] * b[i - 1] / q : 0.0);
+        if (q == 0.0) q = 1e-300;
+        if (q < 0.0) ++cnt;
+      }
+      if (cnt >= target) u = x; else l = x;
+    }
+    (which == 0 ? emin : emax) = 0.5 * (l + u);
+  }
+}
+
+// dealii::PreconditionChebyshev::vmult / step with point-Jacobi (chebyshev_smoother.h:79-119)
+void cheb_run(exadg_b200_chebyshev * ch, double * x, const double * b, bool zero_start)
+{
+  exadg_b200_operator * op = ch->op;
+  const int64_t n = op->n_local; cudaStream_t s = op->stream;
+  const double theta = ch->theta, delta = ch->delta;
+  if (!zero_start) apply(op, ch->r, x, false);
+  cheb_first(x, ch->xold, ch->inv_diag, b, ch->r, 1.0 / theta, zero_start, n, s); op->launches++;
+  if (ch->degree < 2 || std::fabs(delta) < 1e-40) return;
+  double rhok = delta / theta; const double sigma = theta / delta;
+  for (int k = 0; k < ch->degree - 1; ++k) {
+    apply(op, ch->r, x, false);
+    const double rhokp = 1.0 / (2.0 * sigma - rhok);
+    const double f1 = rhokp * rhok, f2 = 2.0 * rhokp / delta;
+    rhok = rhokp;
+    cheb_step(x, ch->xold, ch->inv_diag, b, ch->r, f1, f2, n, s); op->launches++;
+  }
+}
+} // namespace
+
+extern "C" {
+
+const char * exadg_b200_last_error(void) { return g_last_error.c_str(); }
+int exadg_b200_version(void) { return 100; }
+
+int exadg_b200_create_hypercube(const exadg_b200_hypercube_desc * desc, exadg_b200_operator ** out)
+{
+  return guarded([&]() {
+    if (!desc || !out) throw std::invalid_argument("null argument");
+    if (desc->degree < 1 || desc->degree > 7) throw std::invalid_argument("degree must be in 1..7");
+    HypercubeDesc hd;
+    hd.n_sub = desc->n_subdivisions; hd.refine = desc->n_refinements; hd.mapping_degree = desc->mapping_degree;
+    hd.deformation = desc->deformation; hd.frequency = desc->frequency;
+    for (int f = 0; f < 6; ++f) { if (desc->boundary[f] < 0 || desc->boundary[f] > 2) throw std::invalid_argument("bad boundary type"); hd.bc[f] = desc->boundary[f]; }
+    hd.rank = desc->rank; hd.world = desc->world < 1 ? 1 : desc->world;
+    std::unique_ptr<exadg_b200_operator> op(new exadg_b200_operator);
+    op->dev.degree = desc->degree;
+    op->mesh = make_hypercube(hd);
+    finish_setup(op.get(), desc->ip_factor, desc->force_general != 0);
+    *out = op.release();
+    return EXADG_B200_OK;
+  });
+}
+
+int exadg_b200_create(const exadg_b200_mesh_desc * desc, exadg_b200_operator ** out)
+{
+  return guarded([&]() {
+    if (!desc || !out || !desc->mapping_points || !desc->neighbors || !desc->neighbor_face || !desc->boundary_type) throw std::invalid_argument("null argument");
+    if (desc->degree < 1 || desc->degree > 7) throw std::invalid_argument("degree must be in 1..7");
+    if (desc->mapping_degree < 1 || desc->mapping_degree > 8) throw std::invalid_argument("mapping_degree must be in 1..8");
+    std::unique_ptr<exadg_b200_operator> op(new exadg_b200_operator);
+    op->dev.degree = desc->degree;
+    HostMesh & M = op->mesh;
+    M.mapping_degree = desc->mapping_degree; M.n_owned = desc->n_cells_owned; M.n_ghost = desc->n_cells_ghost;
+    M.n_global_cells = desc->n_global_cells > 0 ? desc->n_global_cells : desc->n_cells_owned;
+    M.global_offset = desc->global_cell_offset;
+    const int64_t nloc = M.n_owned + M.n_ghost;
+    const int np3 = (M.mapping_degree + 1) * (M.mapping_degree + 1) * (M.mapping_degree + 1);
+    M.xmap.assign(desc->mapping_points, desc->mapping_points + (size_t)nloc * np3 * 3);
+    M.nb.assign(desc->neighbors, desc->neighbors + M.n_owned * 6);
+    M.nbface.assign(desc->neighbor_face, desc->neighbor_face + M.n_owned * 6);
+    M.bt.assign(desc->boundary_type, desc->boundary_type + nloc * 6);
+    for (int64_t i = 0; i < M.n_owned * 6; ++i) {
+      if (M.nb[i] >= nloc) throw std::invalid_argument("neighbour index out of range");
+      if ((M.nb[i] < 0) != (M.bt[i] != BT_INTERIOR)) throw std::invalid_argument("boundary_type inconsistent with neighbors");
+    }
+    double h[3];
+    M.cartesian_uniform = detect_cartesian_uniform(M, h);
+    if (M.cartesian_uniform) for (int e = 0; e < 3; ++e) M.h[e] = h[e];
+    M.build_faces();
+    finish_setup(op.get(), desc->ip_factor, desc->force_general != 0);
+    *out = op.release();
+    return EXADG_B200_OK;
+  });
+}
+
+int exadg_b200_destroy(exadg_b200_operator * op)
+{
+  if (!op) return EXADG_B200_OK;
+  cudaDeviceSynchronize();
+  DeviceOperator & D = op->dev;
+  cartesian_plan_destroy(D);
+  cudaFree(D.nb); cudaFree(D.face_id); cudaFree(D.face_info); cudaFree(D.cellG); cudaFree(D.faceG); cudaFree(D.tau_f); cudaFree(D.tau_cell); cudaFree(D.ghost);
+  for (auto p : op->d_send_lists) cudaFree(p);
+  for (auto p : op->d_send_bufs) cudaFree(p);
+  cudaFree(op->d_interior); cudaFree(op->d_boundary); cudaFree(op->d_cell_diag);
+  for (int i = 0; i < 4; ++i) cudaFree(op->w[i]);
+  cudaFree(op->d_stage_src); cudaFree(op->d_stage_dst);
+  reducer_free(op->red);
+  if (op->own_comm && op->comm) nccl().CommDestroy(op->comm);
+  if (op->ev_packed) cudaEventDestroy(op->ev_packed);
+  if (op->ev_halo) cudaEventDestroy(op->ev_halo);
+  if (op->own_stream && op->stream) cudaStreamDestroy(op->stream);
+  if (op->comm_stream) cudaStreamDestroy(op->comm_stream);
+  delete op;
+  return EXADG_B200_OK;
+}
+
+int exadg_b200_set_stream(exadg_b200_operator * op, void * cuda_stream)
+{
+  return guarded([&]() {
+    if (!op) throw std::invalid_argument("null operator");
+    if (op->own_stream && op->stream) { CUDA_CHECK(cudaStreamSynchronize(op->stream)); cudaStreamDestroy(op->stream); }
+    op->stream = (cudaStream_t)cuda_stream; op->own_stream = false;
+    return EXADG_B200_OK;
+  });
+}
+int exadg_b200_synchronize(exadg_b200_operator * op) { return guarded([&]() { CUDA_CHECK(cudaStreamSynchronize(op->stream)); return EXADG_B200_OK; }); }
+
+int64_t exadg_b200_n(const exadg_b200_operator * op) { return op ? op->dev.n_global_dofs : -1; }
+int64_t exadg_b200_local_size(const exadg_b200_operator * op) { return op ? op->n_local : -1; }
+int64_t exadg_b200_n_cells_owned(const exadg_b200_operator * op) { return op ? op->dev.n_owned : -1; }
+int64_t exadg_b200_n_cells_ghost(const exadg_b200_operator * op) { return op ? op->dev.n_ghost : -1; }
+int exadg_b200_is_cartesian_path(const exadg_b200_operator * op) { return op && op->dev.cartesian ? 1 : 0; }
+int exadg_b200_kernel_launches(const exadg_b200_operator * op, int64_t * count) { if (!op || !count) return EXADG_B200_ERR_ARG; *count = op->launches; return EXADG_B200_OK; }
+
+int exadg_b200_initialize_dof_vector(const exadg_b200_operator * op, double ** vec)
+{
+  return guarded([&]() {
+    if (!op || !vec) throw std::invalid_argument("null argument");
+    const size_t bytes = (size_t)std::max<int64_t>(op->n_local, 1) * sizeof(double);
+    CUDA_CHECK(cudaMalloc(vec, bytes));
+    CUDA_CHECK(cudaMemset(*vec, 0, bytes));
+    return EXADG_B200_OK;
+  });
+}
+int exadg_b200_free_dof_vector(double * vec) { return guarded([&]() { CUDA_CHECK(cudaFree(vec)); return EXADG_B200_OK; }); }
+
+int exadg_b200_vmult(exadg_b200_operator * op, double * dst, const double * src)
+{ return guarded([&]() { if (!op) throw std::invalid_argument("null operator"); apply(op, dst, src, false); return EXADG_B200_OK; }); }
+int exadg_b200_vmult_add(exadg_b200_operator * op, double * dst, const double * src)
+{ return guarded([&]() { if (!op) throw std::invalid_argument("null operator"); apply(op, dst, src, true); return EXADG_B200_OK; }); }
+
+int exadg_b200_vmult_host(exadg_b200_operator * op, double * dst_host, const double * src_host)
+{
+  return guarded([&]() {
+    if (!op || !dst_host || !src_host) throw std::invalid_argument("null argument");
+    const size_t bytes = (size_t)op->n_local * sizeof(double);
+    if (!op->d_stage_src) { CUDA_CHECK(cudaMalloc(&op->d_stage_src, std::max<size_t>(bytes, 16))); CUDA_CHECK(cudaMalloc(&op->d_stage_dst, std::max<size_t>(bytes, 16))); }
+    CUDA_CHECK(cudaMemcpyAsync(op->d_stage_src, src_host, bytes, cudaMemcpyHostToDevice, op->stream));
+    apply(op, op->d_stage_dst, op->d_stage_src, false);
+    CUDA_CHECK(cudaMemcpyAsync(dst_host, op->d_stage_dst, bytes, cudaMemcpyDeviceToHost, op->stream));
+    CUDA_CHECK(cudaStreamSynchronize(op->stream));
+    return EXADG_B200_OK;
+  });
+}
+
+int exadg_b200_calculate_diagonal(exadg_b200_operator * op, double * d) { return guarded([&]() { if (!op) throw std::invalid_argument("null operator"); diagonal(op, d, false); return EXADG_B200_OK; }); }
+int exadg_b200_add_diagonal(exadg_b200_operator * op, double * d) { return guarded([&]() { if (!op) throw std::invalid_argument("null operator"); diagonal(op, d, true); return EXADG_B200_OK; }); }
+int exadg_b200_calculate_inverse_diagonal(exadg_b200_operator * op, double * d)
+{
+  return guarded([&]() {
+    if (!op) throw std::invalid_argument("null operator");
+    diagonal(op, d, false);
+    invert_diagonal(d, op->n_local, op->stream); op->launches++;
+    return EXADG_B200_OK;
+  });
+}
+
+int exadg_b200_jacobi_vmult(exadg_b200_operator * op, double * dst, const double * src, const double * inv_diag)
+{
+  return guarded([&]() {
+    if (!op) throw std::invalid_argument("null operator");
+    check_ptr(dst, "dst"); check_ptr(src, "src"); check_ptr(inv_diag, "inverse_diagonal");
+    jacobi_dot(op->red, 7, dst, inv_diag, src, op->n_local, op->stream); op->launches++;
+    return EXADG_B200_OK;
+  });
+}
+
+int exadg_b200_cg_solve(exadg_b200_operator * op, double * x, const double * b, int preconditioner, exadg_b200_chebyshev * cheb,
+                        double abs_tol, double rel_tol, int max_iter, int * n_iter, double * residuals)
+{
+  return guarded([&]() {
+    if (!op) throw std::invalid_argument("null operator");
+    check_ptr(x, "x"); check_ptr(b, "b");
+    double * inv_diag = nullptr;
+    if (preconditioner == EXADG_B200_PRECOND_POINT_JACOBI) {
+      inv_diag = op->work(3);
+      diagonal(op, inv_diag, false);
+      invert_diagonal(inv_diag, op->n_local, op->stream); op->launches++;
+    } else if (preconditioner == EXADG_B200_PRECOND_CHEBYSHEV) {
+      if (!cheb || cheb->op != op) throw std::invalid_argument("Chebyshev preconditioner missing or built for another operator");
+    } else if (preconditioner != EXADG_B200_PRECOND_NONE) throw std::invalid_argument("unknown preconditioner");
+    return cg(op, x, b, preconditioner, inv_diag, cheb, abs_tol, rel_tol, max_iter, n_iter, residuals, nullptr, nullptr);
+  });
+}
+
+int exadg_b200_chebyshev_create(exadg_b200_operator * op, int degree, double smoothing_range, int eig_cg_n_iterations, exadg_b200_chebyshev ** out)
+{
+  return guarded([&]() {
+    if (!op || !out) throw std::invalid_argument("null argument");
+    std::unique_ptr<exadg_b200_chebyshev> ch(new exadg_b200_chebyshev);
+    ch->op = op; ch->degree = degree; ch->smoothing_range = smoothing_range; ch->eig_cg_n_iterations = eig_cg_n_iterations;
+    const int64_t n = op->n_local; const size_t bytes = (size_t)std::max<int64_t>(n, 1) * sizeof(double);
+    CUDA_CHECK(cudaMalloc(&ch->inv_diag, bytes)); CUDA_CHECK(cudaMalloc(&ch->xold, bytes)); CUDA_CHECK(cudaMalloc(&ch->r, bytes));
+    diagonal(op, ch->inv_diag, false);
+    invert_diagonal(ch->inv_diag, n, op->stream); op->launches++;
+    // eigenvalue estimate: <= eig_cg_n_iterations Jacobi-preconditioned CG steps on (global index mod 11) - mean
+    double * rhs = ch->r, * sol = ch->xold;
+    fill_mod11(rhs, op->mesh.global_offset * (int64_t)(op->dev.n * op->dev.n * op->dev.n), n, op->stream); op->launches++;
+    sum(op->red, 6, rhs, n, op->stream); op->launches++;
+    allreduce(op, op->red.result + 6, 1);
+    const double mean = read_scalar(op, 6) / (double)op->dev.n_global_dofs;
+    add_scalar(rhs, -mean, n, op->stream); op->launches++;
+    fill(sol, 0.0, n, op->stream); op->launches++;
+    std::vector<double> alphas, betas; int its = 0;
+    cg(op, sol, rhs, EXADG_B200_PRECOND_POINT_JACOBI, ch->inv_diag, nullptr, 1.4901161193847656e-08, 1e-2, eig_cg_n_iterations, &its, nullptr, &alphas, &betas);
+    if (!alphas.empty()) {
+      std::vector<double> a(alphas.size()), b(alphas.size() > 1 ? alphas.size() - 1 : 0);
+      for (size_t i = 0; i < alphas.size(); ++i) {
+        a[i] = 1.0 / alphas[i] + (i > 0 ? betas[i - 1] / alphas[i - 1] : 0.0);
+        if (i + 1 < alphas.size()) b[i] = std::sqrt(betas[i]) / alphas[i];
+      }
+      tridiag_extreme_eigs(a, b, ch->lambda_min_est, ch->lambda_max_est);
+    } else { ch->lambda_min_est = ch->lambda_max_est = 1.0; }
+    const double max_ev = 1.2 * ch->lambda_max_est;
+    const double alpha = smoothing_range > 1.0 ? max_ev / smoothing_range : std::min(0.9 * max_ev, ch->lambda_min_est);
+    ch->delta = 0.5 * (max_ev - alpha); ch->theta = 0.5 * (max_ev + alpha);
+    *out = ch.release();
+    return EXADG_B200_OK;
+  });
+}
+int exadg_b200_chebyshev_destroy(exadg_b200_chebyshev * ch)
+{
+  if (!ch) return EXADG_B200_OK;
+  cudaFree(ch->inv_diag); cudaFree(ch->xold); cudaFree(ch->r);
+  delete ch;
+  return EXADG_B200_OK;
+}
+int exadg_b200_chebyshev_get(const exadg_b200_chebyshev * ch, double * lmin, double * lmax, double * theta, double * delta)
+{
+  if (!ch) return EXADG_B200_ERR_ARG;
+  if (lmin) *lmin = ch->lambda_min_est; if (lmax) *lmax = ch->lambda_max_est; if (theta) *theta = ch->theta; if (delta) *delta = ch->delta;
+  return EXADG_B200_OK;
+}
+int exadg_b200_chebyshev_set_interval(exadg_b200_chebyshev * ch, double theta, double delta)
+{ if (!ch) return EXADG_B200_ERR_ARG; ch->theta = theta; ch->delta = delta; return EXADG_B200_OK; }
+int exadg_b200_chebyshev_vmult(exadg_b200_chebyshev * ch, double * dst, const double * src)
+{ return guarded([&]() { if (!ch) throw std::invalid_argument("null smoother"); check_ptr(dst, "dst"); check_ptr(src, "src"); cheb_run(ch, dst, src, true); return EXADG_B200_OK; }); }
+int exadg_b200_chebyshev_step(exadg_b200_chebyshev * ch, double * dst, const double * src)
+{ return guarded([&]() { if (!ch) throw std::invalid_argument("null smoother"); check_ptr(dst, "dst"); check_ptr(src, "src"); cheb_run(ch, dst, src, false); return EXADG_B200_OK; }); }
+
+int exadg_b200_set_nccl_comm(exadg_b200_operator * op, void * comm)
+{
+  return guarded([&]() {
+    if (!op) throw std::invalid_argument("null operator");
+    if (!nccl().ok) throw std::runtime_error("libnccl.so.2 could not be loaded");
+    op->comm = comm; op->own_comm = false;
+    return EXADG_B200_OK;
+  });
+}
+int exadg_b200_nccl_unique_id(char * id128)
+{
+  return guarded([&]() {
+    if (!nccl().ok) throw std::runtime_error("libnccl.so.2 could not be loaded");
+    if (nccl().GetUniqueId(id128) != 0) throw std::runtime_error("ncclGetUniqueId failed");
+    return EXADG_B200_OK;
+  });
+}
+int exadg_b200_nccl_init(exadg_b200_operator * op, const char * id128)
+{
+  return guarded([&]() {
+    if (!op) throw std::invalid_argument("null operator");
+    if (!nccl().ok) throw std::runtime_error("libnccl.so.2 could not be loaded");
+    NcclId id; std::memcpy(id.bytes, id128, 128);
+    typedef int (*init_fn)(void **, int, NcclId, int);
+    init_fn f = (init_fn)dlsym(nccl().lib, "ncclCommInitRank");
+    if (!f || f(&op->comm, op->mesh.world, id, op->mesh.rank) != 0) throw std::runtime_error("ncclCommInitRank failed");
+    op->own_comm = true;
+    return EXADG_B200_OK;
+  });
+}
+
+int exadg_b200_halo_n_peers(const exadg_b200_operator * op) { return op ? (int)op->mesh.peers.size() : -1; }
+int exadg_b200_halo_peer(const exadg_b200_operator * op, int i, int * peer_rank, int64_t * send_cells, int64_t * recv_begin, int64_t * recv_cells)
+{
+  if (!op || i < 0 || i >= (int)op->mesh.peers.size()) return EXADG_B200_ERR_ARG;
+  const PeerPlan & p = op->mesh.peers[i];
+  if (peer_rank) *peer_rank = p.rank; if (send_cells) *send_cells = (int64_t)p.send_cells.size();
+  if (recv_begin) *recv_begin = p.recv_begin; if (recv_cells) *recv_cells = p.recv_count;
+  return EXADG_B200_OK;
+}
+int exadg_b200_halo_send_list(const exadg_b200_operator * op, int i, int32_t * cells)
+{
+  if (!op || !cells || i < 0 || i >= (int)op->mesh.peers.size()) return EXADG_B200_ERR_ARG;
+  std::memcpy(cells, op->mesh.peers[i].send_cells.data(), op->mesh.peers[i].send_cells.size() * sizeof(int32_t));
+  return EXADG_B200_OK;
+}
+int exadg_b200_ghost_global_ids(const exadg_b200_operator * op, int64_t * ids)
+{
+  if (!op || !ids) return EXADG_B200_ERR_ARG;
+  std::memcpy(ids, op->mesh.ghost_global.data(), op->mesh.ghost_global.size() * sizeof(int64_t));
+  return EXADG_B200_OK;
+}
+int exadg_b200_fp64_peak(double * dfma_tflops, double * dmma_tflops)
+{ return guarded([&]() { fp64_peak(dfma_tflops, dmma_tflops); return EXADG_B200_OK; }); }
+double * exadg_b200_ghost_buffer(exadg_b200_operator * op) { return op ? op->dev.ghost : nullptr; }
+int exadg_b200_halo_pack(exadg_b200_operator * op, int i, const double * src, double * send_buffer)
+{
+  return guarded([&]() {
+    if (!op || i < 0 || i >= (int)op->mesh.peers.size()) throw std::invalid_argument("bad peer index");
+    const int n3 = op->dev.n * op->dev.n * op->dev.n;
+    const int64_t nc = (int64_t)op->mesh.peers[i].send_cells.size();
+    pack_cells_kernel<<<(unsigned)std::min<int64_t>((nc * n3 + 255) / 256, 148 * 8), 256, 0, op->stream>>>(src, op->d_send_lists[i], nc, n3, send_buffer);
+    op->launches++;
+    CUDA_CHECK(cudaGetLastError());
+    return EXADG_B200_OK;
+  });
+}
+
+} // extern "C"

@@ -1,0 +1,60 @@
+// Device-side data of the SIPG Laplace operator: the GPU replacement for what
+// dealii::MatrixFree / FEEvaluation / FEFaceEvaluation hold for this path (a3, a5, a8, a10, a11).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "mesh.hpp"
+
+namespace exadg_b200
+{
+#define EXADG_MAX_N 8 // degrees 1..7
+
+struct DeviceOperator
+{
+  int degree = 0, n = 0;
+  int64_t n_owned = 0, n_ghost = 0, n_faces = 0;
+  int64_t n_global_dofs = 0;
+  // connectivity
+  int32_t * nb = nullptr;       // [owned][6]
+  int32_t * face_id = nullptr;  // [owned][6]
+  uint8_t * face_info = nullptr; // [owned][6]
+  // general geometry (null on the Cartesian fast path)
+  double * cellG = nullptr;     // [owned][6][n^3]  symmetric J^-1 J^-T JxW: xx,yy,zz,xy,xz,yz
+  double * faceG = nullptr;     // [n_faces][7][n^2] a_minus(3), a_plus(3), JxW
+  double * tau_f = nullptr;     // [n_faces] penalty incl. (k+1)^2 IP_factor
+  double * tau_cell = nullptr;  // [owned+ghost] surface/volume
+  // ghost values of src, filled by the halo exchange
+  double * ghost = nullptr;     // [n_ghost][n^3]
+  // Cartesian fast path
+  bool cartesian = false;       // uniform boxes + all faces interior
+  double h[3] = {0, 0, 0};
+  double tau_hat = 0;           // tau_K (k+1)^2 IP_factor of the uniform box (times h_d = tau_hat_d)
+  void * cart_plan = nullptr;   // batch plan of the Cartesian kernel (vmult_cartesian.cu)
+};
+
+// ---- geometry.cu ----
+void setup_geometry(DeviceOperator & op, const HostMesh & mesh, double ip_factor, cudaStream_t stream);
+
+// ---- vmult_general.cu ----
+// dst (+)= A src on owned cells listed in cells[0..n_cells) (or all owned cells if cells == nullptr)
+void launch_vmult_general(const DeviceOperator & op, double * dst, const double * src, bool add, const int32_t * cells, int64_t n_cells, cudaStream_t stream);
+void launch_diagonal_general(const DeviceOperator & op, double * diag, bool add, cudaStream_t stream);
+
+// ---- vmult_cartesian.cu ----
+bool cartesian_supported(int n);
+size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh);
+void cartesian_plan_destroy(DeviceOperator & op);
+// which: 0 all cell batches, 1 batches touching no ghost cell, 2 batches touching ghost cells
+void launch_vmult_cartesian_part(const DeviceOperator & op, double * dst, const double * src, bool add, int which, cudaStream_t stream);
+
+// ---- microbench.cu ----
+void fp64_peak(double * dfma_tflops, double * dmma_tflops);
+
+void cuda_check(cudaError_t e, const char * what);
+#define CUDA_CHECK(x) ::exadg_b200::cuda_check((x), #x)
+
+} // namespace exadg_b200

@@ -1,0 +1,419 @@
+// Cartesian fast path of the SIPG Laplace vmult: uniform axis-aligned cells, all faces interior
+// (the periodic box of applications/poisson/throughput, I/grid/periodic_box.h:35-88), FP64.
+//
+// Same operator as vmult_general.cu (cell_loop + face_loop of I/operators/operator_base.cpp:1349-1397
+// with the fluxes of I/poisson/spatial_discretization/laplace_operator.h:180-197), restructured for the
+// FP64 pipe, which - not HBM - bounds this case.  On a uniform box the operator is a sum of
+// Kronecker products,
+//     A = sum_d c_d (M x M x L_d),      c_d = h_e h_f / h_d,
+// with the 1-D mass matrix M and the 1-D SIPG operator L_d (cell stiffness + both faces, coupling a
+// line of a cell to the same line of its two neighbours in direction d only through the neighbour's
+// end value v and end derivative g).  Factoring the mass matrices out,
+//     y = (M x M x M) sum_d c_d (Minv L_d) u,
+// costs 6 n^4 + 18 n^3 FMAs per cell (n = k+1) instead of ~12 n^4 + 100 n^3 for the quadrature-point
+// evaluation, with identical results up to round-off (M and L_d are the exact Gauss(k+1) integrals the
+// reference evaluates).  The Gauss-Lobatto end nodes make the value trace a plain nodal read.
+//
+// Mapping to the SM: a CTA owns a batch of B consecutive cells (a 4x4x2 brick in Morton order) staged in
+// shared memory; a thread owns one xy-plane of one cell in registers (n^2 values: the x and y sweeps and
+// the final M_x, M_y sweeps never leave the register file) and n z-lines for the z sweeps.  1-D matrices
+// are kernel parameters = constant-bank operands of the DFMAs.  Neighbour traces inside the batch are
+// exchanged through shared memory; traces of cells outside the batch (host-precomputed list) are
+// computed once per batch from global memory/L2.  Every DoF of dst is written once, coalesced.
+#include <algorithm>
+#include <cstring>
+
+#include "operator.cuh"
+
+namespace exadg_b200
+{
+namespace
+{
+template<int N>
+struct CartTables
+{
+  double G[3][N * N]; // c_d Minv (K + own-side face terms, tau_hat_d folded in)
+  double P[3][2][N];  // c_d * 1/2 sigma_s * Minv l'(s)          times neighbour end value
+  double Q[3][2][N];  // -c_d * Minv e_s                           times (1/2 sigma_s g_nb + tau_hat_d v_nb)
+  double M[N * N];
+  double fd[2][N];    // l_j'(s)
+  double tau_hat[3];
+};
+
+struct CartArgs
+{
+  const int32_t * nb;        // [owned][6]
+  const int2 * halo;         // [n_batches][H] (lc<<3|f, neighbour cell)
+  const int32_t * halo_cnt;  // [n_batches]
+  const int32_t * batches;   // optional list of batch ids
+  const double * src; const double * ghost; double * dst;
+  int64_t n_owned; int n_items; int H; int add;
+};
+
+template<int N> struct CartCfg { static constexpr int B = (N >= 4) ? 32 : 64; };
+
+template<int N>
+__global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_cartesian_kernel(const __grid_constant__ CartTables<N> T, const CartArgs A)
+{
+  constexpr int B = CartCfg<N>::B, NT = B * N;
+  constexpr int N2 = N * N, N3 = N2 * N;
+  constexpr int PS = N2 | 1, CS = N * PS; // odd plane stride: conflict-free plane- and line-wise access
+  extern __shared__ double smem[];
+  double * U = smem;                 // [B][CS]  src values, later the staging buffer of the result
+  double * Tt = U + B * CS;          // [B][CS]  partial results
+  double * GN = Tt + B * CS;         // [B][2][N2] own end derivatives of the current direction
+  double * HV = GN + B * 2 * N2;     // [H][N2] end values of out-of-batch neighbours
+  double * HG = HV + (size_t)A.H * N2; // [H][N2] end derivatives of out-of-batch neighbours
+  int * nbS = reinterpret_cast<int *>(HG + (size_t)A.H * N2); // [B][6]
+  int * slotS = nbS + B * 6;         // [B][6]
+
+  const int t = threadIdx.x, lc = t / N, s = t % N;
+  const int batch = A.batches ? A.batches[blockIdx.x] : (int)blockIdx.x;
+  const int64_t b0 = (int64_t)batch * B;
+  const int nvalid = (int)min((int64_t)B, A.n_owned - b0);
+  const bool valid = lc < nvalid;
+
+  // ---- phase L: stage the batch, its neighbour table and the traces of out-of-batch neighbours ----
+  for (int i = t; i < B * 6; i += NT) { nbS[i] = (i / 6 < nvalid) ? A.nb[b0 * 6 + i] : -1; slotS[i] = -1; }
+  for (int i = t; i < nvalid * N3; i += NT) {
+    const int c = i / N3, rem = i % N3, k = rem / N2, e = rem % N2;
+    U[c * CS + k * PS + e] = A.src[b0 * N3 + i];
+  }
+  __syncthreads();
+  {
+    const int cnt = A.halo_cnt[batch];
+    const int2 * hl = A.halo + (size_t)batch * A.H;
+    for (int item = t; item < cnt * N2; item += NT) {
+      const int e = item / N2, ab = item % N2, a = ab % N, b = ab / N;
+      const int2 h = hl[e];
+      const int f = h.x & 7, d = f >> 1, sp = (f & 1) ^ 1; // neighbour is entered through its face (d, sp)
+      const double * un = (h.y < A.n_owned) ? A.src + (size_t)h.y * N3 : A.ghost + (size_t)(h.y - A.n_owned) * N3;
+      const int sd = (d == 0) ? 1 : (d == 1 ? N : N2);
+      const int s1 = (d == 0) ? N : 1, s2 = (d == 2) ? N : N2;
+      const double * line = un + a * s1 + b * s2;
+      double g = 0.0, v = 0.0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const double x = line[i * sd];
+        g = fma(sp ? T.fd[1][i] : T.fd[0][i], x, g);
+        if (i == 0 && !sp) v = x;
+        if (i == N - 1 && sp) v = x;
+      }
+      HV[e * N2 + ab] = v; HG[e * N2 + ab] = g;
+      if (ab == 0) slotS[(h.x >> 3) * 6 + f] = e;
+    }
+  }
+  __syncthreads();
+
+  double u[N][N], acc[N][N];
+  if (valid) {
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int i = 0; i < N; ++i) { u[j][i] = U[lc * CS + s * PS + i + N * j]; acc[j][i] = 0.0; }
+  }
+
+  // ---- x and y sweeps on the register plane z = s ----
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    if (valid) {
+#pragma unroll
+      for (int l = 0; l < N; ++l) { // line l: d=0 -> row j=l (runs over i); d=1 -> column i=l (runs over j)
+        double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+        for (int m = 0; m < N; ++m) {
+          const double x = (d == 0) ? u[l][m] : u[m][l];
+          g0 = fma(T.fd[0][m], x, g0); g1 = fma(T.fd[1][m], x, g1);
+        }
+        GN[(lc * 2 + 0) * N2 + l + N * s] = g0;
+        GN[(lc * 2 + 1) * N2 + l + N * s] = g1;
+      }
+    }
+    __syncthreads();
+    if (valid) {
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        const int f = 2 * d + side;
+        const int nbl = nbS[lc * 6 + f] - (int)b0;
+        const bool inb = (nbl >= 0 && nbl < B);
+        const int slot = slotS[lc * 6 + f];
+        const double hs = side ? 0.5 : -0.5; // 1/2 sigma_s
+#pragma unroll
+        for (int l = 0; l < N; ++l) {
+          double vn, gn;
+          if (inb) {
+            const int endn = side ? 0 : N - 1; // neighbour's end node facing us
+            vn = (d == 0) ? U[nbl * CS + s * PS + endn + N * l] : U[nbl * CS + s * PS + l + N * endn];
+            gn = GN[(nbl * 2 + (side ^ 1)) * N2 + l + N * s];
+          } else {
+            vn = HV[slot * N2 + l + N * s]; gn = HG[slot * N2 + l + N * s];
+          }
+          const double tt = fma(hs, gn, T.tau_hat[d] * vn);
+#pragma unroll
+          for (int m = 0; m < N; ++m) {
+            double & y = (d == 0) ? acc[l][m] : acc[m][l];
+            y = fma(T.P[d][side][m], vn, y);
+            y = fma(T.Q[d][side][m], tt, y);
+          }
+        }
+      }
+#pragma unroll
+      for (int l = 0; l < N; ++l)
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+          double y = (d == 0) ? acc[l][r] : acc[r][l];
+#pragma unroll
+          for (int c = 0; c < N; ++c) y = fma(T.G[d][r * N + c], (d == 0) ? u[l][c] : u[c][l], y);
+          if (d == 0) acc[l][r] = y; else acc[r][l] = y;
+        }
+    }
+    __syncthreads(); // GN is reused by the next direction
+  }
+  if (valid) {
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int i = 0; i < N; ++i) Tt[lc * CS + s * PS + i + N * j] = acc[j][i];
+  }
+
+  // ---- z sweep: this thread owns the n lines (i, j = s) ----
+  if (valid) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const double x = U[lc * CS + k * PS + i + N * s];
+        u[i][k] = x; // reuse the plane registers: u[i][k] = value of line i at height k
+        g0 = fma(T.fd[0][k], x, g0); g1 = fma(T.fd[1][k], x, g1);
+      }
+      GN[(lc * 2 + 0) * N2 + i + N * s] = g0;
+      GN[(lc * 2 + 1) * N2 + i + N * s] = g1;
+    }
+  }
+  __syncthreads(); // Tt planes and z traces visible
+  if (valid) {
+    int nbl[2], slot[2]; bool inb[2];
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      nbl[side] = nbS[lc * 6 + 4 + side] - (int)b0;
+      inb[side] = (nbl[side] >= 0 && nbl[side] < B);
+      slot[side] = slotS[lc * 6 + 4 + side];
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double w[N];
+#pragma unroll
+      for (int k = 0; k < N; ++k) w[k] = Tt[lc * CS + k * PS + i + N * s];
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        double vn, gn;
+        if (inb[side]) {
+          const int endn = side ? 0 : N - 1;
+          vn = U[nbl[side] * CS + endn * PS + i + N * s];
+          gn = GN[(nbl[side] * 2 + (side ^ 1)) * N2 + i + N * s];
+        } else {
+          vn = HV[slot[side] * N2 + i + N * s]; gn = HG[slot[side] * N2 + i + N * s];
+        }
+        const double tt = fma(side ? 0.5 : -0.5, gn, T.tau_hat[2] * vn);
+#pragma unroll
+        for (int k = 0; k < N; ++k) { w[k] = fma(T.P[2][side][k], vn, w[k]); w[k] = fma(T.Q[2][side][k], tt, w[k]); }
+      }
+#pragma unroll
+      for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int c = 0; c < N; ++c) w[r] = fma(T.G[2][r * N + c], u[i][c], w[r]);
+      // mass matrix along z, in place (this thread owns the whole line)
+#pragma unroll
+      for (int r = 0; r < N; ++r) {
+        double y = 0.0;
+#pragma unroll
+        for (int c = 0; c < N; ++c) y = fma(T.M[r * N + c], w[c], y);
+        Tt[lc * CS + r * PS + i + N * s] = y;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- mass matrices along x and y on the register plane, staged into U ----
+  if (valid) {
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int i = 0; i < N; ++i) u[j][i] = Tt[lc * CS + s * PS + i + N * j];
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int r = 0; r < N; ++r) {
+        double y = 0.0;
+#pragma unroll
+        for (int c = 0; c < N; ++c) y = fma(T.M[r * N + c], u[j][c], y);
+        acc[j][r] = y;
+      }
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int r = 0; r < N; ++r) {
+        double y = 0.0;
+#pragma unroll
+        for (int c = 0; c < N; ++c) y = fma(T.M[r * N + c], acc[c][i], y);
+        U[lc * CS + s * PS + i + N * r] = y;
+      }
+  }
+  __syncthreads();
+  // ---- coalesced store ----
+  for (int i = t; i < nvalid * N3; i += NT) {
+    const int c = i / N3, rem = i % N3, k = rem / N2, e = rem % N2;
+    const double v = U[c * CS + k * PS + e];
+    if (A.add) A.dst[b0 * N3 + i] += v; else A.dst[b0 * N3 + i] = v;
+  }
+}
+
+struct CartPlan
+{
+  int n = 0, B = 0, H = 0, n_batches = 0;
+  int2 * d_halo = nullptr; int32_t * d_cnt = nullptr;
+  int32_t * d_interior = nullptr, * d_boundary = nullptr; int n_interior = 0, n_boundary = 0;
+  size_t smem = 0;
+  std::vector<char> tables; // CartTables<n> of this operator (depends on h and tau)
+};
+
+template<int N>
+CartTables<N> make_cart_tables(const DeviceOperator & op)
+{
+  Tables1D tab(N - 1);
+  CartTables<N> T;
+  for (int d = 0; d < 3; ++d) {
+    const int e = (d + 1) % 3, f = (d + 2) % 3;
+    const real_t cd = (real_t)op.h[e] * op.h[f] / op.h[d];
+    const real_t tau_hat = (real_t)op.tau_hat * op.h[d];
+    T.tau_hat[d] = (double)tau_hat;
+    // own-side 1-D operator K + sum_s [ -1/2 sigma (d e^T + e d^T) + tau_hat e e^T ]
+    std::vector<real_t> L(tab.K);
+    for (int s = 0; s < 2; ++s) {
+      const real_t sig = s ? 1 : -1; const int end = s ? N - 1 : 0;
+      for (int i = 0; i < N; ++i) { L[i * N + end] -= sig * tab.fd[s][i] / 2; L[end * N + i] -= sig * tab.fd[s][i] / 2; }
+      L[end * N + end] += tau_hat;
+    }
+    for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) {
+      real_t v = 0;
+      for (int m = 0; m < N; ++m) v += tab.Minv[i * N + m] * L[m * N + j];
+      T.G[d][i * N + j] = (double)(cd * v);
+    }
+    for (int s = 0; s < 2; ++s) {
+      const real_t sig = s ? 1 : -1; const int end = s ? N - 1 : 0;
+      for (int i = 0; i < N; ++i) {
+        real_t md = 0;
+        for (int m = 0; m < N; ++m) md += tab.Minv[i * N + m] * tab.fd[s][m];
+        T.P[d][s][i] = (double)(cd * sig / 2 * md);
+        T.Q[d][s][i] = (double)(-cd * tab.Minv[i * N + end]);
+      }
+    }
+  }
+  for (int i = 0; i < N * N; ++i) T.M[i] = (double)tab.M[i];
+  for (int s = 0; s < 2; ++s) for (int i = 0; i < N; ++i) T.fd[s][i] = (double)tab.fd[s][i];
+  return T;
+}
+
+template<int N>
+void launch_n(const DeviceOperator & op, const CartPlan & plan, double * dst, const double * src, bool add, int which, cudaStream_t stream)
+{
+  constexpr int B = CartCfg<N>::B;
+  const CartTables<N> & T = *reinterpret_cast<const CartTables<N> *>(plan.tables.data());
+  static bool configured = false;
+  if (!configured) { CUDA_CHECK(cudaFuncSetAttribute(vmult_cartesian_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)); configured = true; }
+  CartArgs A;
+  A.nb = op.nb; A.halo = plan.d_halo; A.halo_cnt = plan.d_cnt; A.src = src; A.ghost = op.ghost; A.dst = dst;
+  A.n_owned = op.n_owned; A.H = plan.H; A.add = add ? 1 : 0;
+  A.batches = which == 0 ? nullptr : (which == 1 ? plan.d_interior : plan.d_boundary);
+  A.n_items = which == 0 ? plan.n_batches : (which == 1 ? plan.n_interior : plan.n_boundary);
+  if (A.n_items == 0) return;
+  vmult_cartesian_kernel<N><<<A.n_items, B * N, plan.smem, stream>>>(T, A);
+  CUDA_CHECK(cudaGetLastError());
+}
+} // namespace
+
+bool cartesian_supported(int n) { return n >= 2 && n <= 5; }
+
+template<int N>
+void store_tables(CartPlan & P, const DeviceOperator & op)
+{
+  const CartTables<N> T = make_cart_tables<N>(op);
+  P.tables.resize(sizeof(T));
+  std::memcpy(P.tables.data(), &T, sizeof(T));
+}
+
+// builds the batch plan (halo lists, interior/boundary batches, tables); returns the dynamic shared
+// memory per CTA, or 0 if the batch does not fit (caller falls back to the general kernel)
+size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh)
+{
+  CartPlan * Pp = new CartPlan;
+  CartPlan & P = *Pp;
+  P.n = op.n;
+  const int N = op.n;
+  P.B = (N >= 4) ? 32 : 64;
+  P.n_batches = (int)((mesh.n_owned + P.B - 1) / P.B);
+  std::vector<std::vector<int2>> lists(P.n_batches);
+  std::vector<int32_t> interior, boundary;
+  for (int b = 0; b < P.n_batches; ++b) {
+    const int64_t b0 = (int64_t)b * P.B, b1 = std::min<int64_t>(b0 + P.B, mesh.n_owned);
+    bool ghost = false;
+    for (int64_t c = b0; c < b1; ++c) for (int f = 0; f < 6; ++f) {
+      const int32_t p = mesh.nb[c * 6 + f];
+      if (p >= b0 && p < b1) continue;
+      lists[b].push_back(make_int2((int)(((c - b0) << 3) | f), p));
+      ghost |= (p >= mesh.n_owned);
+    }
+    P.H = std::max<int>(P.H, (int)lists[b].size());
+    (ghost ? boundary : interior).push_back(b);
+  }
+  P.H = std::max(P.H, 1);
+  const int N2 = N * N, PS = N2 | 1, CS = N * PS;
+  P.smem = ((size_t)2 * P.B * CS + (size_t)P.B * 2 * N2 + (size_t)2 * P.H * N2) * sizeof(double) + (size_t)P.B * 12 * sizeof(int);
+  if (P.smem > 227 * 1024 - 1024) { delete Pp; return 0; } // does not fit: caller falls back to the general kernel
+  std::vector<int2> flat((size_t)P.n_batches * P.H, make_int2(0, 0));
+  std::vector<int32_t> cnt(P.n_batches);
+  for (int b = 0; b < P.n_batches; ++b) { cnt[b] = (int32_t)lists[b].size(); std::copy(lists[b].begin(), lists[b].end(), flat.begin() + (size_t)b * P.H); }
+  CUDA_CHECK(cudaMalloc(&P.d_halo, flat.size() * sizeof(int2)));
+  CUDA_CHECK(cudaMemcpy(P.d_halo, flat.data(), flat.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMalloc(&P.d_cnt, cnt.size() * sizeof(int32_t)));
+  CUDA_CHECK(cudaMemcpy(P.d_cnt, cnt.data(), cnt.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  P.n_interior = (int)interior.size(); P.n_boundary = (int)boundary.size();
+  if (mesh.world > 1) {
+    if (P.n_interior) { CUDA_CHECK(cudaMalloc(&P.d_interior, interior.size() * 4)); CUDA_CHECK(cudaMemcpy(P.d_interior, interior.data(), interior.size() * 4, cudaMemcpyHostToDevice)); }
+    if (P.n_boundary) { CUDA_CHECK(cudaMalloc(&P.d_boundary, boundary.size() * 4)); CUDA_CHECK(cudaMemcpy(P.d_boundary, boundary.data(), boundary.size() * 4, cudaMemcpyHostToDevice)); }
+  }
+  switch (N) {
+    case 2: store_tables<2>(P, op); break;
+    case 3: store_tables<3>(P, op); break;
+    case 4: store_tables<4>(P, op); break;
+    case 5: store_tables<5>(P, op); break;
+    default: delete Pp; return 0;
+  }
+  op.cart_plan = Pp;
+  return P.smem;
+}
+
+void cartesian_plan_destroy(DeviceOperator & op)
+{
+  CartPlan * P = static_cast<CartPlan *>(op.cart_plan);
+  if (!P) return;
+  cudaFree(P->d_halo); cudaFree(P->d_cnt); cudaFree(P->d_interior); cudaFree(P->d_boundary);
+  delete P;
+  op.cart_plan = nullptr;
+}
+
+// which: 0 all batches, 1 batches that touch no ghost cell, 2 batches that do
+void launch_vmult_cartesian_part(const DeviceOperator & op, double * dst, const double * src, bool add, int which, cudaStream_t stream)
+{
+  const CartPlan * plan = static_cast<const CartPlan *>(op.cart_plan);
+  if (!plan) throw std::runtime_error("Cartesian plan missing");
+  switch (op.n) {
+    case 2: launch_n<2>(op, *plan, dst, src, add, which, stream); break;
+    case 3: launch_n<3>(op, *plan, dst, src, add, which, stream); break;
+    case 4: launch_n<4>(op, *plan, dst, src, add, which, stream); break;
+    case 5: launch_n<5>(op, *plan, dst, src, add, which, stream); break;
+    default: throw std::runtime_error("Cartesian fast path supports degrees 1..4");
+  }
+}
+
+} // namespace exadg_b200

@@ -1,0 +1,302 @@
+// General-geometry SIPG Laplace vmult (curved / non-periodic meshes), FP64, degrees 1..7.
+//
+// One kernel fuses what the reference does in three MatrixFree loops
+// (I/operators/operator_base.cpp:1349-1434): the cell integral, the own side of all six face
+// integrals (interior faces and homogeneous Dirichlet/Neumann boundary faces) and the write of
+// dst.  Evaluating every interior face from both sides (the reference's cell-based view,
+// operator_base.cpp:1618-1704) removes the scatter-add into the neighbour and with it any atomics
+// or colouring: each DoF of dst is written exactly once, by one thread, in a fixed order.
+//
+// Thread layout: n^2 threads per cell (n = k+1), CPB cells per CTA; every 1-D contraction is done by
+// the thread that owns the line, which keeps the line in registers (n loads, n^2 FMAs, n stores);
+// the 1-D matrices are kernel parameters, i.e. constant-bank operands of the DFMAs.
+// Work is done in the collocation basis psi (Lagrange polynomials on the Gauss points):
+//   u_q = S u;  cell: R = sum_e Dq_e^T [G (Dq u_q)];  faces: rank-1 updates of R along normal lines;
+//   y = S^T R   (S^T maps test coefficients back to the nodal basis since span{psi} = span{l}).
+// Quadrature-point physics follows laplace_operator.cpp:129-265 and laplace_operator.h:180-197.
+#include "operator.cuh"
+
+namespace exadg_b200
+{
+namespace
+{
+template<int N>
+struct GenTables
+{
+  double S[N * N], Dq[N * N], sv[2][N], sd[2][N], fd[2][N];
+};
+
+struct GenArgs
+{
+  const int32_t * nb; const int32_t * face_id; const uint8_t * face_info;
+  const double * cellG; const double * faceG; const double * tau_f;
+  const double * src; const double * ghost; double * dst;
+  const int32_t * cells; int64_t n_items; int64_t n_owned; int add;
+};
+
+template<int N, bool TRANSPOSE>
+__device__ __forceinline__ void sweep(const double * __restrict__ M, const double * in, double * out, int base, int stride)
+{
+  double u[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) u[i] = in[base + i * stride];
+#pragma unroll
+  for (int r = 0; r < N; ++r) {
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < N; ++c) acc = fma(TRANSPOSE ? M[c * N + r] : M[r * N + c], u[c], acc);
+    out[base + r * stride] = acc;
+  }
+}
+
+// MODE 0: dst (+)= A src.  MODE 1: diagonal (unit vectors column by column, neighbour function zero:
+// do_face_int_integral, laplace_operator.cpp:165-191; operator_base.cpp:1552-1616).
+template<int N, int CPB, int MODE>
+__global__ void __launch_bounds__(N * N * CPB) vmult_general_kernel(const __grid_constant__ GenTables<N> T, const GenArgs A)
+{
+  constexpr int NP = N | 1;          // odd x-extent: conflict-free 64-bit shared accesses in every direction
+  constexpr int SZ = NP * N * N;
+  constexpr int N2 = N * N, N3 = N * N * N;
+  constexpr int FS = 10 * N2;        // face scratch per cell
+  extern __shared__ double smem[];
+  const int t = threadIdx.x, lc = t / N2, r = t % N2, a = r % N, b = r / N;
+  double * Uq = smem + (size_t)lc * (4 * SZ + FS);
+  double * F0 = Uq + SZ, * F1 = F0 + SZ, * F2 = F1 + SZ;
+  double * W = F2 + SZ; // [10][N2]
+  const int64_t item = (int64_t)blockIdx.x * CPB + lc;
+  const bool valid = item < A.n_items;
+  const int64_t cell = valid ? (A.cells ? (int64_t)A.cells[item] : item) : (A.cells ? (int64_t)A.cells[0] : 0);
+
+  const int lbase[3] = {NP * (a + N * b), a + NP * N * b, a + NP * b};
+  const int lstr[3] = {1, NP, NP * N};
+  const int nstr[3] = {1, N, N2}; // nodal (global) strides
+
+  for (int col = 0; col < (MODE == 1 ? N3 : 1); ++col) {
+    // ---- P0: nodal values into shared memory ----
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const int nodal = a + N * (b + N * k);
+      double v;
+      if (MODE == 1) v = (nodal == col) ? 1.0 : 0.0;
+      else v = A.src[cell * N3 + nodal];
+      Uq[a + NP * (b + N * k)] = v;
+    }
+    __syncthreads();
+    // ---- P1: to the collocation basis ----
+    sweep<N, false>(T.S, Uq, Uq, lbase[0], lstr[0]); __syncthreads();
+    sweep<N, false>(T.S, Uq, Uq, lbase[1], lstr[1]); __syncthreads();
+    sweep<N, false>(T.S, Uq, Uq, lbase[2], lstr[2]); __syncthreads();
+    // ---- P2: reference gradient ----
+    sweep<N, false>(T.Dq, Uq, F0, lbase[0], lstr[0]);
+    sweep<N, false>(T.Dq, Uq, F1, lbase[1], lstr[1]);
+    sweep<N, false>(T.Dq, Uq, F2, lbase[2], lstr[2]);
+    __syncthreads();
+    // ---- P3: flux = G grad (get_gradient + submit_gradient, laplace_operator.cpp:135) ----
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const int q = a + N * (b + N * k), s = a + NP * (b + N * k);
+      const double * g = A.cellG + (size_t)cell * 6 * N3 + q;
+      const double gxx = g[0], gyy = g[N3], gzz = g[2 * N3], gxy = g[3 * N3], gxz = g[4 * N3], gyz = g[5 * N3];
+      const double d0 = F0[s], d1 = F1[s], d2 = F2[s];
+      F0[s] = gxx * d0 + gxy * d1 + gxz * d2;
+      F1[s] = gxy * d0 + gyy * d1 + gyz * d2;
+      F2[s] = gxz * d0 + gyz * d1 + gzz * d2;
+    }
+    __syncthreads();
+    // ---- P4: test with grad psi ----
+    sweep<N, true>(T.Dq, F0, F0, lbase[0], lstr[0]);
+    sweep<N, true>(T.Dq, F1, F1, lbase[1], lstr[1]);
+    sweep<N, true>(T.Dq, F2, F2, lbase[2], lstr[2]);
+    __syncthreads();
+    double * R = F0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) { const int s = a + NP * (b + N * k); R[s] += F1[s] + F2[s]; }
+    __syncthreads();
+
+    // ---- P5: faces, one direction (two faces) at a time ----
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      double * Wvm = W, * Wv2 = W + 2 * N2, * Wd2 = W + 4 * N2, * Wv2t = W + 6 * N2, * Wd2t = W + 8 * N2;
+      double vm[2], dm[2];
+      int32_t nbc[2]; int32_t F[2]; int info[2];
+      {
+        double u[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) u[i] = Uq[lbase[d] + i * lstr[d]];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          double v = 0.0, g = 0.0;
+#pragma unroll
+          for (int i = 0; i < N; ++i) { v = fma(T.sv[s][i], u[i], v); g = fma(T.sd[s][i], u[i], g); }
+          vm[s] = v; dm[s] = g;
+          Wvm[s * N2 + r] = v;
+        }
+      }
+      const int t1 = (d == 0) ? 1 : 0, t2 = (d == 2) ? 1 : 2;
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int f = 2 * d + s;
+        nbc[s] = A.nb[cell * 6 + f]; F[s] = A.face_id[cell * 6 + f]; info[s] = A.face_info[cell * 6 + f];
+        double v2 = 0.0, d2 = 0.0;
+        if (MODE == 0 && nbc[s] >= 0) {
+          const double * un = (nbc[s] < A.n_owned) ? A.src + (size_t)nbc[s] * N3 : A.ghost + (size_t)(nbc[s] - A.n_owned) * N3;
+          const int sp = info[s] & 1; // side of the neighbour's face (standard orientation: same direction d)
+          const int off = a * nstr[t1] + b * nstr[t2];
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            const double x = un[off + i * nstr[d]];
+            d2 = fma(sp ? T.fd[1][i] : T.fd[0][i], x, d2);
+            if (i == 0 && !sp) v2 = x;      // l_j(0) = delta_{j,0}
+            if (i == N - 1 && sp) v2 = x;   // l_j(1) = delta_{j,n-1}
+          }
+        }
+        Wv2[s * N2 + r] = v2; Wd2[s * N2 + r] = d2;
+      }
+      __syncthreads();
+      // nodal -> collocation on the face, first tangential direction
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        double x = 0.0, y = 0.0;
+#pragma unroll
+        for (int p = 0; p < N; ++p) { x = fma(T.S[a * N + p], Wv2[s * N2 + p + N * b], x); y = fma(T.S[a * N + p], Wd2[s * N2 + p + N * b], y); }
+        Wv2t[s * N2 + r] = x; Wd2t[s * N2 + r] = y;
+      }
+      __syncthreads();
+      double vp[2], dp[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        double x = 0.0, y = 0.0;
+#pragma unroll
+        for (int p = 0; p < N; ++p) { x = fma(T.S[b * N + p], Wv2t[s * N2 + a + N * p], x); y = fma(T.S[b * N + p], Wd2t[s * N2 + a + N * p], y); }
+        vp[s] = x; dp[s] = y;
+        Wv2[s * N2 + r] = x;
+      }
+      __syncthreads();
+      double zc[2], cgd[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        double m1 = 0.0, m2 = 0.0, p1 = 0.0, p2 = 0.0;
+#pragma unroll
+        for (int p = 0; p < N; ++p) {
+          m1 = fma(T.Dq[a * N + p], Wvm[s * N2 + p + N * b], m1); m2 = fma(T.Dq[b * N + p], Wvm[s * N2 + a + N * p], m2);
+          p1 = fma(T.Dq[a * N + p], Wv2[s * N2 + p + N * b], p1); p2 = fma(T.Dq[b * N + p], Wv2[s * N2 + a + N * p], p2);
+        }
+        const bool plus = info[s] & 8; const int bt = (info[s] >> 4) & 3;
+        const double sgn = plus ? -1.0 : 1.0;
+        const double * fg = A.faceG + (size_t)F[s] * 7 * N2 + r;
+        const int om = plus ? 3 : 0, op = plus ? 0 : 3;
+        double am[3], ap[3];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) { am[e] = sgn * fg[(om + e) * N2]; ap[e] = sgn * fg[(op + e) * N2]; }
+        const double jxw = fg[6 * N2], tau = A.tau_f[F[s]];
+        const double dnm = am[d] * dm[s] + am[t1] * m1 + am[t2] * m2;
+        double dnp = ap[d] * dp[s] + ap[t1] * p1 + ap[t2] * p2;
+        double vpl = vp[s];
+        if (bt == BT_DIRICHLET) { vpl = -vm[s]; dnp = dnm; }        // weak_boundary_conditions.h:44,118-121
+        else if (bt == BT_NEUMANN) { vpl = vm[s]; dnp = -dnm; }     // :45,124-127
+        else if (MODE == 1) { vpl = 0.0; dnp = 0.0; }               // exterior function zero
+        const double jump = vm[s] - vpl;
+        const double gf = -0.5 * jump;                              // laplace_operator.h:180-185
+        const double vf = 0.5 * (dnm + dnp) - tau * jump;           // laplace_operator.h:187-197
+        zc[s] = -vf * jxw;                                          // submit_value(-value_flux)
+        cgd[s] = am[d] * gf * jxw;                                  // submit_normal_derivative(gradient_flux)
+        Wv2t[s * N2 + r] = am[t1] * gf * jxw;
+        Wd2t[s * N2 + r] = am[t2] * gf * jxw;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        double z = zc[s];
+#pragma unroll
+        for (int p = 0; p < N; ++p) { z = fma(T.Dq[p * N + a], Wv2t[s * N2 + p + N * b], z); z = fma(T.Dq[p * N + b], Wd2t[s * N2 + a + N * p], z); }
+        zc[s] = z;
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        double x = R[lbase[d] + i * lstr[d]];
+        x = fma(T.sv[0][i], zc[0], x); x = fma(T.sd[0][i], cgd[0], x);
+        x = fma(T.sv[1][i], zc[1], x); x = fma(T.sd[1][i], cgd[1], x);
+        R[lbase[d] + i * lstr[d]] = x;
+      }
+      __syncthreads();
+    }
+    // ---- P6: back to the nodal basis, write ----
+    sweep<N, true>(T.S, R, R, lbase[0], lstr[0]); __syncthreads();
+    sweep<N, true>(T.S, R, R, lbase[1], lstr[1]); __syncthreads();
+    sweep<N, true>(T.S, R, R, lbase[2], lstr[2]); __syncthreads();
+    if (MODE == 1) {
+      const int k = col / N2;
+      if (valid && r == col % N2) {
+        const double v = R[a + NP * (b + N * k)];
+        if (A.add) A.dst[cell * N3 + col] += v; else A.dst[cell * N3 + col] = v;
+      }
+    } else if (valid) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const int nodal = a + N * (b + N * k);
+        const double v = R[a + NP * (b + N * k)];
+        if (A.add) A.dst[cell * N3 + nodal] += v; else A.dst[cell * N3 + nodal] = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template<int N>
+GenTables<N> make_tables()
+{
+  Tables1D tab(N - 1);
+  GenTables<N> T;
+  for (int i = 0; i < N * N; ++i) { T.S[i] = (double)tab.S[i]; T.Dq[i] = (double)tab.Dq[i]; }
+  for (int s = 0; s < 2; ++s) for (int i = 0; i < N; ++i) { T.sv[s][i] = (double)tab.sv[s][i]; T.sd[s][i] = (double)tab.sd[s][i]; T.fd[s][i] = (double)tab.fd[s][i]; }
+  return T;
+}
+
+template<int N, int MODE>
+void launch_n(const DeviceOperator & op, double * dst, const double * src, bool add, const int32_t * cells, int64_t n_items, cudaStream_t stream)
+{
+  constexpr int CPB = (N * N >= 64) ? 2 : (N * N >= 36 ? 4 : (N * N >= 16 ? 8 : 16));
+  constexpr int NP = N | 1;
+  static const GenTables<N> T = make_tables<N>();
+  const size_t smem = (size_t)CPB * (4 * NP * N * N + 10 * N * N) * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(vmult_general_kernel<N, CPB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  GenArgs A;
+  A.nb = op.nb; A.face_id = op.face_id; A.face_info = op.face_info; A.cellG = op.cellG; A.faceG = op.faceG; A.tau_f = op.tau_f;
+  A.src = src; A.ghost = op.ghost; A.dst = dst; A.cells = cells; A.n_items = n_items; A.n_owned = op.n_owned; A.add = add ? 1 : 0;
+  if (n_items == 0) return;
+  const unsigned grid = (unsigned)((n_items + CPB - 1) / CPB);
+  vmult_general_kernel<N, CPB, MODE><<<grid, N * N * CPB, smem, stream>>>(T, A);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+template<int MODE>
+void dispatch(const DeviceOperator & op, double * dst, const double * src, bool add, const int32_t * cells, int64_t n_items, cudaStream_t stream)
+{
+  switch (op.n) {
+    case 2: launch_n<2, MODE>(op, dst, src, add, cells, n_items, stream); break;
+    case 3: launch_n<3, MODE>(op, dst, src, add, cells, n_items, stream); break;
+    case 4: launch_n<4, MODE>(op, dst, src, add, cells, n_items, stream); break;
+    case 5: launch_n<5, MODE>(op, dst, src, add, cells, n_items, stream); break;
+    case 6: launch_n<6, MODE>(op, dst, src, add, cells, n_items, stream); break;
+    case 7: launch_n<7, MODE>(op, dst, src, add, cells, n_items, stream); break;
+    case 8: launch_n<8, MODE>(op, dst, src, add, cells, n_items, stream); break;
+    default: throw std::runtime_error("unsupported degree (1..7)");
+  }
+}
+} // namespace
+
+void launch_vmult_general(const DeviceOperator & op, double * dst, const double * src, bool add, const int32_t * cells, int64_t n_cells, cudaStream_t stream)
+{
+  dispatch<0>(op, dst, src, add, cells, cells ? n_cells : op.n_owned, stream);
+}
+
+void launch_diagonal_general(const DeviceOperator & op, double * diag, bool add, cudaStream_t stream)
+{
+  dispatch<1>(op, diag, nullptr, add, nullptr, op.n_owned, stream);
+}
+
+} // namespace exadg_b200

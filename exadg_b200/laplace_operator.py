@@ -1,0 +1,324 @@
+"""Python mirror of the reference's operator / solver interface for the SIPG Laplace path.
+
+Names, argument meaning and error behaviour follow
+  ExaDG::OperatorBase                I/operators/operator_base.h:123-398
+  ExaDG::Poisson::LaplaceOperator    I/poisson/spatial_discretization/laplace_operator.h:238-300
+  ExaDG::Krylov::KrylovSolver        I/solvers_and_preconditioners/solvers/iterative_solvers_dealii_wrapper.h:101-246
+  ExaDG::JacobiPreconditioner        I/solvers_and_preconditioners/preconditioners/jacobi_preconditioner.h:33-86
+  ExaDG::ChebyshevSmoother           I/solvers_and_preconditioners/multigrid/smoothers/chebyshev_smoother.h:35-175
+Everything forwards to the C ABI; vectors are torch CUDA float64 tensors (device memory only).
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+
+class ExaDGError(RuntimeError):
+    """The reference throws dealii::ExcMessage through AssertThrow; the C ABI returns a status."""
+
+
+def _lib():
+    from . import load_library
+    return load_library()
+
+
+def _check(status):
+    if status != 0:
+        raise ExaDGError("exadg_b200 status %d: %s" % (status, _lib().exadg_b200_last_error().decode()))
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise ExaDGError("exadg_b200 needs a CUDA device (there is no CPU fallback)")
+    return torch
+
+
+def _ptr(t, n=None):
+    torch = _torch()
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+        raise ExaDGError("vectors must be contiguous CUDA float64 tensors")
+    if n is not None and t.numel() != n:
+        raise ExaDGError("vector has %d entries, operator expects %d" % (t.numel(), n))
+    return C.c_void_p(t.data_ptr())
+
+
+class LaplaceOperator:
+    """Poisson::LaplaceOperator<3, double, 1> (DG) on the GPU."""
+
+    value_type = np.float64  # typedef Number value_type (laplace_operator.h:248)
+
+    def __init__(self, handle):
+        self._h = handle
+        L = _lib()
+        self._n_global = L.exadg_b200_n(handle)
+        self._n_local = L.exadg_b200_local_size(handle)
+        self.n_cells_owned = L.exadg_b200_n_cells_owned(handle)
+        self.n_cells_ghost = L.exadg_b200_n_cells_ghost(handle)
+        self.is_cartesian_path = L.exadg_b200_is_cartesian_path(handle)
+        # kernels are launched on an operator-owned stream; callers synchronise through synchronize()
+
+    # -- construction ------------------------------------------------------------------------------
+    @classmethod
+    def hypercube(cls, degree, n_subdivisions=1, n_refinements=0, mapping_degree=1, deformation=0.0, frequency=2,
+                  boundary=(0,) * 6, ip_factor=1.0, rank=0, world=1, force_general=False):
+        """Grid of applications/poisson/throughput (periodic box) or applications/poisson/sine."""
+        _torch()
+        d = _desc(degree, n_subdivisions, n_refinements, mapping_degree, deformation, frequency, boundary, ip_factor, rank, world, force_general)
+        h = C.c_void_p()
+        _check(_lib().exadg_b200_create_hypercube(C.byref(d), C.byref(h)))
+        op = cls(h)
+        op.degree = degree
+        return op
+
+    @classmethod
+    def from_mesh(cls, degree, mapping_degree, mapping_points, neighbors, neighbor_face, boundary_type, n_cells_ghost=0,
+                  ip_factor=1.0, force_general=False):
+        """What a reference-side binding passes after extracting the mesh from dealii::MatrixFree."""
+        from . import MeshDesc
+        _torch()
+        xm = np.ascontiguousarray(mapping_points, dtype=np.float64)
+        nb = np.ascontiguousarray(neighbors, dtype=np.int32)
+        nf = np.ascontiguousarray(neighbor_face, dtype=np.uint8)
+        bt = np.ascontiguousarray(boundary_type, dtype=np.uint8)
+        d = MeshDesc()
+        d.degree, d.mapping_degree = degree, mapping_degree
+        d.n_cells_owned, d.n_cells_ghost = nb.shape[0], n_cells_ghost
+        d.mapping_points = xm.ctypes.data_as(C.POINTER(C.c_double))
+        d.neighbors = nb.ctypes.data_as(C.POINTER(C.c_int32))
+        d.neighbor_face = nf.ctypes.data_as(C.POINTER(C.c_uint8))
+        d.boundary_type = bt.ctypes.data_as(C.POINTER(C.c_uint8))
+        d.ip_factor, d.n_global_cells, d.global_cell_offset, d.force_general = ip_factor, nb.shape[0], 0, int(force_general)
+        h = C.c_void_p()
+        _check(_lib().exadg_b200_create(C.byref(d), C.byref(h)))
+        op = cls(h)
+        op.degree = degree
+        return op
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib().exadg_b200_destroy(h)
+            except Exception:
+                pass
+
+    # -- OperatorBase surface ----------------------------------------------------------------------
+    def m(self):
+        return self._n_global
+
+    def n(self):
+        return self._n_global
+
+    def local_size(self):
+        return self._n_local
+
+    def el(self, i, j):
+        # operator_base.cpp:216-222
+        raise ExaDGError("Matrix-free does not allow for entry access")
+
+    def initialize_dof_vector(self):
+        torch = _torch()
+        return torch.zeros(self._n_local, dtype=torch.float64, device="cuda")
+
+    def vmult(self, dst, src):
+        _check(_lib().exadg_b200_vmult(self._h, _ptr(dst, self._n_local), _ptr(src, self._n_local)))
+        self.synchronize_with_torch()
+
+    def vmult_add(self, dst, src):
+        _check(_lib().exadg_b200_vmult_add(self._h, _ptr(dst, self._n_local), _ptr(src, self._n_local)))
+        self.synchronize_with_torch()
+
+    apply = vmult          # operator_base.cpp:156-168: vmult forwards to apply on the matrix-free path
+    apply_add = vmult_add
+    vmult_interface_down = vmult        # operator_base.cpp:184-190
+    vmult_add_interface_up = vmult_add  # operator_base.cpp:192-198
+
+    def vmult_async(self, dst, src):
+        """vmult without the trailing stream synchronisation (benchmark loop)."""
+        _check(_lib().exadg_b200_vmult(self._h, _ptr(dst, self._n_local), _ptr(src, self._n_local)))
+
+    def vmult_host(self, dst_host, src_host):
+        """dst = A src through pinned/pageable HOST tensors (H2D, vmult, D2H inside)."""
+        for t in (dst_host, src_host):
+            if t.is_cuda or t.numel() != self._n_local or not t.is_contiguous():
+                raise ExaDGError("vmult_host expects contiguous host tensors of the local size")
+        _check(_lib().exadg_b200_vmult_host(self._h, C.c_void_p(dst_host.data_ptr()), C.c_void_p(src_host.data_ptr())))
+
+    def calculate_diagonal(self, diagonal):
+        _check(_lib().exadg_b200_calculate_diagonal(self._h, _ptr(diagonal, self._n_local)))
+        self.synchronize_with_torch()
+
+    def add_diagonal(self, diagonal):
+        _check(_lib().exadg_b200_add_diagonal(self._h, _ptr(diagonal, self._n_local)))
+        self.synchronize_with_torch()
+
+    def calculate_inverse_diagonal(self, diagonal):
+        _check(_lib().exadg_b200_calculate_inverse_diagonal(self._h, _ptr(diagonal, self._n_local)))
+        self.synchronize_with_torch()
+
+    def operator_is_singular(self):
+        return False
+
+    def is_empty_locally(self):
+        return self.n_cells_owned == 0
+
+    # -- stream handling ---------------------------------------------------------------------------
+    def synchronize(self):
+        _check(_lib().exadg_b200_synchronize(self._h))
+
+    synchronize_with_torch = synchronize
+
+    def use_torch_stream(self):
+        """Launch on torch's current stream so torch.cuda.Event timing sees the kernels."""
+        torch = _torch()
+        _check(_lib().exadg_b200_set_stream(self._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def kernel_launches(self):
+        c = C.c_int64(0)
+        _check(_lib().exadg_b200_kernel_launches(self._h, C.byref(c)))
+        return c.value
+
+    # -- halo plan (multi-GPU) ---------------------------------------------------------------------
+    def halo_plan(self):
+        L = _lib()
+        peers = []
+        for i in range(L.exadg_b200_halo_n_peers(self._h)):
+            r, ns, rb, rc = C.c_int(), C.c_int64(), C.c_int64(), C.c_int64()
+            _check(L.exadg_b200_halo_peer(self._h, i, C.byref(r), C.byref(ns), C.byref(rb), C.byref(rc)))
+            cells = np.zeros(ns.value, dtype=np.int32)
+            _check(L.exadg_b200_halo_send_list(self._h, i, cells.ctypes.data_as(C.POINTER(C.c_int32))))
+            peers.append(dict(rank=r.value, send_cells=cells, recv_begin=rb.value, recv_count=rc.value))
+        return peers
+
+    def ghost_global_ids(self):
+        ids = np.zeros(self.n_cells_ghost, dtype=np.int64)
+        if self.n_cells_ghost:
+            _check(_lib().exadg_b200_ghost_global_ids(self._h, ids.ctypes.data_as(C.POINTER(C.c_int64))))
+        return ids
+
+    def init_nccl(self, id_bytes):
+        _check(_lib().exadg_b200_nccl_init(self._h, id_bytes))
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    _check(_lib().exadg_b200_nccl_unique_id(buf))
+    return buf.raw
+
+
+def _desc(degree, n_subdivisions, n_refinements, mapping_degree, deformation, frequency, boundary, ip_factor, rank, world, force_general):
+    from . import HypercubeDesc
+    d = HypercubeDesc()
+    d.degree, d.n_subdivisions, d.n_refinements, d.mapping_degree = degree, n_subdivisions, n_refinements, mapping_degree
+    d.deformation, d.frequency, d.ip_factor = float(deformation), frequency, float(ip_factor)
+    for i in range(6):
+        d.boundary[i] = int(boundary[i])
+    d.rank, d.world, d.force_general = rank, world, int(force_general)
+    return d
+
+
+class JacobiPreconditioner:
+    """jacobi_preconditioner.h:33-86: stores 1/diag(A); vmult is a pointwise scaling."""
+
+    def __init__(self, op):
+        self.op = op
+        self.inverse_diagonal = op.initialize_dof_vector()
+        self.update()
+
+    def update(self):
+        self.op.calculate_inverse_diagonal(self.inverse_diagonal)
+
+    def vmult(self, dst, src):
+        _check(_lib().exadg_b200_jacobi_vmult(self.op._h, _ptr(dst), _ptr(src), _ptr(self.inverse_diagonal)))
+        self.op.synchronize()
+
+
+class ChebyshevSmoother:
+    """chebyshev_smoother.h:35-175 with the defaults of multigrid_parameters.h:169-180."""
+
+    def __init__(self, op, iterations=5, smoothing_range=20.0, iterations_eigenvalue_estimation=20):
+        self.op = op
+        h = C.c_void_p()
+        _check(_lib().exadg_b200_chebyshev_create(op._h, iterations, smoothing_range, iterations_eigenvalue_estimation, C.byref(h)))
+        self._h = h
+        v = [C.c_double() for _ in range(4)]
+        _check(_lib().exadg_b200_chebyshev_get(h, *[C.byref(x) for x in v]))
+        self.lambda_min_est, self.lambda_max_est, self.theta, self.delta = [x.value for x in v]
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib().exadg_b200_chebyshev_destroy(h)
+            except Exception:
+                pass
+
+    def set_interval(self, theta, delta):
+        _check(_lib().exadg_b200_chebyshev_set_interval(self._h, theta, delta))
+        self.theta, self.delta = theta, delta
+
+    def vmult(self, dst, src):
+        _check(_lib().exadg_b200_chebyshev_vmult(self._h, _ptr(dst), _ptr(src)))
+        self.op.synchronize()
+
+    def step(self, dst, src):
+        _check(_lib().exadg_b200_chebyshev_step(self._h, _ptr(dst), _ptr(src)))
+        self.op.synchronize()
+
+
+@dataclass
+class SolverData:
+    """solver_data.h: SolverData(max_iter, abs_tol, rel_tol); Poisson defaults parameters.cpp:47."""
+    max_iter: int = 10000
+    abs_tol: float = 1e-20
+    rel_tol: float = 1e-12
+
+
+class KrylovSolverCG:
+    """Krylov::KrylovSolver with linear_solver = CG (dealii::SolverCG + ReductionControl)."""
+
+    def __init__(self, op, preconditioner=None, solver_data=None):
+        self.op = op
+        self.preconditioner = preconditioner
+        self.solver_data = solver_data or SolverData()
+        self.l2_0 = self.l2_n = self.rho = self.n_10 = 0.0
+        self.n = 0
+        self.residuals = None
+
+    def solve(self, dst, rhs):
+        """Returns the number of iterations (solver_control.last_step()); raises if not converged."""
+        sd = self.solver_data
+        kind, cheb = 0, None
+        if isinstance(self.preconditioner, JacobiPreconditioner):
+            kind = 1
+        elif isinstance(self.preconditioner, ChebyshevSmoother):
+            kind, cheb = 2, self.preconditioner._h
+        elif self.preconditioner is not None:
+            raise ExaDGError("unsupported preconditioner")
+        hist = np.zeros(sd.max_iter + 1)
+        it = C.c_int(0)
+        status = _lib().exadg_b200_cg_solve(self.op._h, _ptr(dst), _ptr(rhs), kind, cheb, sd.abs_tol, sd.rel_tol, sd.max_iter,
+                                           C.byref(it), hist.ctypes.data_as(C.POINTER(C.c_double)))
+        self.n = it.value
+        self.residuals = hist[: it.value + 1].copy()
+        if status == 4:
+            raise ExaDGError("SolverControl::NoConvergence after %d iterations" % it.value)
+        _check(status)
+        if not np.isfinite(self.residuals[-1]):
+            raise ExaDGError("Last iteration step contained NaN or Inf values.")
+        # do_compute_performance_metrics (iterative_solvers_dealii_wrapper.h:63-78)
+        self.l2_0, self.l2_n = self.residuals[0], self.residuals[-1]
+        if self.n > 0 and self.l2_0 > 0 and self.l2_n > 0:
+            self.rho = (self.l2_n / self.l2_0) ** (1.0 / self.n)
+            self.n_10 = -10.0 * np.log(10.0) / np.log(self.rho)
+        return self.n
+
+
+def fp64_peak():
+    """Measured FP64 rates (TFLOP/s): register-resident DFMA chains and DMMA m8n8k4."""
+    _torch()
+    a, b = C.c_double(), C.c_double()
+    _check(_lib().exadg_b200_fp64_peak(C.byref(a), C.byref(b)))
+    return a.value, b.value

@@ -1,0 +1,152 @@
+/*
+ * exadg_b200.h -- C ABI of the B200-native SIPG Laplace operator (libexadg_b200.so).
+ *
+ * The reference (ExaDG) has no FFI for this path: the interface is the C++ class surface of
+ * ExaDG::OperatorBase / ExaDG::Poisson::LaplaceOperator consumed by dealii::SolverCG,
+ * dealii::PreconditionChebyshev, JacobiPreconditioner and the multigrid V-cycle.  Every entry
+ * point below names the reference member it replaces (paths relative to the reference root,
+ * I/ = include/exadg/).  A header-only C++ shim with the reference's names lives in
+ * exadg_b200/laplace_operator.h; INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *  - all functions return 0 on success, non-zero on error (the reference throws through
+ *    AssertThrow; the shim converts the status into an exception); exadg_b200_last_error() gives the
+ *    message of the last failure on the calling thread;
+ *  - vectors are FP64 DEVICE pointers holding the locally owned DoFs, cell by cell in active-cell
+ *    order, (k+1)^3 values per cell, lexicographic inside the cell (x fastest) - the layout of
+ *    dealii::LinearAlgebra::distributed::Vector for FE_DGQ(k); pointers must be
+ *    16-byte aligned; dst and src must not alias in vmult (as in the reference);
+ *  - *_host variants take HOST pointers and copy;
+ *  - one operator object per GPU/process; it is bound to one CUDA stream and, like the
+ *    reference's operator (mutable state in const methods), not re-entrant.
+ */
+#ifndef EXADG_B200_H
+#define EXADG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct exadg_b200_operator exadg_b200_operator;
+typedef struct exadg_b200_chebyshev exadg_b200_chebyshev;
+
+enum { EXADG_B200_OK = 0, EXADG_B200_ERR_ARG = 1, EXADG_B200_ERR_CUDA = 2, EXADG_B200_ERR_UNSUPPORTED = 3, EXADG_B200_ERR_NOT_CONVERGED = 4 };
+enum { EXADG_B200_PERIODIC = 0, EXADG_B200_DIRICHLET = 1, EXADG_B200_NEUMANN = 2 };
+enum { EXADG_B200_PRECOND_NONE = 0, EXADG_B200_PRECOND_POINT_JACOBI = 1, EXADG_B200_PRECOND_CHEBYSHEV = 2 };
+
+/* Hypercube grids of the reference's benchmark/test applications
+ * (I/grid/periodic_box.h:35-88, applications/poisson/throughput/application.h:93-165,
+ *  applications/poisson/sine/application.h:180-330): subdivided_hyper_cube(n_sub,-1,1), refine_global,
+ *  optional sine deformation (I/grid/deformed_cube_manifold.h:47-60), p4est-style partition. */
+typedef struct {
+  int degree;          /* k = 1..7, FE_DGQ(k), QGauss(k+1) */
+  int n_subdivisions;  /* cells per direction of the coarse grid */
+  int n_refinements;   /* global refinements */
+  int mapping_degree;  /* MappingQ degree (>= 1) */
+  double deformation;  /* 0: Cartesian; else amplitude of the sine deformation */
+  int frequency;       /* deformation frequency (reference uses 2) */
+  int boundary[6];     /* per domain face x-,x+,y-,y+,z-,z+: EXADG_B200_PERIODIC / DIRICHLET / NEUMANN */
+  double ip_factor;    /* LaplaceKernelData::IP_factor (laplace_operator.h:40-46) */
+  int rank, world;     /* partition (one rank per GPU) */
+  int force_general;   /* non-zero: do not use the Cartesian fast path (testing) */
+} exadg_b200_hypercube_desc;
+
+/* General mesh: what a reference-side binding extracts from dealii::MatrixFree / Triangulation
+ * (I/poisson/spatial_discretization/operator.cpp:261-284).  All arrays are HOST pointers, copied. */
+typedef struct {
+  int degree;
+  int mapping_degree;
+  int64_t n_cells_owned, n_cells_ghost;
+  const double *mapping_points;   /* [(owned+ghost)][(m+1)^3][3] MappingQ support points, lexicographic */
+  const int32_t *neighbors;       /* [owned][6] local cell index (ghosts: owned + i) or -1 on the boundary */
+  const uint8_t *neighbor_face;   /* [owned][6] face number seen from the neighbour (standard orientation only) */
+  const uint8_t *boundary_type;   /* [(owned+ghost)][6] 0 interior/periodic, 1 Dirichlet, 2 Neumann */
+  double ip_factor;
+  int64_t n_global_cells, global_cell_offset;
+  int force_general;
+} exadg_b200_mesh_desc;
+
+const char *exadg_b200_last_error(void);
+int exadg_b200_version(void);
+
+/* LaplaceOperator::initialize (I/poisson/spatial_discretization/laplace_operator.cpp:33-51) together with
+ * MatrixFree::reinit and IP::calculate_penalty_parameter (I/operators/interior_penalty_parameter.h:43-99) */
+int exadg_b200_create_hypercube(const exadg_b200_hypercube_desc *desc, exadg_b200_operator **op);
+int exadg_b200_create(const exadg_b200_mesh_desc *desc, exadg_b200_operator **op);
+int exadg_b200_destroy(exadg_b200_operator *op);
+/* bind to a CUDA stream (cudaStream_t passed as void*); default: a stream owned by the operator */
+int exadg_b200_set_stream(exadg_b200_operator *op, void *cuda_stream);
+int exadg_b200_synchronize(exadg_b200_operator *op);
+
+/* OperatorBase::m()/n() (I/operators/operator_base.cpp:199-214): global number of DoFs */
+int64_t exadg_b200_n(const exadg_b200_operator *op);
+int64_t exadg_b200_local_size(const exadg_b200_operator *op);   /* locally owned DoFs */
+int64_t exadg_b200_n_cells_owned(const exadg_b200_operator *op);
+int64_t exadg_b200_n_cells_ghost(const exadg_b200_operator *op);
+int exadg_b200_is_cartesian_path(const exadg_b200_operator *op);  /* 1 if the Cartesian fast kernel is used */
+int exadg_b200_kernel_launches(const exadg_b200_operator *op, int64_t *count); /* kernels launched so far by this operator */
+
+/* OperatorBase::initialize_dof_vector (operator_base.cpp:232-237): allocate a zeroed device vector */
+int exadg_b200_initialize_dof_vector(const exadg_b200_operator *op, double **vec);
+int exadg_b200_free_dof_vector(double *vec);
+
+/* OperatorBase::vmult / apply (operator_base.cpp:156-168, 264-310): dst = A src */
+int exadg_b200_vmult(exadg_b200_operator *op, double *dst, const double *src);
+/* OperatorBase::vmult_add / apply_add (operator_base.cpp:170-182, 312-354): dst += A src */
+int exadg_b200_vmult_add(exadg_b200_operator *op, double *dst, const double *src);
+/* same through host buffers (H2D copy, vmult, D2H copy) */
+int exadg_b200_vmult_host(exadg_b200_operator *op, double *dst_host, const double *src_host);
+
+/* OperatorBase::calculate_diagonal / add_diagonal / calculate_inverse_diagonal
+ * (operator_base.cpp:608-646, 249-262; invert_diagonal.h:35-46) */
+int exadg_b200_calculate_diagonal(exadg_b200_operator *op, double *diagonal);
+int exadg_b200_add_diagonal(exadg_b200_operator *op, double *diagonal);
+int exadg_b200_calculate_inverse_diagonal(exadg_b200_operator *op, double *diagonal);
+
+/* JacobiPreconditioner::vmult (I/solvers_and_preconditioners/preconditioners/jacobi_preconditioner.h:50-62) */
+int exadg_b200_jacobi_vmult(exadg_b200_operator *op, double *dst, const double *src, const double *inverse_diagonal);
+
+/* Krylov::KrylovSolver::solve with solver "cg" = dealii::SolverCG + ReductionControl(max_iter, abs_tol, rel_tol)
+ * (I/solvers_and_preconditioners/solvers/iterative_solvers_dealii_wrapper.h:137-221).  x holds the initial
+ * guess.  n_iter = ReductionControl::last_step(); residuals (optional, host, length >= max_iter+1) gets
+ * the l2 residual history.  Returns EXADG_B200_ERR_NOT_CONVERGED when max_iter is reached (the reference
+ * throws SolverControl::NoConvergence). */
+int exadg_b200_cg_solve(exadg_b200_operator *op, double *x, const double *b, int preconditioner, exadg_b200_chebyshev *cheb,
+                        double abs_tol, double rel_tol, int max_iter, int *n_iter, double *residuals);
+
+/* ChebyshevSmoother (I/solvers_and_preconditioners/multigrid/smoothers/chebyshev_smoother.h:41-42,149-172):
+ * dealii::PreconditionChebyshev with point-Jacobi; lambda_max from eig_cg_n_iterations CG steps. */
+int exadg_b200_chebyshev_create(exadg_b200_operator *op, int degree, double smoothing_range, int eig_cg_n_iterations, exadg_b200_chebyshev **cheb);
+int exadg_b200_chebyshev_destroy(exadg_b200_chebyshev *cheb);
+int exadg_b200_chebyshev_get(const exadg_b200_chebyshev *cheb, double *lambda_min_est, double *lambda_max_est, double *theta, double *delta);
+int exadg_b200_chebyshev_set_interval(exadg_b200_chebyshev *cheb, double theta, double delta);
+/* SmootherBase::vmult (zero initial guess) and ::step (chebyshev_smoother.h:79-119) */
+int exadg_b200_chebyshev_vmult(exadg_b200_chebyshev *cheb, double *dst, const double *src);
+int exadg_b200_chebyshev_step(exadg_b200_chebyshev *cheb, double *dst, const double *src);
+
+/* Multi-GPU halo exchange of src (the update_ghost_values of MatrixFree::loop).
+ * The library packs the owned cells each peer needs; transport is pluggable:
+ *  - exadg_b200_set_nccl_comm: pass an initialised ncclComm_t (as void*); ghost import uses grouped
+ *    ncclSend/ncclRecv and dot products use ncclAllReduce on the operator's stream;
+ *  - without a communicator and world > 1 the halo can be driven from outside with
+ *    exadg_b200_halo_* (used by the gloo CPU tests of the plan). */
+int exadg_b200_set_nccl_comm(exadg_b200_operator *op, void *nccl_comm);
+/* convenience: create the communicator inside the library (id from rank 0, broadcast by the caller) */
+int exadg_b200_nccl_unique_id(char *id128);
+int exadg_b200_nccl_init(exadg_b200_operator *op, const char *id128);
+int exadg_b200_halo_n_peers(const exadg_b200_operator *op);
+int exadg_b200_halo_peer(const exadg_b200_operator *op, int i, int *peer_rank, int64_t *send_cells, int64_t *recv_cell_begin, int64_t *recv_cells);
+int exadg_b200_halo_send_list(const exadg_b200_operator *op, int i, int32_t *cells_host);
+int exadg_b200_ghost_global_ids(const exadg_b200_operator *op, int64_t *ids_host);
+double *exadg_b200_ghost_buffer(exadg_b200_operator *op);        /* device, [n_ghost][(k+1)^3] */
+int exadg_b200_halo_pack(exadg_b200_operator *op, int i, const double *src, double *send_buffer); /* device buffers */
+
+/* FP64 pipe microbenchmarks used for the roofline denominators (DFMA and DMMA rates) */
+int exadg_b200_fp64_peak(double *dfma_tflops, double *dmma_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EXADG_B200_H */

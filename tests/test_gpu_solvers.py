@@ -1,0 +1,110 @@
+"""CG / Jacobi / Chebyshev around vmult: iteration counts identical to the oracle's restatement of
+dealii::SolverCG, residual histories and results to 1e-10 relative."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.oracle import OracleChebyshev, OracleOperator, synthetic_vector
+
+pytestmark = pytest.mark.gpu
+P6 = (0,) * 6
+SINE_BC = (1, 2, 1, 1, 1, 1)
+
+
+def pair(degree, n_sub, refine, m=1, deformation=0.0, bc=P6):
+    import exadg_b200
+    return (exadg_b200.LaplaceOperator.hypercube(degree, n_sub, refine, m, deformation, 2, bc),
+            OracleOperator(degree, n_sub, refine, m, deformation, 2, bc))
+
+
+@pytest.mark.parametrize("precond", ["none", "jacobi"])
+@pytest.mark.parametrize("case", [(3, 2, 1, 3, 0.15, SINE_BC), (4, 2, 1, 3, 0.0, SINE_BC), (2, 2, 2, 1, 0.1, (1,) * 6)])
+def test_cg_iteration_counts_identical(case, precond):
+    import exadg_b200
+    op, ref = pair(*case)
+    b = ref.rhs_sine()
+    x_ref, it_ref, hist_ref, conv = ref.cg(b, jacobi=(precond == "jacobi"), abs_tol=1e-20, rel_tol=1e-10, max_it=10000)
+    assert conv
+    P = exadg_b200.JacobiPreconditioner(op) if precond == "jacobi" else None
+    solver = exadg_b200.KrylovSolverCG(op, P, exadg_b200.SolverData(10000, 1e-20, 1e-10))
+    x = op.initialize_dof_vector()
+    its = solver.solve(x, torch.from_numpy(b).cuda())
+    assert its == it_ref, (its, it_ref)
+    # residual histories agree far below the stopping threshold => the count is robust, not luck
+    m = min(len(hist_ref), len(solver.residuals))
+    assert np.abs(solver.residuals[:m] / hist_ref[:m] - 1.0).max() < 1e-6
+    assert np.linalg.norm(x.cpu().numpy() - x_ref) < 1e-8 * np.linalg.norm(x_ref)
+
+
+def test_cg_reproduces_reference_golden_l2_error():
+    """End to end on the GPU: sine case k=3 Cartesian -> 1.48342e-02 (cartesian.output:261)."""
+    import exadg_b200
+    op, ref = pair(3, 2, 2, 3, 0.0, SINE_BC)
+    b = ref.rhs_sine()
+    solver = exadg_b200.KrylovSolverCG(op, exadg_b200.JacobiPreconditioner(op), exadg_b200.SolverData(10000, 1e-20, 1e-10))
+    x = op.initialize_dof_vector()
+    solver.solve(x, torch.from_numpy(b).cuda())
+    err = ref.l2_error_sine(x.cpu().numpy())
+    assert abs(err / 1.48342e-02 - 1.0) < 6e-6
+
+
+def test_cg_max_iter_raises_like_no_convergence():
+    import exadg_b200
+    op, ref = pair(3, 2, 1, 1, 0.0, SINE_BC)
+    b = torch.from_numpy(ref.rhs_sine()).cuda()
+    solver = exadg_b200.KrylovSolverCG(op, None, exadg_b200.SolverData(3, 1e-20, 1e-12))
+    with pytest.raises(exadg_b200.ExaDGError):
+        solver.solve(op.initialize_dof_vector(), b)
+    assert solver.n == 3
+
+
+@pytest.mark.parametrize("case", [(3, 2, 1, 3, 0.15, SINE_BC), (2, 1, 2, 1, 0.0, (1,) * 6)])
+def test_chebyshev_smoother_matches_oracle(case):
+    import exadg_b200
+    op, ref = pair(*case)
+    ch_ref = OracleChebyshev(ref, 5, 20.0, 20)
+    ch = exadg_b200.ChebyshevSmoother(op, 5, 20.0, 20)
+    assert abs(ch.lambda_max_est / ch_ref.lambda_max_est - 1.0) < 1e-8
+    assert abs(ch.theta / ch_ref.theta - 1.0) < 1e-8 and abs(ch.delta / ch_ref.delta - 1.0) < 1e-8
+    ch.set_interval(ch_ref.theta, ch_ref.delta)  # identical interval -> identical recurrence
+    b = synthetic_vector(ref.n_dofs)
+    y_ref = ch_ref.vmult(b)
+    y = op.initialize_dof_vector()
+    ch.vmult(y, torch.from_numpy(b).cuda())
+    assert np.linalg.norm(y.cpu().numpy() - y_ref) < 1e-11 * np.linalg.norm(y_ref)
+    x0 = synthetic_vector(ref.n_dofs, seed=3)
+    z_ref = ch_ref.step(x0, b)
+    z = torch.from_numpy(x0.copy()).cuda()
+    ch.step(z, torch.from_numpy(b).cuda())
+    assert np.linalg.norm(z.cpu().numpy() - z_ref) < 1e-11 * np.linalg.norm(z_ref)
+
+
+def test_cg_with_chebyshev_preconditioner_iteration_count():
+    import exadg_b200
+    op, ref = pair(3, 2, 1, 3, 0.15, SINE_BC)
+    ch_ref = OracleChebyshev(ref, 5, 20.0, 20)
+    ch = exadg_b200.ChebyshevSmoother(op, 5, 20.0, 20)
+    ch.set_interval(ch_ref.theta, ch_ref.delta)
+    b = ref.rhs_sine()
+    x_ref, it_ref, hist_ref, conv = ch_ref.cg(b, rel_tol=1e-10)
+    solver = exadg_b200.KrylovSolverCG(op, ch, exadg_b200.SolverData(10000, 1e-20, 1e-10))
+    x = op.initialize_dof_vector()
+    its = solver.solve(x, torch.from_numpy(b).cuda())
+    assert its == it_ref
+    assert np.linalg.norm(x.cpu().numpy() - x_ref) < 1e-8 * np.linalg.norm(x_ref)
+
+
+def test_jacobi_vmult_is_pointwise_scaling():
+    import exadg_b200
+    op, ref = pair(2, 2, 1, 1, 0.1, SINE_BC)
+    P = exadg_b200.JacobiPreconditioner(op)
+    x = synthetic_vector(ref.n_dofs)
+    y = op.initialize_dof_vector()
+    P.vmult(y, torch.from_numpy(x).cuda())
+    assert np.abs(y.cpu().numpy() - ref.inverse_diagonal() * x).max() < 1e-12 * np.abs(x / ref.diagonal()).max()
+
+
+def test_fp64_microbenchmarks_run():
+    import exadg_b200
+    dfma, dmma = exadg_b200.fp64_peak()
+    assert dfma > 1.0 and dmma > 0.1
