@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py -- DoFs/s of the 3-D SIPG Laplace matrix-free vmult (FP64) on B200.
+
+Contract (see the task description): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line.
+A step = one vmult over the whole DoF vector.  Workload at N=1: BASELINE.json configs[1] at the degree the
+metric is quoted on (k=4): periodic Cartesian box, 96^3 cells, 110,592,000 DoFs (885 MB per vector, i.e.
+inputs larger than the 126 MB L2).  N>1 is weak scaling (per-GPU cell count kept ~constant: 120^3, 152^3,
+192^3 cells for N=2,4,8; N=8 is BASELINE.json configs[4]), cells partitioned p4est-style, ghost import over
+NCCL overlapped with interior cells.
+`--impl reference` times the CPU restatement of the reference (oracle/, OpenMP over all host cores) on a
+bounded sample of the same workload; the real deal.II/ExaDG binary cannot be built here.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "DoFs/s of 3D SIPG Laplace matrix-free vmult (fp64, k=4)"
+B_ALG = 16.0  # algorithmic bytes per DoF of the affine vmult: read src once + write dst once
+GRIDS = {1: (3, 5), 2: (15, 3), 4: (19, 3), 8: (3, 6)}  # n_gpus -> (n_subdivisions, n_refinements): 96, 120, 152, 192 cells per direction
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload_key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if one exists."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(workload_key)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(degree, seconds=12.0, cells_1d=16):
+    """The oracle (port of the reference algorithm, OpenMP over cells) on the host cores, bounded sample."""
+    import numpy as np
+    from oracle.oracle import OracleOperator, lib, synthetic_vector
+    n_sub, refine = 1, 0
+    while (n_sub << refine) < cells_1d:
+        refine += 1
+    op = OracleOperator(degree, n_sub, refine, 1, 0.0)
+    x = synthetic_vector(op.n_dofs)
+    y = np.zeros_like(x)
+    threads = lib().orc_max_threads()
+    op.vmult_cellwise(x, threads, dst=y)  # warm-up
+    best, reps, t_start = float("inf"), 0, time.time()
+    while time.time() - t_start < seconds or reps < 3:
+        t0 = time.perf_counter()
+        op.vmult_cellwise(x, threads, dst=y)
+        best = min(best, time.perf_counter() - t0)
+        reps += 1
+    return {"value": op.n_dofs / best, "unit": "DoFs/s", "cores": threads, "kind": "port",
+            "sample": "k=%d periodic Cartesian box, %d^3 cells (%d DoFs), min over %d vmults in %.0f s, oracle/sipg_oracle.c orc_vmult_cellwise, gcc -O3 -march=x86-64-v3 -fopenmp"
+                      % (degree, n_sub << refine, op.n_dofs, reps, time.time() - t_start)}, op.n_dofs / best, best
+
+
+def run_reference(args):
+    """Reference arm: the CPU implementation of the path on the box's host cores (oracle port)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    degree = args.degree
+    from oracle.oracle import OracleOperator, lib, synthetic_vector
+    import numpy as np
+    op = OracleOperator(degree, 1, 5 if degree <= 4 else 4, 1, 0.0)  # 32^3 cells (4.1 M DoFs at k=4)
+    x = synthetic_vector(op.n_dofs)
+    y = np.zeros_like(x)
+    threads = lib().orc_max_threads()
+    for _ in range(args.warmup):
+        op.vmult_cellwise(x, threads, dst=y)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        op.vmult_cellwise(x, threads, dst=y)
+    dt = time.perf_counter() - t0
+    value = op.n_dofs * args.steps / dt
+    sample = "each step = one vmult on a bounded sample of the workload: k=%d periodic Cartesian box, 32^3 cells (%d DoFs); oracle port, OpenMP" % (degree, op.n_dofs)
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "DoFs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "SIPG Laplace vmult, k=%d, periodic Cartesian box (CPU sample: 32^3 cells)" % degree},
+           "cpu_baseline": {"value": value, "unit": "DoFs/s", "cores": threads, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "DoFs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def run_gpu(args):
+    import torch
+    import exadg_b200
+    from exadg_b200.laplace_operator import nccl_unique_id
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    degree = args.degree
+    if args.cells:
+        n_sub, refine = args.cells, 0
+        while n_sub % 2 == 0 and n_sub > 1:
+            n_sub //= 2
+            refine += 1
+    else:
+        n_sub, refine = GRIDS.get(world, (3, 5))
+    deformation = 0.1 if args.mesh == "curvilinear" else 0.0
+    op = exadg_b200.LaplaceOperator.hypercube(degree, n_sub, refine, 1, deformation, 2, (0,) * 6, 1.0, rank=rank, world=world)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        op.init_nccl(bytes(idt.cpu().numpy().tobytes()))
+    op.use_torch_stream()
+    n_local, n_global = op.local_size(), op.n()
+    g = torch.Generator(device="cuda").manual_seed(42 + rank)
+    src = torch.rand(n_local, dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    dst = op.initialize_dof_vector()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        op.vmult_async(dst, src)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = op.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        op.vmult_async(dst, src)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = op.kernel_launches() - launches0
+    # reference protocol as a cross-check (throughput_parameters.h:53-84): min over repeats of the mean over inner reps
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end to end through the host-buffer entry point: pinned host src -> H2D -> vmult -> D2H pinned dst
+    h_src = torch.empty(n_local, dtype=torch.float64).pin_memory()
+    h_src.copy_(src.cpu())
+    h_dst = torch.empty(n_local, dtype=torch.float64).pin_memory()
+    e2e_steps = max(1, min(args.steps, 5))
+    op.vmult_host(h_dst, h_src)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        op.vmult_host(h_dst, h_src)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = t.item()
+    if world == 1:
+        assert (h_dst.cuda() - dst).abs().max().item() == 0.0
+
+    if rank == 0:
+        value = n_global * args.steps / (ms * 1e-3)
+        peak, peak_src = measured_peak()
+        b_alg = B_ALG if deformation == 0.0 else 16.0 + 48.0 + 168.0 / (degree + 1)
+        # the vmult kernel is the only kernel of a step at N=1 (halo pack/exchange are separate launches at N>1),
+        # so its average launch duration is ms / steps, measured with CUDA events on the launching stream
+        achieved = b_alg * (n_global / world) * args.steps / (ms * 1e-3) / 1e9
+        key = "k%d_%s" % (degree, args.mesh)
+        out = {"metric": METRIC if degree == 4 else METRIC.replace("k=4", "k=%d" % degree), "value": value, "unit": "DoFs/s", "n_gpus": world,
+               "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": "SIPG Laplace vmult, FE_DGQ(%d), Gauss(%d), periodic %s box, %d^3 cells, %d DoFs, src uniform(-1,1)"
+                                      % (degree, degree + 1, "Cartesian" if deformation == 0.0 else "sine-deformed (trilinear)", n_sub << refine, n_global),
+                          "l2_policy": "inputs larger than L2 (%.0f MB per vector per GPU)" % (n_local * 8 / 1e6),
+                          "kernel_path": "cartesian" if op.is_cartesian_path else "general", "partition": "p4est-style contiguous Morton ranges, %d rank(s)" % world},
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(key),
+                            "peak_source": peak_src, "algorithmic_bytes_per_dof": b_alg, "dofs_per_launch": n_global // world},
+               "e2e": {"value": n_global * e2e_steps / e2e_s, "unit": "DoFs/s", "h2d_bytes_per_step": n_global * 8, "d2h_bytes_per_step": n_global * 8,
+                       "api": "exadg_b200_vmult_host (pinned host src/dst, copies inside the timed region)"},
+               "gpu_launches": launches, "clocks": clocks}
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline(degree, seconds=args.cpu_seconds)[0]
+        if args.fp64_peak:
+            dfma, dmma = exadg_b200.fp64_peak()
+            out["fp64"] = {"dfma_tflops_measured": dfma, "dmma_tflops_measured": dmma}
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--degree", type=int, default=4)
+    ap.add_argument("--mesh", default="cartesian", choices=["cartesian", "curvilinear"])
+    ap.add_argument("--cells", type=int, default=0, help="cells per direction (default: the workload of the contract)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--fp64-peak", action="store_true", help="also report measured DFMA / DMMA rates")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
