@@ -50,6 +50,38 @@ struct CartArgs
   int64_t n_owned; int n_items; int H; int add;
 };
 
+// ---- TMA (bulk async copy) + mbarrier helpers, sm_90+/sm_100a PTX ----
+__device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t * bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t * bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity)
+{
+  uint32_t done;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+// global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void * smem_dst, const void * gsrc, uint32_t bytes, uint64_t * bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> global (plain store or FP64 add-reduction for vmult_add)
+__device__ __forceinline__ void tma_store_1d(void * gdst, const void * smem_src, uint32_t bytes, bool add)
+{
+  if (add) asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+  else asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 template<int N> struct CartCfg { static constexpr int B = (N >= 4) ? 32 : 64; };
 
 template<int N>
@@ -58,51 +90,89 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
   constexpr int B = CartCfg<N>::B, NT = B * N;
   constexpr int N2 = N * N, N3 = N2 * N;
   constexpr int PS = N2 | 1, CS = N * PS; // odd plane stride: conflict-free plane- and line-wise access
-  extern __shared__ double smem[];
+  extern __shared__ __align__(128) double smem[];
   double * U = smem;                 // [B][CS]  src values, later the staging buffer of the result
   double * Tt = U + B * CS;          // [B][CS]  partial results
   double * GN = Tt + B * CS;         // [B][2][N2] own end derivatives of the current direction
   double * HV = GN + B * 2 * N2;     // [H][N2] end values of out-of-batch neighbours
   double * HG = HV + (size_t)A.H * N2; // [H][N2] end derivatives of out-of-batch neighbours
-  int * nbS = reinterpret_cast<int *>(HG + (size_t)A.H * N2); // [B][6]
+  int2 * hlS = reinterpret_cast<int2 *>(HG + (size_t)A.H * N2); // [H] halo list of this batch
+  int * nbS = reinterpret_cast<int *>(hlS + A.H); // [B][6]
   int * slotS = nbS + B * 6;         // [B][6]
+  uint64_t * bar = reinterpret_cast<uint64_t *>(slotS + B * 6);
 
   const int t = threadIdx.x, lc = t / N, s = t % N;
   const int batch = A.batches ? A.batches[blockIdx.x] : (int)blockIdx.x;
   const int64_t b0 = (int64_t)batch * B;
   const int nvalid = (int)min((int64_t)B, A.n_owned - b0);
   const bool valid = lc < nvalid;
+  // contiguous cell data (odd n: no padding) goes through one TMA bulk copy; 16-byte granularity
+  const uint32_t bytes = (uint32_t)(nvalid * N3 * sizeof(double));
+  const bool use_tma = (PS == N2) && (bytes % 16 == 0);
 
   // ---- phase L: stage the batch, its neighbour table and the traces of out-of-batch neighbours ----
+  if (use_tma) {
+    if (t == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (t == 0) { mbar_expect_tx(bar, bytes); tma_load_1d(U, A.src + b0 * N3, bytes, bar); }
+  }
+  const int cnt = A.halo_cnt[batch];
   for (int i = t; i < B * 6; i += NT) { nbS[i] = (i / 6 < nvalid) ? A.nb[b0 * 6 + i] : -1; slotS[i] = -1; }
-  for (int i = t; i < nvalid * N3; i += NT) {
-    const int c = i / N3, rem = i % N3, k = rem / N2, e = rem % N2;
-    U[c * CS + k * PS + e] = A.src[b0 * N3 + i];
+  for (int i = t; i < cnt; i += NT) hlS[i] = A.halo[(size_t)batch * A.H + i];
+  if (!use_tma) {
+    constexpr int UNR = 8; // independent loads in flight per thread
+    for (int i0 = t; i0 < nvalid * N3; i0 += NT * UNR) {
+      double v[UNR];
+#pragma unroll
+      for (int q = 0; q < UNR; ++q) { const int i = i0 + q * NT; v[q] = (i < nvalid * N3) ? A.src[b0 * N3 + i] : 0.0; }
+#pragma unroll
+      for (int q = 0; q < UNR; ++q) {
+        const int i = i0 + q * NT;
+        if (i < nvalid * N3) { const int c = i / N3, rem = i % N3, k = rem / N2, e = rem % N2; U[c * CS + k * PS + e] = v[q]; }
+      }
+    }
   }
   __syncthreads();
   {
-    const int cnt = A.halo_cnt[batch];
-    const int2 * hl = A.halo + (size_t)batch * A.H;
-    for (int item = t; item < cnt * N2; item += NT) {
-      const int e = item / N2, ab = item % N2, a = ab % N, b = ab / N;
-      const int2 h = hl[e];
-      const int f = h.x & 7, d = f >> 1, sp = (f & 1) ^ 1; // neighbour is entered through its face (d, sp)
-      const double * un = (h.y < A.n_owned) ? A.src + (size_t)h.y * N3 : A.ghost + (size_t)(h.y - A.n_owned) * N3;
-      const int sd = (d == 0) ? 1 : (d == 1 ? N : N2);
-      const int s1 = (d == 0) ? N : 1, s2 = (d == 2) ? N : N2;
-      const double * line = un + a * s1 + b * s2;
-      double g = 0.0, v = 0.0;
+    constexpr int UNR = 5; // 5 items x n loads in flight per thread
+    for (int it0 = t; it0 < cnt * N2; it0 += NT * UNR) {
+      double x[UNR][N]; int sp[UNR];
 #pragma unroll
-      for (int i = 0; i < N; ++i) {
-        const double x = line[i * sd];
-        g = fma(sp ? T.fd[1][i] : T.fd[0][i], x, g);
-        if (i == 0 && !sp) v = x;
-        if (i == N - 1 && sp) v = x;
+      for (int q = 0; q < UNR; ++q) {
+        const int item = it0 + q * NT;
+        sp[q] = 0;
+        if (item < cnt * N2) {
+          const int e = item / N2, ab = item % N2, a = ab % N, b = ab / N;
+          const int2 h = hlS[e];
+          const int f = h.x & 7, d = f >> 1;
+          sp[q] = (f & 1) ^ 1; // neighbour is entered through its face (d, sp)
+          const double * un = (h.y < A.n_owned) ? A.src + (size_t)h.y * N3 : A.ghost + (size_t)(h.y - A.n_owned) * N3;
+          const int sd = (d == 0) ? 1 : (d == 1 ? N : N2);
+          const int s1 = (d == 0) ? N : 1, s2 = (d == 2) ? N : N2;
+          const double * line = un + a * s1 + b * s2;
+#pragma unroll
+          for (int i = 0; i < N; ++i) x[q][i] = line[i * sd];
+        } else {
+#pragma unroll
+          for (int i = 0; i < N; ++i) x[q][i] = 0.0;
+        }
       }
-      HV[e * N2 + ab] = v; HG[e * N2 + ab] = g;
-      if (ab == 0) slotS[(h.x >> 3) * 6 + f] = e;
+#pragma unroll
+      for (int q = 0; q < UNR; ++q) {
+        const int item = it0 + q * NT;
+        if (item < cnt * N2) {
+          const int e = item / N2, ab = item % N2;
+          double g = 0.0;
+#pragma unroll
+          for (int i = 0; i < N; ++i) g = fma(sp[q] ? T.fd[1][i] : T.fd[0][i], x[q][i], g);
+          HV[e * N2 + ab] = sp[q] ? x[q][N - 1] : x[q][0];
+          HG[e * N2 + ab] = g;
+          if (ab == 0) { const int2 h = hlS[e]; slotS[(h.x >> 3) * 6 + (h.x & 7)] = e; }
+        }
+      }
     }
   }
+  if (use_tma) mbar_wait(bar, 0);
   __syncthreads();
 
   double u[N][N], acc[N][N];
@@ -259,6 +329,13 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
         U[lc * CS + s * PS + i + N * r] = y;
       }
   }
+  if (use_tma) {
+    // result batch is contiguous in dst: one TMA bulk store (or FP64 add-reduction for vmult_add)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (t == 0) tma_store_1d(A.dst + b0 * N3, U, bytes, A.add != 0);
+    return;
+  }
   __syncthreads();
   // ---- coalesced store ----
   for (int i = t; i < nvalid * N3; i += NT) {
@@ -368,7 +445,7 @@ size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh)
   }
   P.H = std::max(P.H, 1);
   const int N2 = N * N, PS = N2 | 1, CS = N * PS;
-  P.smem = ((size_t)2 * P.B * CS + (size_t)P.B * 2 * N2 + (size_t)2 * P.H * N2) * sizeof(double) + (size_t)P.B * 12 * sizeof(int);
+  P.smem = ((size_t)2 * P.B * CS + (size_t)P.B * 2 * N2 + (size_t)2 * P.H * N2) * sizeof(double) + (size_t)P.H * sizeof(int2) + (size_t)P.B * 12 * sizeof(int) + 16;
   if (P.smem > 227 * 1024 - 1024) { delete Pp; return 0; } // does not fit: caller falls back to the general kernel
   std::vector<int2> flat((size_t)P.n_batches * P.H, make_int2(0, 0));
   std::vector<int32_t> cnt(P.n_batches);

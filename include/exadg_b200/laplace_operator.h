@@ -1,0 +1,121 @@
+// Header-only C++ shim over the C ABI (include/exadg_b200.h) that mirrors the public surface of
+// ExaDG::OperatorBase / ExaDG::Poisson::LaplaceOperator for the matrix-free DG Laplace path, so that
+// dealii::SolverCG / dealii::PreconditionChebyshev-style templates (which only need vmult and a
+// vector type) and ExaDG's JacobiPreconditioner / MultigridOperator wrappers can call it unchanged.
+//
+//   reference member (I/ = include/exadg/)                                   -> shim
+//   OperatorBase::vmult / vmult_add            I/operators/operator_base.cpp:156-182   -> vmult / vmult_add
+//   OperatorBase::apply / apply_add            operator_base.cpp:264-354               -> apply / apply_add
+//   OperatorBase::vmult_interface_down / _up   operator_base.cpp:184-198               -> same names
+//   OperatorBase::m / n / el                   operator_base.cpp:199-222               -> m / n / el (el throws)
+//   OperatorBase::initialize_dof_vector        operator_base.cpp:232-237               -> initialize_dof_vector
+//   OperatorBase::calculate_diagonal / add_diagonal / calculate_inverse_diagonal
+//                                              operator_base.cpp:249-262, 608-646      -> same names
+//   LaplaceOperator::initialize                I/poisson/spatial_discretization/laplace_operator.cpp:33-51 -> constructors
+//   typedef Number value_type                  laplace_operator.h:248                  -> value_type
+// Errors: the reference throws dealii::ExcMessage via AssertThrow; the shim throws std::runtime_error
+// carrying exadg_b200_last_error().
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+
+#include "../exadg_b200.h"
+
+namespace ExaDG
+{
+namespace B200
+{
+inline void check(int status)
+{
+  if (status != EXADG_B200_OK) throw std::runtime_error(std::string("exadg_b200: ") + exadg_b200_last_error());
+}
+
+// Device vector with the locally owned DoFs (the role of dealii::LinearAlgebra::distributed::Vector<double>;
+// ghost entries live inside the operator).  Movable, not copyable.
+class DeviceVector
+{
+public:
+  DeviceVector() = default;
+  DeviceVector(DeviceVector const &) = delete;
+  DeviceVector & operator=(DeviceVector const &) = delete;
+  DeviceVector(DeviceVector && o) noexcept : ptr(o.ptr), n(o.n) { o.ptr = nullptr; o.n = 0; }
+  DeviceVector & operator=(DeviceVector && o) noexcept { std::swap(ptr, o.ptr); std::swap(n, o.n); return *this; }
+  ~DeviceVector() { if (ptr) exadg_b200_free_dof_vector(ptr); }
+  double * data() { return ptr; }
+  double const * data() const { return ptr; }
+  std::int64_t locally_owned_size() const { return n; }
+
+private:
+  friend class LaplaceOperator;
+  double * ptr = nullptr;
+  std::int64_t n = 0;
+};
+
+class LaplaceOperator
+{
+public:
+  typedef double value_type;
+  typedef DeviceVector VectorType;
+
+  // benchmark / test grids of the reference (periodic box, sine case)
+  explicit LaplaceOperator(exadg_b200_hypercube_desc const & desc) { check(exadg_b200_create_hypercube(&desc, &op)); }
+  // general mesh extracted from dealii::MatrixFree by the reference-side binding
+  explicit LaplaceOperator(exadg_b200_mesh_desc const & desc) { check(exadg_b200_create(&desc, &op)); }
+  LaplaceOperator(LaplaceOperator const &) = delete;
+  LaplaceOperator & operator=(LaplaceOperator const &) = delete;
+  ~LaplaceOperator() { exadg_b200_destroy(op); }
+
+  void vmult(VectorType & dst, VectorType const & src) const { check(exadg_b200_vmult(op, dst.data(), src.data())); }
+  void vmult_add(VectorType & dst, VectorType const & src) const { check(exadg_b200_vmult_add(op, dst.data(), src.data())); }
+  void apply(VectorType & dst, VectorType const & src) const { vmult(dst, src); }
+  void apply_add(VectorType & dst, VectorType const & src) const { vmult_add(dst, src); }
+  void vmult_interface_down(VectorType & dst, VectorType const & src) const { vmult(dst, src); }
+  void vmult_add_interface_up(VectorType & dst, VectorType const & src) const { vmult_add(dst, src); }
+
+  std::int64_t m() const { return n(); }
+  std::int64_t n() const { return exadg_b200_n(op); }
+  double el(unsigned int, unsigned int) const { throw std::runtime_error("Matrix-free does not allow for entry access"); }
+  bool is_empty_locally() const { return exadg_b200_n_cells_owned(op) == 0; }
+  bool operator_is_singular() const { return false; }
+
+  void initialize_dof_vector(VectorType & v) const
+  {
+    VectorType fresh;
+    check(exadg_b200_initialize_dof_vector(op, &fresh.ptr));
+    fresh.n = exadg_b200_local_size(op);
+    v = std::move(fresh);
+  }
+
+  void calculate_diagonal(VectorType & diagonal) const
+  {
+    if (diagonal.locally_owned_size() == 0) initialize_dof_vector(diagonal);
+    check(exadg_b200_calculate_diagonal(op, diagonal.data()));
+  }
+  void add_diagonal(VectorType & diagonal) const { check(exadg_b200_add_diagonal(op, diagonal.data())); }
+  void calculate_inverse_diagonal(VectorType & diagonal) const
+  {
+    if (diagonal.locally_owned_size() == 0) initialize_dof_vector(diagonal);
+    check(exadg_b200_calculate_inverse_diagonal(op, diagonal.data()));
+  }
+
+  // Krylov::KrylovSolver::solve with "cg" (iterative_solvers_dealii_wrapper.h:137-221); returns last_step()
+  unsigned int solve_cg(VectorType & dst, VectorType const & rhs, int preconditioner, exadg_b200_chebyshev * cheb, double abs_tol, double rel_tol,
+                        unsigned int max_iter) const
+  {
+    int n_iter = 0;
+    check(exadg_b200_cg_solve(op, dst.data(), rhs.data(), preconditioner, cheb, abs_tol, rel_tol, (int)max_iter, &n_iter, nullptr));
+    return (unsigned int)n_iter;
+  }
+
+  void synchronize() const { check(exadg_b200_synchronize(op)); }
+  exadg_b200_operator * handle() const { return op; }
+
+private:
+  exadg_b200_operator * op = nullptr;
+};
+
+} // namespace B200
+} // namespace ExaDG
