@@ -44,10 +44,11 @@ struct CartArgs
 {
   const int32_t * nb;        // [owned][6]
   const int2 * halo;         // [n_batches][H] (lc<<3|f, neighbour cell)
-  const int32_t * halo_cnt;  // [n_batches]
+  const int2 * halo_cnt;     // [n_batches] (x/y-face entries, z-face entries)
   const int32_t * batches;   // optional list of batch ids
   const double * src; const double * ghost; double * dst;
   int64_t n_owned; int n_items; int H; int add;
+  int n_sm;
 };
 
 // ---- TMA (bulk async copy) + mbarrier helpers, sm_90+/sm_100a PTX ----
@@ -82,10 +83,16 @@ __device__ __forceinline__ void tma_store_1d(void * gdst, const void * smem_src,
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-template<int N> struct CartCfg { static constexpr int B = (N >= 4) ? 32 : 64; };
+// B cells per CTA, B*N compute threads.  For n = 5 that is 5 warps; warps are bound to the four SM
+// sub-partitions by (warp id % 4), so sub-partition 0 would carry 2 of every 5 warps of every CTA and its
+// FP64 pipe (16 lanes) would cap the SM at 62 %.  The CTA is therefore launched with one spare warp and
+// every other CTA arriving on an SM shifts its compute warps by one (warps 1..5 instead of 0..4), which
+// spreads two resident CTAs as 3,3,2,2 warps over the sub-partitions.  The spare warp exits at once.
+template<int N> struct CartCfg { static constexpr int B = (N >= 4) ? 32 : 64; static constexpr int PAD = ((B * N) % 128 == 0) ? 0 : 32; };
+#define CTA_SYNC() asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory")
 
 template<int N>
-__global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_cartesian_kernel(const __grid_constant__ CartTables<N> T, const CartArgs A)
+__global__ void __launch_bounds__(CartCfg<N>::B * N + CartCfg<N>::PAD, (N == 5) ? 2 : 1) vmult_cartesian_kernel(const __grid_constant__ CartTables<N> T, const CartArgs A)
 {
   constexpr int B = CartCfg<N>::B, NT = B * N;
   constexpr int N2 = N * N, N3 = N2 * N;
@@ -99,9 +106,16 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
   int2 * hlS = reinterpret_cast<int2 *>(HG + (size_t)A.H * N2); // [H] halo list of this batch
   int * nbS = reinterpret_cast<int *>(hlS + A.H); // [B][6]
   int * slotS = nbS + B * 6;         // [B][6]
-  uint64_t * bar = reinterpret_cast<uint64_t *>(slotS + B * 6);
+  uint64_t * bar = reinterpret_cast<uint64_t *>(slotS + B * 6); // [2]: batch data, staged halo cells
 
-  const int t = threadIdx.x, lc = t / N, s = t % N;
+  int t = threadIdx.x;
+  if (CartCfg<N>::PAD) {
+    // CTAs are dispatched round-robin over the SMs and retire roughly in launch order, so the two CTAs
+    // resident on an SM are bid and bid +- n_sm: alternate the warp shift with (bid / n_sm)
+    t -= ((blockIdx.x / A.n_sm) & 1) * 32;
+    if (t < 0 || t >= NT) return; // spare warp
+  }
+  const int lc = t / N, s = t % N;
   const int batch = A.batches ? A.batches[blockIdx.x] : (int)blockIdx.x;
   const int64_t b0 = (int64_t)batch * B;
   const int nvalid = (int)min((int64_t)B, A.n_owned - b0);
@@ -111,14 +125,21 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
   const bool use_tma = (PS == N2) && (bytes % 16 == 0);
 
   // ---- phase L: stage the batch, its neighbour table and the traces of out-of-batch neighbours ----
-  if (use_tma) {
-    if (t == 0) mbar_init(bar, 1);
-    __syncthreads();
-    if (t == 0) { mbar_expect_tx(bar, bytes); tma_load_1d(U, A.src + b0 * N3, bytes, bar); }
-  }
-  const int cnt = A.halo_cnt[batch];
+  // Every out-of-batch neighbour contributes the end value / end derivative of all n^2 lines normal to the
+  // shared face, i.e. its whole cell is needed once.  The cells are fetched by TMA bulk copies into the (still
+  // unused) Tt region and reduced to traces from shared memory; the copies for the z faces are issued before
+  // the x/y sweeps and consumed after them, so their latency hides behind the FP64 work.
+  constexpr int SLOT = (N3 + 3) & ~1;            // doubles per staged cell: 8 B front pad for odd cells, 16 B granularity
+  constexpr int CAP_L = (B * CS) / SLOT;          // staged cells of the overlapped (late) round: Tt only
+  constexpr int CAP_E = (B * CS + B * 2 * N2) / SLOT; // early rounds may spill into the GN region behind Tt
+  double * ST = Tt;
+  if (t == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
+  CTA_SYNC();
+  if (use_tma && t == 0) { mbar_expect_tx(bar, bytes); tma_load_1d(U, A.src + b0 * N3, bytes, bar); }
+  const int2 hc = A.halo_cnt[batch];              // x = number of x/y-face entries, y = number of z-face entries (sorted that way)
+  const int cnt = hc.x + hc.y;
   for (int i = t; i < B * 6; i += NT) { nbS[i] = (i / 6 < nvalid) ? A.nb[b0 * 6 + i] : -1; slotS[i] = -1; }
-  for (int i = t; i < cnt; i += NT) hlS[i] = A.halo[(size_t)batch * A.H + i];
+  for (int i = t; i < cnt; i += NT) { const int2 h = A.halo[(size_t)batch * A.H + i]; hlS[i] = h; }
   if (!use_tma) {
     constexpr int UNR = 8; // independent loads in flight per thread
     for (int i0 = t; i0 < nvalid * N3; i0 += NT * UNR) {
@@ -132,48 +153,61 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
       }
     }
   }
-  __syncthreads();
-  {
-    constexpr int UNR = 5; // 5 items x n loads in flight per thread
-    for (int it0 = t; it0 < cnt * N2; it0 += NT * UNR) {
-      double x[UNR][N]; int sp[UNR];
-#pragma unroll
-      for (int q = 0; q < UNR; ++q) {
-        const int item = it0 + q * NT;
-        sp[q] = 0;
-        if (item < cnt * N2) {
-          const int e = item / N2, ab = item % N2, a = ab % N, b = ab / N;
-          const int2 h = hlS[e];
-          const int f = h.x & 7, d = f >> 1;
-          sp[q] = (f & 1) ^ 1; // neighbour is entered through its face (d, sp)
-          const double * un = (h.y < A.n_owned) ? A.src + (size_t)h.y * N3 : A.ghost + (size_t)(h.y - A.n_owned) * N3;
-          const int sd = (d == 0) ? 1 : (d == 1 ? N : N2);
-          const int s1 = (d == 0) ? N : 1, s2 = (d == 2) ? N : N2;
-          const double * line = un + a * s1 + b * s2;
-#pragma unroll
-          for (int i = 0; i < N; ++i) x[q][i] = line[i * sd];
-        } else {
-#pragma unroll
-          for (int i = 0; i < N; ++i) x[q][i] = 0.0;
-        }
+  CTA_SYNC(); // hlS, nbS visible
+  uint32_t hpar = 0; // parity of the halo barrier
+  // issue the bulk copies of entries [e0, e0 + n) into the staging slots (warp 0; one copy per lane and pass)
+  auto stage_issue = [&](int e0, int n) {
+    if (t < 32) {
+      for (int q = t; q < n; q += 32) {
+        const int2 h = hlS[e0 + q];
+        const double * cellp = (h.y < A.n_owned) ? A.src + (size_t)h.y * N3 : A.ghost + (size_t)(h.y - A.n_owned) * N3;
+        const uint32_t odd = (uint32_t)((reinterpret_cast<uintptr_t>(cellp) >> 3) & 1); // only 8-byte aligned: start 8 B earlier
+        const uint32_t nbytes = (uint32_t)((N3 + odd + ((N3 + odd) & 1)) * sizeof(double));
+        asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar + 1)), "r"(nbytes) : "memory");
+        tma_load_1d(ST + q * SLOT, cellp - odd, nbytes, bar + 1);
       }
-#pragma unroll
-      for (int q = 0; q < UNR; ++q) {
-        const int item = it0 + q * NT;
-        if (item < cnt * N2) {
-          const int e = item / N2, ab = item % N2;
-          double g = 0.0;
-#pragma unroll
-          for (int i = 0; i < N; ++i) g = fma(sp[q] ? T.fd[1][i] : T.fd[0][i], x[q][i], g);
-          HV[e * N2 + ab] = sp[q] ? x[q][N - 1] : x[q][0];
-          HG[e * N2 + ab] = g;
-          if (ab == 0) { const int2 h = hlS[e]; slotS[(h.x >> 3) * 6 + (h.x & 7)] = e; }
-        }
-      }
+      __syncwarp();
+      // the single arrival comes last: the phase cannot complete before every lane has added its byte count
+      if (t == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar + 1)) : "memory");
     }
+  };
+  // reduce staged cells to traces: item = (entry, line); line end value and end derivative
+  auto stage_reduce = [&](int e0, int n) {
+    for (int item = t; item < n * N2; item += NT) {
+      const int q = item / N2, ab = item % N2, a = ab % N, bq = ab / N;
+      const int2 h = hlS[e0 + q];
+      const int f = h.x & 7, d = f >> 1, sp = (f & 1) ^ 1; // the neighbour is entered through its face (d, sp)
+      const double * cellp = (h.y < A.n_owned) ? A.src + (size_t)h.y * N3 : A.ghost + (size_t)(h.y - A.n_owned) * N3;
+      const int odd = (int)((reinterpret_cast<uintptr_t>(cellp) >> 3) & 1);
+      const int sd = (d == 0) ? 1 : (d == 1 ? N : N2);
+      const int s1 = (d == 0) ? N : 1, s2 = (d == 2) ? N : N2;
+      const double * line = ST + q * SLOT + odd + a * s1 + bq * s2;
+      const double * fdp = sp ? T.fd[1] : T.fd[0];
+      double x[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) x[i] = line[i * sd];
+      double g = fdp[0] * x[0];
+#pragma unroll
+      for (int i = 1; i < N; ++i) g = fma(fdp[i], x[i], g);
+      HV[(e0 + q) * N2 + ab] = sp ? x[N - 1] : x[0];
+      HG[(e0 + q) * N2 + ab] = g;
+      if (ab == 0) slotS[(h.x >> 3) * 6 + f] = e0 + q;
+    }
+  };
+  // x/y-face entries (and z-face entries beyond one round) are consumed right away
+  const int z_first = hc.x;                                   // first z entry
+  const int z_now = (hc.y > CAP_L) ? hc.y - CAP_L : 0;        // z entries that do not fit the overlapped round
+  for (int e0 = 0; e0 < hc.x + z_now; e0 += CAP_E) {
+    const int n = min(CAP_E, hc.x + z_now - e0);
+    stage_issue(e0, n);
+    mbar_wait(bar + 1, hpar); hpar ^= 1;
+    stage_reduce(e0, n);
+    CTA_SYNC(); // staging slots are reused
   }
+  const int z_late0 = z_first + z_now, z_late = cnt - z_late0; // overlapped round
+  if (z_late > 0) stage_issue(z_late0, z_late);
   if (use_tma) mbar_wait(bar, 0);
-  __syncthreads();
+  CTA_SYNC();
 
   double u[N][N], acc[N][N];
   if (valid) {
@@ -187,19 +221,21 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
 #pragma unroll
   for (int d = 0; d < 2; ++d) {
     if (valid) {
+      // end derivatives of the n lines of this plane (line l: d=0 -> row j=l, d=1 -> column i=l); 2n independent chains
+      double g0[N], g1[N];
 #pragma unroll
-      for (int l = 0; l < N; ++l) { // line l: d=0 -> row j=l (runs over i); d=1 -> column i=l (runs over j)
-        double g0 = 0.0, g1 = 0.0;
+      for (int l = 0; l < N; ++l) { const double x = (d == 0) ? u[l][0] : u[0][l]; g0[l] = T.fd[0][0] * x; g1[l] = T.fd[1][0] * x; }
 #pragma unroll
-        for (int m = 0; m < N; ++m) {
+      for (int m = 1; m < N; ++m)
+#pragma unroll
+        for (int l = 0; l < N; ++l) {
           const double x = (d == 0) ? u[l][m] : u[m][l];
-          g0 = fma(T.fd[0][m], x, g0); g1 = fma(T.fd[1][m], x, g1);
+          g0[l] = fma(T.fd[0][m], x, g0[l]); g1[l] = fma(T.fd[1][m], x, g1[l]);
         }
-        GN[(lc * 2 + 0) * N2 + l + N * s] = g0;
-        GN[(lc * 2 + 1) * N2 + l + N * s] = g1;
-      }
+#pragma unroll
+      for (int l = 0; l < N; ++l) { GN[(lc * 2 + 0) * N2 + l + N * s] = g0[l]; GN[(lc * 2 + 1) * N2 + l + N * s] = g1[l]; }
     }
-    __syncthreads();
+    CTA_SYNC();
     if (valid) {
 #pragma unroll
       for (int side = 0; side < 2; ++side) {
@@ -208,36 +244,49 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
         const bool inb = (nbl >= 0 && nbl < B);
         const int slot = slotS[lc * 6 + f];
         const double hs = side ? 0.5 : -0.5; // 1/2 sigma_s
+        double vn[N], tt[N];
 #pragma unroll
         for (int l = 0; l < N; ++l) {
-          double vn, gn;
+          double gn;
           if (inb) {
             const int endn = side ? 0 : N - 1; // neighbour's end node facing us
-            vn = (d == 0) ? U[nbl * CS + s * PS + endn + N * l] : U[nbl * CS + s * PS + l + N * endn];
+            vn[l] = (d == 0) ? U[nbl * CS + s * PS + endn + N * l] : U[nbl * CS + s * PS + l + N * endn];
             gn = GN[(nbl * 2 + (side ^ 1)) * N2 + l + N * s];
           } else {
-            vn = HV[slot * N2 + l + N * s]; gn = HG[slot * N2 + l + N * s];
+            vn[l] = HV[slot * N2 + l + N * s]; gn = HG[slot * N2 + l + N * s];
           }
-          const double tt = fma(hs, gn, T.tau_hat[d] * vn);
-#pragma unroll
-          for (int m = 0; m < N; ++m) {
-            double & y = (d == 0) ? acc[l][m] : acc[m][l];
-            y = fma(T.P[d][side][m], vn, y);
-            y = fma(T.Q[d][side][m], tt, y);
-          }
+          tt[l] = fma(hs, gn, T.tau_hat[d] * vn[l]);
         }
+#pragma unroll
+        for (int m = 0; m < N; ++m)
+#pragma unroll
+          for (int l = 0; l < N; ++l) {
+            if (d == 0) acc[l][m] = fma(T.P[d][side][m], vn[l], acc[l][m]); else acc[m][l] = fma(T.P[d][side][m], vn[l], acc[m][l]);
+          }
+#pragma unroll
+        for (int m = 0; m < N; ++m)
+#pragma unroll
+          for (int l = 0; l < N; ++l) {
+            if (d == 0) acc[l][m] = fma(T.Q[d][side][m], tt[l], acc[l][m]); else acc[m][l] = fma(T.Q[d][side][m], tt[l], acc[m][l]);
+          }
       }
+      // G u: column index outermost so that consecutive DFMAs hit 25 independent accumulators
 #pragma unroll
-      for (int l = 0; l < N; ++l)
+      for (int c = 0; c < N; ++c)
 #pragma unroll
-        for (int r = 0; r < N; ++r) {
-          double y = (d == 0) ? acc[l][r] : acc[r][l];
+        for (int l = 0; l < N; ++l)
 #pragma unroll
-          for (int c = 0; c < N; ++c) y = fma(T.G[d][r * N + c], (d == 0) ? u[l][c] : u[c][l], y);
-          if (d == 0) acc[l][r] = y; else acc[r][l] = y;
-        }
+          for (int r = 0; r < N; ++r) {
+            if (d == 0) acc[l][r] = fma(T.G[d][r * N + c], u[l][c], acc[l][r]);
+            else acc[r][l] = fma(T.G[d][r * N + c], u[c][l], acc[r][l]);
+          }
     }
-    __syncthreads(); // GN is reused by the next direction
+    CTA_SYNC(); // GN is reused by the next direction
+  }
+  if (z_late > 0) {
+    mbar_wait(bar + 1, hpar);
+    stage_reduce(z_late0, z_late);
+    CTA_SYNC(); // staging (= Tt) is free again
   }
   if (valid) {
 #pragma unroll
@@ -249,61 +298,76 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
   // ---- z sweep: this thread owns the n lines (i, j = s) ----
   if (valid) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      double g0 = 0.0, g1 = 0.0;
+    for (int i = 0; i < N; ++i)
 #pragma unroll
-      for (int k = 0; k < N; ++k) {
-        const double x = U[lc * CS + k * PS + i + N * s];
-        u[i][k] = x; // reuse the plane registers: u[i][k] = value of line i at height k
-        g0 = fma(T.fd[0][k], x, g0); g1 = fma(T.fd[1][k], x, g1);
-      }
-      GN[(lc * 2 + 0) * N2 + i + N * s] = g0;
-      GN[(lc * 2 + 1) * N2 + i + N * s] = g1;
-    }
+      for (int k = 0; k < N; ++k) u[i][k] = U[lc * CS + k * PS + i + N * s]; // reuse the plane registers: u[i][k] = line i at height k
+    double g0[N], g1[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { g0[i] = T.fd[0][0] * u[i][0]; g1[i] = T.fd[1][0] * u[i][0]; }
+#pragma unroll
+    for (int k = 1; k < N; ++k)
+#pragma unroll
+      for (int i = 0; i < N; ++i) { g0[i] = fma(T.fd[0][k], u[i][k], g0[i]); g1[i] = fma(T.fd[1][k], u[i][k], g1[i]); }
+#pragma unroll
+    for (int i = 0; i < N; ++i) { GN[(lc * 2 + 0) * N2 + i + N * s] = g0[i]; GN[(lc * 2 + 1) * N2 + i + N * s] = g1[i]; }
   }
-  __syncthreads(); // Tt planes and z traces visible
+  CTA_SYNC(); // Tt planes and z traces visible
   if (valid) {
-    int nbl[2], slot[2]; bool inb[2];
+    // all five lines (i, j = s) at once: acc[i][k] = partial result, u[i][k] = src values of the line
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int k = 0; k < N; ++k) acc[i][k] = Tt[lc * CS + k * PS + i + N * s];
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
-      nbl[side] = nbS[lc * 6 + 4 + side] - (int)b0;
-      inb[side] = (nbl[side] >= 0 && nbl[side] < B);
-      slot[side] = slotS[lc * 6 + 4 + side];
-    }
+      const int nbl = nbS[lc * 6 + 4 + side] - (int)b0;
+      const bool inb = (nbl >= 0 && nbl < B);
+      const int slot = slotS[lc * 6 + 4 + side];
+      double vn[N], tt[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      double w[N];
-#pragma unroll
-      for (int k = 0; k < N; ++k) w[k] = Tt[lc * CS + k * PS + i + N * s];
-#pragma unroll
-      for (int side = 0; side < 2; ++side) {
-        double vn, gn;
-        if (inb[side]) {
+      for (int i = 0; i < N; ++i) {
+        double gn;
+        if (inb) {
           const int endn = side ? 0 : N - 1;
-          vn = U[nbl[side] * CS + endn * PS + i + N * s];
-          gn = GN[(nbl[side] * 2 + (side ^ 1)) * N2 + i + N * s];
+          vn[i] = U[nbl * CS + endn * PS + i + N * s];
+          gn = GN[(nbl * 2 + (side ^ 1)) * N2 + i + N * s];
         } else {
-          vn = HV[slot[side] * N2 + i + N * s]; gn = HG[slot[side] * N2 + i + N * s];
+          vn[i] = HV[slot * N2 + i + N * s]; gn = HG[slot * N2 + i + N * s];
         }
-        const double tt = fma(side ? 0.5 : -0.5, gn, T.tau_hat[2] * vn);
-#pragma unroll
-        for (int k = 0; k < N; ++k) { w[k] = fma(T.P[2][side][k], vn, w[k]); w[k] = fma(T.Q[2][side][k], tt, w[k]); }
+        tt[i] = fma(side ? 0.5 : -0.5, gn, T.tau_hat[2] * vn[i]);
       }
 #pragma unroll
-      for (int r = 0; r < N; ++r)
+      for (int k = 0; k < N; ++k)
 #pragma unroll
-        for (int c = 0; c < N; ++c) w[r] = fma(T.G[2][r * N + c], u[i][c], w[r]);
-      // mass matrix along z, in place (this thread owns the whole line)
+        for (int i = 0; i < N; ++i) acc[i][k] = fma(T.P[2][side][k], vn[i], acc[i][k]);
 #pragma unroll
-      for (int r = 0; r < N; ++r) {
-        double y = 0.0;
+      for (int k = 0; k < N; ++k)
 #pragma unroll
-        for (int c = 0; c < N; ++c) y = fma(T.M[r * N + c], w[c], y);
-        Tt[lc * CS + r * PS + i + N * s] = y;
-      }
+        for (int i = 0; i < N; ++i) acc[i][k] = fma(T.Q[2][side][k], tt[i], acc[i][k]);
     }
+#pragma unroll
+    for (int c = 0; c < N; ++c)
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int r = 0; r < N; ++r) acc[i][r] = fma(T.G[2][r * N + c], u[i][c], acc[i][r]);
+    // mass matrix along z (this thread owns the whole lines): u <- M acc
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int r = 0; r < N; ++r) u[i][r] = T.M[r * N] * acc[i][0];
+#pragma unroll
+    for (int c = 1; c < N; ++c)
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int r = 0; r < N; ++r) u[i][r] = fma(T.M[r * N + c], acc[i][c], u[i][r]);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int r = 0; r < N; ++r) Tt[lc * CS + r * PS + i + N * s] = u[i][r];
   }
-  __syncthreads();
+  CTA_SYNC();
   // ---- mass matrices along x and y on the register plane, staged into U ----
   if (valid) {
 #pragma unroll
@@ -313,30 +377,36 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
 #pragma unroll
     for (int j = 0; j < N; ++j)
 #pragma unroll
-      for (int r = 0; r < N; ++r) {
-        double y = 0.0;
+      for (int r = 0; r < N; ++r) acc[j][r] = T.M[r * N] * u[j][0];
 #pragma unroll
-        for (int c = 0; c < N; ++c) y = fma(T.M[r * N + c], u[j][c], y);
-        acc[j][r] = y;
-      }
+    for (int c = 1; c < N; ++c)
 #pragma unroll
-    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j)
 #pragma unroll
-      for (int r = 0; r < N; ++r) {
-        double y = 0.0;
+        for (int r = 0; r < N; ++r) acc[j][r] = fma(T.M[r * N + c], u[j][c], acc[j][r]);
 #pragma unroll
-        for (int c = 0; c < N; ++c) y = fma(T.M[r * N + c], acc[c][i], y);
-        U[lc * CS + s * PS + i + N * r] = y;
-      }
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+      for (int i = 0; i < N; ++i) u[r][i] = T.M[r * N] * acc[0][i];
+#pragma unroll
+    for (int c = 1; c < N; ++c)
+#pragma unroll
+      for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int i = 0; i < N; ++i) u[r][i] = fma(T.M[r * N + c], acc[c][i], u[r][i]);
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+      for (int i = 0; i < N; ++i) U[lc * CS + s * PS + i + N * r] = u[r][i];
   }
   if (use_tma) {
     // result batch is contiguous in dst: one TMA bulk store (or FP64 add-reduction for vmult_add)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
+    CTA_SYNC();
     if (t == 0) tma_store_1d(A.dst + b0 * N3, U, bytes, A.add != 0);
     return;
   }
-  __syncthreads();
+  CTA_SYNC();
   // ---- coalesced store ----
   for (int i = t; i < nvalid * N3; i += NT) {
     const int c = i / N3, rem = i % N3, k = rem / N2, e = rem % N2;
@@ -348,7 +418,7 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
 struct CartPlan
 {
   int n = 0, B = 0, H = 0, n_batches = 0;
-  int2 * d_halo = nullptr; int32_t * d_cnt = nullptr;
+  int2 * d_halo = nullptr; int2 * d_cnt = nullptr; int n_sm = 148;
   int32_t * d_interior = nullptr, * d_boundary = nullptr; int n_interior = 0, n_boundary = 0;
   size_t smem = 0;
   std::vector<char> tables; // CartTables<n> of this operator (depends on h and tau)
@@ -400,11 +470,11 @@ void launch_n(const DeviceOperator & op, const CartPlan & plan, double * dst, co
   if (!configured) { CUDA_CHECK(cudaFuncSetAttribute(vmult_cartesian_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)); configured = true; }
   CartArgs A;
   A.nb = op.nb; A.halo = plan.d_halo; A.halo_cnt = plan.d_cnt; A.src = src; A.ghost = op.ghost; A.dst = dst;
-  A.n_owned = op.n_owned; A.H = plan.H; A.add = add ? 1 : 0;
+  A.n_owned = op.n_owned; A.H = plan.H; A.add = add ? 1 : 0; A.n_sm = plan.n_sm;
   A.batches = which == 0 ? nullptr : (which == 1 ? plan.d_interior : plan.d_boundary);
   A.n_items = which == 0 ? plan.n_batches : (which == 1 ? plan.n_interior : plan.n_boundary);
   if (A.n_items == 0) return;
-  vmult_cartesian_kernel<N><<<A.n_items, B * N, plan.smem, stream>>>(T, A);
+  vmult_cartesian_kernel<N><<<A.n_items, B * N + CartCfg<N>::PAD, plan.smem, stream>>>(T, A);
   CUDA_CHECK(cudaGetLastError());
 }
 } // namespace
@@ -445,15 +515,22 @@ size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh)
   }
   P.H = std::max(P.H, 1);
   const int N2 = N * N, PS = N2 | 1, CS = N * PS;
-  P.smem = ((size_t)2 * P.B * CS + (size_t)P.B * 2 * N2 + (size_t)2 * P.H * N2) * sizeof(double) + (size_t)P.H * sizeof(int2) + (size_t)P.B * 12 * sizeof(int) + 16;
+  P.smem = ((size_t)2 * P.B * CS + (size_t)P.B * 2 * N2 + (size_t)2 * P.H * N2) * sizeof(double) + (size_t)P.H * sizeof(int2) + (size_t)P.B * 12 * sizeof(int) + 32;
   if (P.smem > 227 * 1024 - 1024) { delete Pp; return 0; } // does not fit: caller falls back to the general kernel
   std::vector<int2> flat((size_t)P.n_batches * P.H, make_int2(0, 0));
-  std::vector<int32_t> cnt(P.n_batches);
-  for (int b = 0; b < P.n_batches; ++b) { cnt[b] = (int32_t)lists[b].size(); std::copy(lists[b].begin(), lists[b].end(), flat.begin() + (size_t)b * P.H); }
+  std::vector<int2> cnt(P.n_batches);
+  for (int b = 0; b < P.n_batches; ++b) {
+    std::stable_sort(lists[b].begin(), lists[b].end(), [](const int2 & x, const int2 & y) { return ((x.x & 7) >= 4) < ((y.x & 7) >= 4); });
+    int nz = 0;
+    for (auto & e : lists[b]) nz += ((e.x & 7) >= 4);
+    cnt[b] = make_int2((int)lists[b].size() - nz, nz);
+    std::copy(lists[b].begin(), lists[b].end(), flat.begin() + (size_t)b * P.H);
+  }
   CUDA_CHECK(cudaMalloc(&P.d_halo, flat.size() * sizeof(int2)));
   CUDA_CHECK(cudaMemcpy(P.d_halo, flat.data(), flat.size() * sizeof(int2), cudaMemcpyHostToDevice));
-  CUDA_CHECK(cudaMalloc(&P.d_cnt, cnt.size() * sizeof(int32_t)));
-  CUDA_CHECK(cudaMemcpy(P.d_cnt, cnt.data(), cnt.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&P.n_sm, cudaDevAttrMultiProcessorCount, dev); if (P.n_sm < 1) P.n_sm = 148; }
+  CUDA_CHECK(cudaMalloc(&P.d_cnt, cnt.size() * sizeof(int2)));
+  CUDA_CHECK(cudaMemcpy(P.d_cnt, cnt.data(), cnt.size() * sizeof(int2), cudaMemcpyHostToDevice));
   P.n_interior = (int)interior.size(); P.n_boundary = (int)boundary.size();
   if (mesh.world > 1) {
     if (P.n_interior) { CUDA_CHECK(cudaMalloc(&P.d_interior, interior.size() * 4)); CUDA_CHECK(cudaMemcpy(P.d_interior, interior.data(), interior.size() * 4, cudaMemcpyHostToDevice)); }
