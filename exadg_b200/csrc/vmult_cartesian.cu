@@ -103,23 +103,54 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N + CartCfg<N>::PAD, (N == 5) 
   double * GN = Tt + B * CS;         // [B][2][N2] own end derivatives of the current direction
   double * HV = GN + B * 2 * N2;     // [H][N2] end values of out-of-batch neighbours
   double * HG = HV + (size_t)A.H * N2; // [H][N2] end derivatives of out-of-batch neighbours
-  int2 * hlS = reinterpret_cast<int2 *>(HG + (size_t)A.H * N2); // [H] halo list of this batch
-  int * nbS = reinterpret_cast<int *>(hlS + A.H); // [B][6]
-  int * slotS = nbS + B * 6;         // [B][6]
-  uint64_t * bar = reinterpret_cast<uint64_t *>(slotS + B * 6); // [2]: batch data, staged halo cells
+  int2 * hlS2 = reinterpret_cast<int2 *>(HG + (size_t)A.H * N2); // [2][H] halo lists (current batch / prefetched next batch)
+  int * nbS2 = reinterpret_cast<int *>(hlS2 + 2 * A.H);          // [2][B][6] neighbour tables
+  int * slotS = nbS2 + 2 * B * 6;                                // [B][6]
+  int2 * cntS = reinterpret_cast<int2 *>(slotS + B * 6);         // [2]
+  uint64_t * bar = reinterpret_cast<uint64_t *>(cntS + 2);       // [2]: batch data, staged halo cells
 
   int t = threadIdx.x;
   if (CartCfg<N>::PAD) {
-    // CTAs are dispatched round-robin over the SMs and retire roughly in launch order, so the two CTAs
-    // resident on an SM are bid and bid +- n_sm: alternate the warp shift with (bid / n_sm)
+    // CTAs are dispatched round-robin over the SMs, so the two CTAs resident on an SM are bid and bid + n_sm:
+    // alternate the warp shift with (bid / n_sm)
     t -= ((blockIdx.x / A.n_sm) & 1) * 32;
     if (t < 0 || t >= NT) return; // spare warp
   }
   const int lc = t / N, s = t % N;
-  const int batch = A.batches ? A.batches[blockIdx.x] : (int)blockIdx.x;
+  constexpr int SLOT = (N3 + 3) & ~1;            // doubles per staged cell: 8 B front pad for odd cells, 16 B granularity
+  constexpr int CAP_L = (B * CS) / SLOT;          // staged cells of the overlapped (late) round: Tt only
+  constexpr int CAP_E = (B * CS + B * 2 * N2) / SLOT; // early rounds may spill into the GN region behind Tt
+  double * ST = Tt;
+  uint32_t hpar = 0, upar = 0; // parities of the two mbarriers
+  if (t == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
+
+  // Persistent CTA: batches it, it + gridDim.x, ...  The neighbour table and halo list of the NEXT batch are
+  // fetched into registers while the current batch is computed and parked in the second shared-memory slot at
+  // the end of the iteration, so that every batch starts with all its bulk copies issued at once (one memory
+  // latency per batch instead of a chain of three dependent ones).
+  auto batch_of = [&](int it) { return A.batches ? A.batches[it] : it; };
+  int cur = 0;
+  {
+    const int it0 = blockIdx.x;
+    if (it0 < A.n_items) {
+      const int bt = batch_of(it0);
+      const int64_t c0 = (int64_t)bt * B;
+      const int nv = (int)min((int64_t)B, A.n_owned - c0);
+      const int2 hc0 = A.halo_cnt[bt];
+      if (t == 0) cntS[0] = hc0;
+      for (int i = t; i < B * 6; i += NT) nbS2[i] = (i / 6 < nv) ? A.nb[c0 * 6 + i] : -1;
+      for (int i = t; i < hc0.x + hc0.y; i += NT) hlS2[i] = A.halo[(size_t)bt * A.H + i];
+    }
+  }
+  CTA_SYNC();
+
+  for (int it = blockIdx.x; it < A.n_items; it += gridDim.x, cur ^= 1) {
+  const int batch = batch_of(it);
   const int64_t b0 = (int64_t)batch * B;
   const int nvalid = (int)min((int64_t)B, A.n_owned - b0);
   const bool valid = lc < nvalid;
+  int2 * hlS = hlS2 + cur * A.H;
+  int * nbS = nbS2 + cur * B * 6;
   // contiguous cell data (odd n: no padding) goes through one TMA bulk copy; 16-byte granularity
   const uint32_t bytes = (uint32_t)(nvalid * N3 * sizeof(double));
   const bool use_tma = (PS == N2) && (bytes % 16 == 0);
@@ -129,17 +160,12 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N + CartCfg<N>::PAD, (N == 5) 
   // shared face, i.e. its whole cell is needed once.  The cells are fetched by TMA bulk copies into the (still
   // unused) Tt region and reduced to traces from shared memory; the copies for the z faces are issued before
   // the x/y sweeps and consumed after them, so their latency hides behind the FP64 work.
-  constexpr int SLOT = (N3 + 3) & ~1;            // doubles per staged cell: 8 B front pad for odd cells, 16 B granularity
-  constexpr int CAP_L = (B * CS) / SLOT;          // staged cells of the overlapped (late) round: Tt only
-  constexpr int CAP_E = (B * CS + B * 2 * N2) / SLOT; // early rounds may spill into the GN region behind Tt
-  double * ST = Tt;
-  if (t == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
-  CTA_SYNC();
+  if (t == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // earlier generic accesses of U / staging before the bulk copies
   if (use_tma && t == 0) { mbar_expect_tx(bar, bytes); tma_load_1d(U, A.src + b0 * N3, bytes, bar); }
-  const int2 hc = A.halo_cnt[batch];              // x = number of x/y-face entries, y = number of z-face entries (sorted that way)
+  const int2 hc = cntS[cur];                      // x = number of x/y-face entries, y = number of z-face entries (sorted that way)
   const int cnt = hc.x + hc.y;
-  for (int i = t; i < B * 6; i += NT) { nbS[i] = (i / 6 < nvalid) ? A.nb[b0 * 6 + i] : -1; slotS[i] = -1; }
-  for (int i = t; i < cnt; i += NT) { const int2 h = A.halo[(size_t)batch * A.H + i]; hlS[i] = h; }
+  for (int i = t; i < B * 6; i += NT) slotS[i] = -1;
+  CTA_SYNC(); // slot table reset before any trace is registered
   if (!use_tma) {
     constexpr int UNR = 8; // independent loads in flight per thread
     for (int i0 = t; i0 < nvalid * N3; i0 += NT * UNR) {
@@ -153,8 +179,6 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N + CartCfg<N>::PAD, (N == 5) 
       }
     }
   }
-  CTA_SYNC(); // hlS, nbS visible
-  uint32_t hpar = 0; // parity of the halo barrier
   // issue the bulk copies of entries [e0, e0 + n) into the staging slots (warp 0; one copy per lane and pass)
   auto stage_issue = [&](int e0, int n) {
     if (t < 32) {
@@ -197,16 +221,33 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N + CartCfg<N>::PAD, (N == 5) 
   // x/y-face entries (and z-face entries beyond one round) are consumed right away
   const int z_first = hc.x;                                   // first z entry
   const int z_now = (hc.y > CAP_L) ? hc.y - CAP_L : 0;        // z entries that do not fit the overlapped round
+  // prefetch of the next batch's tables (registers now, shared memory at the end of the iteration)
+  const int itn = it + gridDim.x;
+  const bool has_next = itn < A.n_items;
+  int pre_nb[(B * 6 + NT - 1) / NT]; int2 pre_hl = make_int2(0, 0); int2 pre_cnt = make_int2(0, 0);
+  auto prefetch_next = [&]() {
+    if (!has_next) return;
+    const int bn = batch_of(itn);
+    const int64_t c0 = (int64_t)bn * B;
+    const int nv = (int)min((int64_t)B, A.n_owned - c0);
+#pragma unroll
+    for (int q = 0; q < (B * 6 + NT - 1) / NT; ++q) { const int i = t + q * NT; pre_nb[q] = (i < B * 6 && i / 6 < nv) ? A.nb[c0 * 6 + i] : -1; }
+    pre_cnt = A.halo_cnt[bn];
+    if (t < A.H) pre_hl = A.halo[(size_t)bn * A.H + t];
+  };
+  bool prefetched = false;
   for (int e0 = 0; e0 < hc.x + z_now; e0 += CAP_E) {
     const int n = min(CAP_E, hc.x + z_now - e0);
     stage_issue(e0, n);
+    if (!prefetched) { prefetch_next(); prefetched = true; }
     mbar_wait(bar + 1, hpar); hpar ^= 1;
     stage_reduce(e0, n);
     CTA_SYNC(); // staging slots are reused
   }
   const int z_late0 = z_first + z_now, z_late = cnt - z_late0; // overlapped round
   if (z_late > 0) stage_issue(z_late0, z_late);
-  if (use_tma) mbar_wait(bar, 0);
+  if (!prefetched) { prefetch_next(); prefetched = true; }
+  if (use_tma) { mbar_wait(bar, upar); upar ^= 1; }
   CTA_SYNC();
 
   double u[N][N], acc[N][N];
@@ -284,7 +325,7 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N + CartCfg<N>::PAD, (N == 5) 
     CTA_SYNC(); // GN is reused by the next direction
   }
   if (z_late > 0) {
-    mbar_wait(bar + 1, hpar);
+    mbar_wait(bar + 1, hpar); hpar ^= 1;
     stage_reduce(z_late0, z_late);
     CTA_SYNC(); // staging (= Tt) is free again
   }
@@ -399,20 +440,30 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N + CartCfg<N>::PAD, (N == 5) 
 #pragma unroll
       for (int i = 0; i < N; ++i) U[lc * CS + s * PS + i + N * r] = u[r][i];
   }
+  // park the prefetched tables of the next batch
+  if (has_next) {
+    int * nbN = nbS2 + (cur ^ 1) * B * 6;
+#pragma unroll
+    for (int q = 0; q < (B * 6 + NT - 1) / NT; ++q) { const int i = t + q * NT; if (i < B * 6) nbN[i] = pre_nb[q]; }
+    if (t < A.H) hlS2[(cur ^ 1) * A.H + t] = pre_hl;
+    if (t == 0) cntS[cur ^ 1] = pre_cnt;
+  }
   if (use_tma) {
     // result batch is contiguous in dst: one TMA bulk store (or FP64 add-reduction for vmult_add)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     CTA_SYNC();
-    if (t == 0) tma_store_1d(A.dst + b0 * N3, U, bytes, A.add != 0);
-    return;
+    if (t == 0) tma_store_1d(A.dst + b0 * N3, U, bytes, A.add != 0); // returns when the source has been read
+  } else {
+    CTA_SYNC();
+    // ---- coalesced store ----
+    for (int i = t; i < nvalid * N3; i += NT) {
+      const int c = i / N3, rem = i % N3, k = rem / N2, e = rem % N2;
+      const double v = U[c * CS + k * PS + e];
+      if (A.add) A.dst[b0 * N3 + i] += v; else A.dst[b0 * N3 + i] = v;
+    }
   }
-  CTA_SYNC();
-  // ---- coalesced store ----
-  for (int i = t; i < nvalid * N3; i += NT) {
-    const int c = i / N3, rem = i % N3, k = rem / N2, e = rem % N2;
-    const double v = U[c * CS + k * PS + e];
-    if (A.add) A.dst[b0 * N3 + i] += v; else A.dst[b0 * N3 + i] = v;
-  }
+  CTA_SYNC(); // U, staging and the parked tables are ready for the next batch
+  } // persistent loop
 }
 
 struct CartPlan
@@ -474,7 +525,13 @@ void launch_n(const DeviceOperator & op, const CartPlan & plan, double * dst, co
   A.batches = which == 0 ? nullptr : (which == 1 ? plan.d_interior : plan.d_boundary);
   A.n_items = which == 0 ? plan.n_batches : (which == 1 ? plan.n_interior : plan.n_boundary);
   if (A.n_items == 0) return;
-  vmult_cartesian_kernel<N><<<A.n_items, B * N + CartCfg<N>::PAD, plan.smem, stream>>>(T, A);
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, vmult_cartesian_kernel<N>, B * N + CartCfg<N>::PAD, plan.smem));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+  }
+  const int grid = std::min(A.n_items, plan.n_sm * ctas_per_sm);
+  vmult_cartesian_kernel<N><<<grid, B * N + CartCfg<N>::PAD, plan.smem, stream>>>(T, A);
   CUDA_CHECK(cudaGetLastError());
 }
 } // namespace
@@ -515,8 +572,8 @@ size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh)
   }
   P.H = std::max(P.H, 1);
   const int N2 = N * N, PS = N2 | 1, CS = N * PS;
-  P.smem = ((size_t)2 * P.B * CS + (size_t)P.B * 2 * N2 + (size_t)2 * P.H * N2) * sizeof(double) + (size_t)P.H * sizeof(int2) + (size_t)P.B * 12 * sizeof(int) + 32;
-  if (P.smem > 227 * 1024 - 1024) { delete Pp; return 0; } // does not fit: caller falls back to the general kernel
+  P.smem = ((size_t)2 * P.B * CS + (size_t)P.B * 2 * N2 + (size_t)2 * P.H * N2) * sizeof(double) + (size_t)2 * P.H * sizeof(int2) + (size_t)P.B * 18 * sizeof(int) + 16 + 32;
+  if (P.smem > 227 * 1024 - 1024 || P.H > P.B * N) { delete Pp; return 0; } // does not fit: caller falls back to the general kernel
   std::vector<int2> flat((size_t)P.n_batches * P.H, make_int2(0, 0));
   std::vector<int2> cnt(P.n_batches);
   for (int b = 0; b < P.n_batches; ++b) {
