@@ -44,7 +44,7 @@ struct CartArgs
 {
   const int32_t * nb;        // [owned][6]
   const int2 * halo;         // [n_batches][H] (lc<<3|f, neighbour cell)
-  const int2 * halo_cnt;     // [n_batches] (x/y-face entries, z-face entries)
+  const int4 * halo_cnt;     // [n_batches] number of x-, y-, z-face entries
   const int32_t * batches;   // optional list of batch ids
   const double * src; const double * ghost; double * dst;
   int64_t n_owned; int n_items; int H; int add;
@@ -83,6 +83,45 @@ __device__ __forceinline__ void tma_store_1d(void * gdst, const void * smem_src,
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// End value and end derivative of the n^2 lines of out-of-batch neighbour cells that are normal to the shared
+// face (direction D): entries [e0, e1) of the halo list, one line per thread and entry, loads straight from
+// global memory / L2 (the cell is contiguous, every byte of it is used by the 25 threads of a group).
+// Small per-cell TMA copies were measured to cost ~100 issue cycles each, far more than these loads.
+template<int N, int D, typename Tab>
+__device__ __forceinline__ void halo_traces(const Tab & T, const int2 * hlS, int e0, int e1, int grp, int n_grp, int ab, const double * src, const double * ghost,
+                                            int64_t n_owned, double * HV, double * HG, int * slotS)
+{
+  constexpr int N2 = N * N, N3 = N2 * N;
+  constexpr int sd = (D == 0) ? 1 : (D == 1 ? N : N2);
+  constexpr int s1 = (D == 0) ? N : 1, s2 = (D == 2) ? N : N2;
+  constexpr int UNR = 3;
+  const int off = (ab % N) * s1 + (ab / N) * s2;
+  for (int e = e0 + grp; e < e1; e += n_grp * UNR) {
+    double x[UNR][N]; int2 h[UNR];
+#pragma unroll
+    for (int q = 0; q < UNR; ++q) {
+      const int eq = e + q * n_grp;
+      h[q] = hlS[eq < e1 ? eq : e];
+      const double * line = ((h[q].y < n_owned) ? src + (size_t)h[q].y * N3 : ghost + (size_t)(h[q].y - n_owned) * N3) + off;
+#pragma unroll
+      for (int i = 0; i < N; ++i) x[q][i] = line[i * sd];
+    }
+#pragma unroll
+    for (int q = 0; q < UNR; ++q) {
+      const int eq = e + q * n_grp;
+      if (eq < e1) {
+        double g0 = T.fd[0][0] * x[q][0], g1 = T.fd[1][0] * x[q][0];
+#pragma unroll
+        for (int i = 1; i < N; ++i) { g0 = fma(T.fd[0][i], x[q][i], g0); g1 = fma(T.fd[1][i], x[q][i], g1); }
+        const bool sp = !(h[q].x & 1); // the neighbour is entered through its face (D, sp) = opposite side of ours
+        HV[eq * N2 + ab] = sp ? x[q][N - 1] : x[q][0];
+        HG[eq * N2 + ab] = sp ? g1 : g0;
+        if (ab == 0) slotS[(h[q].x >> 3) * 6 + (h[q].x & 7)] = eq;
+      }
+    }
+  }
+}
+
 // B cells per CTA, B*N compute threads.  For n = 5 that is 5 warps; warps are bound to the four SM
 // sub-partitions by (warp id % 4), so sub-partition 0 would carry 2 of every 5 warps of every CTA and its
 // FP64 pipe (16 lanes) would cap the SM at 62 %.  The CTA is therefore launched with one spare warp and
@@ -106,8 +145,8 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N + CartCfg<N>::PAD, (N == 5) 
   int2 * hlS2 = reinterpret_cast<int2 *>(HG + (size_t)A.H * N2); // [2][H] halo lists (current batch / prefetched next batch)
   int * nbS2 = reinterpret_cast<int *>(hlS2 + 2 * A.H);          // [2][B][6] neighbour tables
   int * slotS = nbS2 + 2 * B * 6;                                // [B][6]
-  int2 * cntS = reinterpret_cast<int2 *>(slotS + B * 6);         // [2]
-  uint64_t * bar = reinterpret_cast<uint64_t *>(cntS + 2);       // [2]: batch data, staged halo cells
+  int4 * cntS = reinterpret_cast<int4 *>((reinterpret_cast<uintptr_t>(slotS + B * 6) + 15) & ~uintptr_t(15)); // [2]
+  uint64_t * bar = reinterpret_cast<uint64_t *>(cntS + 2);       // batch data mbarrier
 
   int t = threadIdx.x;
   if (CartCfg<N>::PAD) {
@@ -117,12 +156,10 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N + CartCfg<N>::PAD, (N == 5) 
     if (t < 0 || t >= NT) return; // spare warp
   }
   const int lc = t / N, s = t % N;
-  constexpr int SLOT = (N3 + 3) & ~1;            // doubles per staged cell: 8 B front pad for odd cells, 16 B granularity
-  constexpr int CAP_L = (B * CS) / SLOT;          // staged cells of the overlapped (late) round: Tt only
-  constexpr int CAP_E = (B * CS + B * 2 * N2) / SLOT; // early rounds may spill into the GN region behind Tt
-  double * ST = Tt;
-  uint32_t hpar = 0, upar = 0; // parities of the two mbarriers
-  if (t == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
+  uint32_t upar = 0; // parity of the batch-data mbarrier
+  if (t == 0) mbar_init(bar, 1);
+  const int grp = t / N2, ab = t % N2; // halo phase: group of n^2 threads per neighbour cell
+  constexpr int NGRP = NT / N2;
 
   // Persistent CTA: batches it, it + gridDim.x, ...  The neighbour table and halo list of the NEXT batch are
   // fetched into registers while the current batch is computed and parked in the second shared-memory slot at
@@ -136,10 +173,10 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N + CartCfg<N>::PAD, (N == 5) 
       const int bt = batch_of(it0);
       const int64_t c0 = (int64_t)bt * B;
       const int nv = (int)min((int64_t)B, A.n_owned - c0);
-      const int2 hc0 = A.halo_cnt[bt];
+      const int4 hc0 = A.halo_cnt[bt];
       if (t == 0) cntS[0] = hc0;
       for (int i = t; i < B * 6; i += NT) nbS2[i] = (i / 6 < nv) ? A.nb[c0 * 6 + i] : -1;
-      for (int i = t; i < hc0.x + hc0.y; i += NT) hlS2[i] = A.halo[(size_t)bt * A.H + i];
+      for (int i = t; i < hc0.x + hc0.y + hc0.z; i += NT) hlS2[i] = A.halo[(size_t)bt * A.H + i];
     }
   }
   CTA_SYNC();
@@ -162,8 +199,7 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N + CartCfg<N>::PAD, (N == 5) 
   // the x/y sweeps and consumed after them, so their latency hides behind the FP64 work.
   if (t == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // earlier generic accesses of U / staging before the bulk copies
   if (use_tma && t == 0) { mbar_expect_tx(bar, bytes); tma_load_1d(U, A.src + b0 * N3, bytes, bar); }
-  const int2 hc = cntS[cur];                      // x = number of x/y-face entries, y = number of z-face entries (sorted that way)
-  const int cnt = hc.x + hc.y;
+  const int4 hc = cntS[cur];                      // number of x-, y-, z-face entries of the halo list (sorted that way)
   for (int i = t; i < B * 6; i += NT) slotS[i] = -1;
   CTA_SYNC(); // slot table reset before any trace is registered
   if (!use_tma) {
@@ -179,52 +215,10 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N + CartCfg<N>::PAD, (N == 5) 
       }
     }
   }
-  // issue the bulk copies of entries [e0, e0 + n) into the staging slots (warp 0; one copy per lane and pass)
-  auto stage_issue = [&](int e0, int n) {
-    if (t < 32) {
-      for (int q = t; q < n; q += 32) {
-        const int2 h = hlS[e0 + q];
-        const double * cellp = (h.y < A.n_owned) ? A.src + (size_t)h.y * N3 : A.ghost + (size_t)(h.y - A.n_owned) * N3;
-        const uint32_t odd = (uint32_t)((reinterpret_cast<uintptr_t>(cellp) >> 3) & 1); // only 8-byte aligned: start 8 B earlier
-        const uint32_t nbytes = (uint32_t)((N3 + odd + ((N3 + odd) & 1)) * sizeof(double));
-        asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar + 1)), "r"(nbytes) : "memory");
-        tma_load_1d(ST + q * SLOT, cellp - odd, nbytes, bar + 1);
-      }
-      __syncwarp();
-      // the single arrival comes last: the phase cannot complete before every lane has added its byte count
-      if (t == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar + 1)) : "memory");
-    }
-  };
-  // reduce staged cells to traces: item = (entry, line); line end value and end derivative
-  auto stage_reduce = [&](int e0, int n) {
-    for (int item = t; item < n * N2; item += NT) {
-      const int q = item / N2, ab = item % N2, a = ab % N, bq = ab / N;
-      const int2 h = hlS[e0 + q];
-      const int f = h.x & 7, d = f >> 1, sp = (f & 1) ^ 1; // the neighbour is entered through its face (d, sp)
-      const double * cellp = (h.y < A.n_owned) ? A.src + (size_t)h.y * N3 : A.ghost + (size_t)(h.y - A.n_owned) * N3;
-      const int odd = (int)((reinterpret_cast<uintptr_t>(cellp) >> 3) & 1);
-      const int sd = (d == 0) ? 1 : (d == 1 ? N : N2);
-      const int s1 = (d == 0) ? N : 1, s2 = (d == 2) ? N : N2;
-      const double * line = ST + q * SLOT + odd + a * s1 + bq * s2;
-      const double * fdp = sp ? T.fd[1] : T.fd[0];
-      double x[N];
-#pragma unroll
-      for (int i = 0; i < N; ++i) x[i] = line[i * sd];
-      double g = fdp[0] * x[0];
-#pragma unroll
-      for (int i = 1; i < N; ++i) g = fma(fdp[i], x[i], g);
-      HV[(e0 + q) * N2 + ab] = sp ? x[N - 1] : x[0];
-      HG[(e0 + q) * N2 + ab] = g;
-      if (ab == 0) slotS[(h.x >> 3) * 6 + f] = e0 + q;
-    }
-  };
-  // x/y-face entries (and z-face entries beyond one round) are consumed right away
-  const int z_first = hc.x;                                   // first z entry
-  const int z_now = (hc.y > CAP_L) ? hc.y - CAP_L : 0;        // z entries that do not fit the overlapped round
   // prefetch of the next batch's tables (registers now, shared memory at the end of the iteration)
   const int itn = it + gridDim.x;
   const bool has_next = itn < A.n_items;
-  int pre_nb[(B * 6 + NT - 1) / NT]; int2 pre_hl = make_int2(0, 0); int2 pre_cnt = make_int2(0, 0);
+  int pre_nb[(B * 6 + NT - 1) / NT]; int2 pre_hl = make_int2(0, 0); int4 pre_cnt = make_int4(0, 0, 0, 0);
   auto prefetch_next = [&]() {
     if (!has_next) return;
     const int bn = batch_of(itn);
@@ -235,18 +229,12 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N + CartCfg<N>::PAD, (N == 5) 
     pre_cnt = A.halo_cnt[bn];
     if (t < A.H) pre_hl = A.halo[(size_t)bn * A.H + t];
   };
-  bool prefetched = false;
-  for (int e0 = 0; e0 < hc.x + z_now; e0 += CAP_E) {
-    const int n = min(CAP_E, hc.x + z_now - e0);
-    stage_issue(e0, n);
-    if (!prefetched) { prefetch_next(); prefetched = true; }
-    mbar_wait(bar + 1, hpar); hpar ^= 1;
-    stage_reduce(e0, n);
-    CTA_SYNC(); // staging slots are reused
+  prefetch_next();
+  if (grp < NGRP) {
+    halo_traces<N, 0>(T, hlS, 0, hc.x, grp, NGRP, ab, A.src, A.ghost, A.n_owned, HV, HG, slotS);
+    halo_traces<N, 1>(T, hlS, hc.x, hc.x + hc.y, grp, NGRP, ab, A.src, A.ghost, A.n_owned, HV, HG, slotS);
+    halo_traces<N, 2>(T, hlS, hc.x + hc.y, hc.x + hc.y + hc.z, grp, NGRP, ab, A.src, A.ghost, A.n_owned, HV, HG, slotS);
   }
-  const int z_late0 = z_first + z_now, z_late = cnt - z_late0; // overlapped round
-  if (z_late > 0) stage_issue(z_late0, z_late);
-  if (!prefetched) { prefetch_next(); prefetched = true; }
   if (use_tma) { mbar_wait(bar, upar); upar ^= 1; }
   CTA_SYNC();
 
@@ -323,11 +311,6 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N + CartCfg<N>::PAD, (N == 5) 
           }
     }
     CTA_SYNC(); // GN is reused by the next direction
-  }
-  if (z_late > 0) {
-    mbar_wait(bar + 1, hpar); hpar ^= 1;
-    stage_reduce(z_late0, z_late);
-    CTA_SYNC(); // staging (= Tt) is free again
   }
   if (valid) {
 #pragma unroll
@@ -469,7 +452,7 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N + CartCfg<N>::PAD, (N == 5) 
 struct CartPlan
 {
   int n = 0, B = 0, H = 0, n_batches = 0;
-  int2 * d_halo = nullptr; int2 * d_cnt = nullptr; int n_sm = 148;
+  int2 * d_halo = nullptr; int4 * d_cnt = nullptr; int n_sm = 148;
   int32_t * d_interior = nullptr, * d_boundary = nullptr; int n_interior = 0, n_boundary = 0;
   size_t smem = 0;
   std::vector<char> tables; // CartTables<n> of this operator (depends on h and tau)
@@ -572,22 +555,22 @@ size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh)
   }
   P.H = std::max(P.H, 1);
   const int N2 = N * N, PS = N2 | 1, CS = N * PS;
-  P.smem = ((size_t)2 * P.B * CS + (size_t)P.B * 2 * N2 + (size_t)2 * P.H * N2) * sizeof(double) + (size_t)2 * P.H * sizeof(int2) + (size_t)P.B * 18 * sizeof(int) + 16 + 32;
+  P.smem = ((size_t)2 * P.B * CS + (size_t)P.B * 2 * N2 + (size_t)2 * P.H * N2) * sizeof(double) + (size_t)2 * P.H * sizeof(int2) + (size_t)P.B * 18 * sizeof(int) + 64 + 32;
   if (P.smem > 227 * 1024 - 1024 || P.H > P.B * N) { delete Pp; return 0; } // does not fit: caller falls back to the general kernel
   std::vector<int2> flat((size_t)P.n_batches * P.H, make_int2(0, 0));
-  std::vector<int2> cnt(P.n_batches);
+  std::vector<int4> cnt(P.n_batches);
   for (int b = 0; b < P.n_batches; ++b) {
-    std::stable_sort(lists[b].begin(), lists[b].end(), [](const int2 & x, const int2 & y) { return ((x.x & 7) >= 4) < ((y.x & 7) >= 4); });
-    int nz = 0;
-    for (auto & e : lists[b]) nz += ((e.x & 7) >= 4);
-    cnt[b] = make_int2((int)lists[b].size() - nz, nz);
+    std::stable_sort(lists[b].begin(), lists[b].end(), [](const int2 & x, const int2 & y) { return ((x.x & 7) >> 1) < ((y.x & 7) >> 1); });
+    int c[3] = {0, 0, 0};
+    for (auto & e : lists[b]) c[(e.x & 7) >> 1]++;
+    cnt[b] = make_int4(c[0], c[1], c[2], 0);
     std::copy(lists[b].begin(), lists[b].end(), flat.begin() + (size_t)b * P.H);
   }
   CUDA_CHECK(cudaMalloc(&P.d_halo, flat.size() * sizeof(int2)));
   CUDA_CHECK(cudaMemcpy(P.d_halo, flat.data(), flat.size() * sizeof(int2), cudaMemcpyHostToDevice));
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&P.n_sm, cudaDevAttrMultiProcessorCount, dev); if (P.n_sm < 1) P.n_sm = 148; }
-  CUDA_CHECK(cudaMalloc(&P.d_cnt, cnt.size() * sizeof(int2)));
-  CUDA_CHECK(cudaMemcpy(P.d_cnt, cnt.data(), cnt.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMalloc(&P.d_cnt, cnt.size() * sizeof(int4)));
+  CUDA_CHECK(cudaMemcpy(P.d_cnt, cnt.data(), cnt.size() * sizeof(int4), cudaMemcpyHostToDevice));
   P.n_interior = (int)interior.size(); P.n_boundary = (int)boundary.size();
   if (mesh.world > 1) {
     if (P.n_interior) { CUDA_CHECK(cudaMalloc(&P.d_interior, interior.size() * 4)); CUDA_CHECK(cudaMemcpy(P.d_interior, interior.data(), interior.size() * 4, cudaMemcpyHostToDevice)); }
