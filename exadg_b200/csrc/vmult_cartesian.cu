@@ -44,11 +44,10 @@ struct CartArgs
 {
   const int32_t * nb;        // [owned][6]
   const int2 * halo;         // [n_batches][H] (lc<<3|f, neighbour cell)
-  const int4 * halo_cnt;     // [n_batches] number of x-, y-, z-face entries
+  const int32_t * halo_cnt;  // [n_batches]
   const int32_t * batches;   // optional list of batch ids
   const double * src; const double * ghost; double * dst;
   int64_t n_owned; int n_items; int H; int add;
-  int n_sm;
 };
 
 // ---- TMA (bulk async copy) + mbarrier helpers, sm_90+/sm_100a PTX ----
@@ -83,55 +82,10 @@ __device__ __forceinline__ void tma_store_1d(void * gdst, const void * smem_src,
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-// End value and end derivative of the n^2 lines of out-of-batch neighbour cells that are normal to the shared
-// face (direction D): entries [e0, e1) of the halo list, one line per thread and entry, loads straight from
-// global memory / L2 (the cell is contiguous, every byte of it is used by the 25 threads of a group).
-// Small per-cell TMA copies were measured to cost ~100 issue cycles each, far more than these loads.
-template<int N, int D, typename Tab>
-__device__ __forceinline__ void halo_traces(const Tab & T, const int2 * hlS, int e0, int e1, int grp, int n_grp, int ab, const double * src, const double * ghost,
-                                            int64_t n_owned, double * HV, double * HG, int * slotS)
-{
-  constexpr int N2 = N * N, N3 = N2 * N;
-  constexpr int sd = (D == 0) ? 1 : (D == 1 ? N : N2);
-  constexpr int s1 = (D == 0) ? N : 1, s2 = (D == 2) ? N : N2;
-  constexpr int UNR = 3;
-  const int off = (ab % N) * s1 + (ab / N) * s2;
-  for (int e = e0 + grp; e < e1; e += n_grp * UNR) {
-    double x[UNR][N]; int2 h[UNR];
-#pragma unroll
-    for (int q = 0; q < UNR; ++q) {
-      const int eq = e + q * n_grp;
-      h[q] = hlS[eq < e1 ? eq : e];
-      const double * line = ((h[q].y < n_owned) ? src + (size_t)h[q].y * N3 : ghost + (size_t)(h[q].y - n_owned) * N3) + off;
-#pragma unroll
-      for (int i = 0; i < N; ++i) x[q][i] = line[i * sd];
-    }
-#pragma unroll
-    for (int q = 0; q < UNR; ++q) {
-      const int eq = e + q * n_grp;
-      if (eq < e1) {
-        double g0 = T.fd[0][0] * x[q][0], g1 = T.fd[1][0] * x[q][0];
-#pragma unroll
-        for (int i = 1; i < N; ++i) { g0 = fma(T.fd[0][i], x[q][i], g0); g1 = fma(T.fd[1][i], x[q][i], g1); }
-        const bool sp = !(h[q].x & 1); // the neighbour is entered through its face (D, sp) = opposite side of ours
-        HV[eq * N2 + ab] = sp ? x[q][N - 1] : x[q][0];
-        HG[eq * N2 + ab] = sp ? g1 : g0;
-        if (ab == 0) slotS[(h[q].x >> 3) * 6 + (h[q].x & 7)] = eq;
-      }
-    }
-  }
-}
-
-// B cells per CTA, B*N compute threads.  For n = 5 that is 5 warps; warps are bound to the four SM
-// sub-partitions by (warp id % 4), so sub-partition 0 would carry 2 of every 5 warps of every CTA and its
-// FP64 pipe (16 lanes) would cap the SM at 62 %.  The CTA is therefore launched with one spare warp and
-// every other CTA arriving on an SM shifts its compute warps by one (warps 1..5 instead of 0..4), which
-// spreads two resident CTAs as 3,3,2,2 warps over the sub-partitions.  The spare warp exits at once.
-template<int N> struct CartCfg { static constexpr int B = (N >= 4) ? 32 : 64; static constexpr int PAD = ((B * N) % 128 == 0) ? 0 : 32; };
-#define CTA_SYNC() asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory")
+template<int N> struct CartCfg { static constexpr int B = (N >= 4) ? 32 : 64; };
 
 template<int N>
-__global__ void __launch_bounds__(CartCfg<N>::B * N + CartCfg<N>::PAD, (N == 5) ? 2 : 1) vmult_cartesian_kernel(const __grid_constant__ CartTables<N> T, const CartArgs A)
+__global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_cartesian_kernel(const __grid_constant__ CartTables<N> T, const CartArgs A)
 {
   constexpr int B = CartCfg<N>::B, NT = B * N;
   constexpr int N2 = N * N, N3 = N2 * N;
@@ -142,66 +96,29 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N + CartCfg<N>::PAD, (N == 5) 
   double * GN = Tt + B * CS;         // [B][2][N2] own end derivatives of the current direction
   double * HV = GN + B * 2 * N2;     // [H][N2] end values of out-of-batch neighbours
   double * HG = HV + (size_t)A.H * N2; // [H][N2] end derivatives of out-of-batch neighbours
-  int2 * hlS2 = reinterpret_cast<int2 *>(HG + (size_t)A.H * N2); // [2][H] halo lists (current batch / prefetched next batch)
-  int * nbS2 = reinterpret_cast<int *>(hlS2 + 2 * A.H);          // [2][B][6] neighbour tables
-  int * slotS = nbS2 + 2 * B * 6;                                // [B][6]
-  int4 * cntS = reinterpret_cast<int4 *>((reinterpret_cast<uintptr_t>(slotS + B * 6) + 15) & ~uintptr_t(15)); // [2]
-  uint64_t * bar = reinterpret_cast<uint64_t *>(cntS + 2);       // batch data mbarrier
+  int2 * hlS = reinterpret_cast<int2 *>(HG + (size_t)A.H * N2); // [H] halo list of this batch
+  int * nbS = reinterpret_cast<int *>(hlS + A.H); // [B][6]
+  int * slotS = nbS + B * 6;         // [B][6]
+  uint64_t * bar = reinterpret_cast<uint64_t *>(slotS + B * 6);
 
-  int t = threadIdx.x;
-  if (CartCfg<N>::PAD) {
-    // CTAs are dispatched round-robin over the SMs, so the two CTAs resident on an SM are bid and bid + n_sm:
-    // alternate the warp shift with (bid / n_sm)
-    t -= ((blockIdx.x / A.n_sm) & 1) * 32;
-    if (t < 0 || t >= NT) return; // spare warp
-  }
-  const int lc = t / N, s = t % N;
-  uint32_t upar = 0; // parity of the batch-data mbarrier
-  if (t == 0) mbar_init(bar, 1);
-  const int grp = t / N2, ab = t % N2; // halo phase: group of n^2 threads per neighbour cell
-  constexpr int NGRP = NT / N2;
-
-  // Persistent CTA: batches it, it + gridDim.x, ...  The neighbour table and halo list of the NEXT batch are
-  // fetched into registers while the current batch is computed and parked in the second shared-memory slot at
-  // the end of the iteration, so that every batch starts with all its bulk copies issued at once (one memory
-  // latency per batch instead of a chain of three dependent ones).
-  auto batch_of = [&](int it) { return A.batches ? A.batches[it] : it; };
-  int cur = 0;
-  {
-    const int it0 = blockIdx.x;
-    if (it0 < A.n_items) {
-      const int bt = batch_of(it0);
-      const int64_t c0 = (int64_t)bt * B;
-      const int nv = (int)min((int64_t)B, A.n_owned - c0);
-      const int4 hc0 = A.halo_cnt[bt];
-      if (t == 0) cntS[0] = hc0;
-      for (int i = t; i < B * 6; i += NT) nbS2[i] = (i / 6 < nv) ? A.nb[c0 * 6 + i] : -1;
-      for (int i = t; i < hc0.x + hc0.y + hc0.z; i += NT) hlS2[i] = A.halo[(size_t)bt * A.H + i];
-    }
-  }
-  CTA_SYNC();
-
-  for (int it = blockIdx.x; it < A.n_items; it += gridDim.x, cur ^= 1) {
-  const int batch = batch_of(it);
+  const int t = threadIdx.x, lc = t / N, s = t % N;
+  const int batch = A.batches ? A.batches[blockIdx.x] : (int)blockIdx.x;
   const int64_t b0 = (int64_t)batch * B;
   const int nvalid = (int)min((int64_t)B, A.n_owned - b0);
   const bool valid = lc < nvalid;
-  int2 * hlS = hlS2 + cur * A.H;
-  int * nbS = nbS2 + cur * B * 6;
   // contiguous cell data (odd n: no padding) goes through one TMA bulk copy; 16-byte granularity
   const uint32_t bytes = (uint32_t)(nvalid * N3 * sizeof(double));
   const bool use_tma = (PS == N2) && (bytes % 16 == 0);
 
   // ---- phase L: stage the batch, its neighbour table and the traces of out-of-batch neighbours ----
-  // Every out-of-batch neighbour contributes the end value / end derivative of all n^2 lines normal to the
-  // shared face, i.e. its whole cell is needed once.  The cells are fetched by TMA bulk copies into the (still
-  // unused) Tt region and reduced to traces from shared memory; the copies for the z faces are issued before
-  // the x/y sweeps and consumed after them, so their latency hides behind the FP64 work.
-  if (t == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // earlier generic accesses of U / staging before the bulk copies
-  if (use_tma && t == 0) { mbar_expect_tx(bar, bytes); tma_load_1d(U, A.src + b0 * N3, bytes, bar); }
-  const int4 hc = cntS[cur];                      // number of x-, y-, z-face entries of the halo list (sorted that way)
-  for (int i = t; i < B * 6; i += NT) slotS[i] = -1;
-  CTA_SYNC(); // slot table reset before any trace is registered
+  if (use_tma) {
+    if (t == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (t == 0) { mbar_expect_tx(bar, bytes); tma_load_1d(U, A.src + b0 * N3, bytes, bar); }
+  }
+  const int cnt = A.halo_cnt[batch];
+  for (int i = t; i < B * 6; i += NT) { nbS[i] = (i / 6 < nvalid) ? A.nb[b0 * 6 + i] : -1; slotS[i] = -1; }
+  for (int i = t; i < cnt; i += NT) hlS[i] = A.halo[(size_t)batch * A.H + i];
   if (!use_tma) {
     constexpr int UNR = 8; // independent loads in flight per thread
     for (int i0 = t; i0 < nvalid * N3; i0 += NT * UNR) {
@@ -215,28 +132,48 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N + CartCfg<N>::PAD, (N == 5) 
       }
     }
   }
-  // prefetch of the next batch's tables (registers now, shared memory at the end of the iteration)
-  const int itn = it + gridDim.x;
-  const bool has_next = itn < A.n_items;
-  int pre_nb[(B * 6 + NT - 1) / NT]; int2 pre_hl = make_int2(0, 0); int4 pre_cnt = make_int4(0, 0, 0, 0);
-  auto prefetch_next = [&]() {
-    if (!has_next) return;
-    const int bn = batch_of(itn);
-    const int64_t c0 = (int64_t)bn * B;
-    const int nv = (int)min((int64_t)B, A.n_owned - c0);
+  __syncthreads();
+  {
+    constexpr int UNR = 5; // 5 items x n loads in flight per thread
+    for (int it0 = t; it0 < cnt * N2; it0 += NT * UNR) {
+      double x[UNR][N]; int sp[UNR];
 #pragma unroll
-    for (int q = 0; q < (B * 6 + NT - 1) / NT; ++q) { const int i = t + q * NT; pre_nb[q] = (i < B * 6 && i / 6 < nv) ? A.nb[c0 * 6 + i] : -1; }
-    pre_cnt = A.halo_cnt[bn];
-    if (t < A.H) pre_hl = A.halo[(size_t)bn * A.H + t];
-  };
-  prefetch_next();
-  if (grp < NGRP) {
-    halo_traces<N, 0>(T, hlS, 0, hc.x, grp, NGRP, ab, A.src, A.ghost, A.n_owned, HV, HG, slotS);
-    halo_traces<N, 1>(T, hlS, hc.x, hc.x + hc.y, grp, NGRP, ab, A.src, A.ghost, A.n_owned, HV, HG, slotS);
-    halo_traces<N, 2>(T, hlS, hc.x + hc.y, hc.x + hc.y + hc.z, grp, NGRP, ab, A.src, A.ghost, A.n_owned, HV, HG, slotS);
+      for (int q = 0; q < UNR; ++q) {
+        const int item = it0 + q * NT;
+        sp[q] = 0;
+        if (item < cnt * N2) {
+          const int e = item / N2, ab = item % N2, a = ab % N, b = ab / N;
+          const int2 h = hlS[e];
+          const int f = h.x & 7, d = f >> 1;
+          sp[q] = (f & 1) ^ 1; // neighbour is entered through its face (d, sp)
+          const double * un = (h.y < A.n_owned) ? A.src + (size_t)h.y * N3 : A.ghost + (size_t)(h.y - A.n_owned) * N3;
+          const int sd = (d == 0) ? 1 : (d == 1 ? N : N2);
+          const int s1 = (d == 0) ? N : 1, s2 = (d == 2) ? N : N2;
+          const double * line = un + a * s1 + b * s2;
+#pragma unroll
+          for (int i = 0; i < N; ++i) x[q][i] = line[i * sd];
+        } else {
+#pragma unroll
+          for (int i = 0; i < N; ++i) x[q][i] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < UNR; ++q) {
+        const int item = it0 + q * NT;
+        if (item < cnt * N2) {
+          const int e = item / N2, ab = item % N2;
+          double g = 0.0;
+#pragma unroll
+          for (int i = 0; i < N; ++i) g = fma(sp[q] ? T.fd[1][i] : T.fd[0][i], x[q][i], g);
+          HV[e * N2 + ab] = sp[q] ? x[q][N - 1] : x[q][0];
+          HG[e * N2 + ab] = g;
+          if (ab == 0) { const int2 h = hlS[e]; slotS[(h.x >> 3) * 6 + (h.x & 7)] = e; }
+        }
+      }
+    }
   }
-  if (use_tma) { mbar_wait(bar, upar); upar ^= 1; }
-  CTA_SYNC();
+  if (use_tma) mbar_wait(bar, 0);
+  __syncthreads();
 
   double u[N][N], acc[N][N];
   if (valid) {
@@ -250,21 +187,19 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N + CartCfg<N>::PAD, (N == 5) 
 #pragma unroll
   for (int d = 0; d < 2; ++d) {
     if (valid) {
-      // end derivatives of the n lines of this plane (line l: d=0 -> row j=l, d=1 -> column i=l); 2n independent chains
-      double g0[N], g1[N];
 #pragma unroll
-      for (int l = 0; l < N; ++l) { const double x = (d == 0) ? u[l][0] : u[0][l]; g0[l] = T.fd[0][0] * x; g1[l] = T.fd[1][0] * x; }
+      for (int l = 0; l < N; ++l) { // line l: d=0 -> row j=l (runs over i); d=1 -> column i=l (runs over j)
+        double g0 = 0.0, g1 = 0.0;
 #pragma unroll
-      for (int m = 1; m < N; ++m)
-#pragma unroll
-        for (int l = 0; l < N; ++l) {
+        for (int m = 0; m < N; ++m) {
           const double x = (d == 0) ? u[l][m] : u[m][l];
-          g0[l] = fma(T.fd[0][m], x, g0[l]); g1[l] = fma(T.fd[1][m], x, g1[l]);
+          g0 = fma(T.fd[0][m], x, g0); g1 = fma(T.fd[1][m], x, g1);
         }
-#pragma unroll
-      for (int l = 0; l < N; ++l) { GN[(lc * 2 + 0) * N2 + l + N * s] = g0[l]; GN[(lc * 2 + 1) * N2 + l + N * s] = g1[l]; }
+        GN[(lc * 2 + 0) * N2 + l + N * s] = g0;
+        GN[(lc * 2 + 1) * N2 + l + N * s] = g1;
+      }
     }
-    CTA_SYNC();
+    __syncthreads();
     if (valid) {
 #pragma unroll
       for (int side = 0; side < 2; ++side) {
@@ -273,44 +208,36 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N + CartCfg<N>::PAD, (N == 5) 
         const bool inb = (nbl >= 0 && nbl < B);
         const int slot = slotS[lc * 6 + f];
         const double hs = side ? 0.5 : -0.5; // 1/2 sigma_s
-        double vn[N], tt[N];
 #pragma unroll
         for (int l = 0; l < N; ++l) {
-          double gn;
+          double vn, gn;
           if (inb) {
             const int endn = side ? 0 : N - 1; // neighbour's end node facing us
-            vn[l] = (d == 0) ? U[nbl * CS + s * PS + endn + N * l] : U[nbl * CS + s * PS + l + N * endn];
+            vn = (d == 0) ? U[nbl * CS + s * PS + endn + N * l] : U[nbl * CS + s * PS + l + N * endn];
             gn = GN[(nbl * 2 + (side ^ 1)) * N2 + l + N * s];
           } else {
-            vn[l] = HV[slot * N2 + l + N * s]; gn = HG[slot * N2 + l + N * s];
+            vn = HV[slot * N2 + l + N * s]; gn = HG[slot * N2 + l + N * s];
           }
-          tt[l] = fma(hs, gn, T.tau_hat[d] * vn[l]);
+          const double tt = fma(hs, gn, T.tau_hat[d] * vn);
+#pragma unroll
+          for (int m = 0; m < N; ++m) {
+            double & y = (d == 0) ? acc[l][m] : acc[m][l];
+            y = fma(T.P[d][side][m], vn, y);
+            y = fma(T.Q[d][side][m], tt, y);
+          }
         }
-#pragma unroll
-        for (int m = 0; m < N; ++m)
-#pragma unroll
-          for (int l = 0; l < N; ++l) {
-            if (d == 0) acc[l][m] = fma(T.P[d][side][m], vn[l], acc[l][m]); else acc[m][l] = fma(T.P[d][side][m], vn[l], acc[m][l]);
-          }
-#pragma unroll
-        for (int m = 0; m < N; ++m)
-#pragma unroll
-          for (int l = 0; l < N; ++l) {
-            if (d == 0) acc[l][m] = fma(T.Q[d][side][m], tt[l], acc[l][m]); else acc[m][l] = fma(T.Q[d][side][m], tt[l], acc[m][l]);
-          }
       }
-      // G u: column index outermost so that consecutive DFMAs hit 25 independent accumulators
 #pragma unroll
-      for (int c = 0; c < N; ++c)
+      for (int l = 0; l < N; ++l)
 #pragma unroll
-        for (int l = 0; l < N; ++l)
+        for (int r = 0; r < N; ++r) {
+          double y = (d == 0) ? acc[l][r] : acc[r][l];
 #pragma unroll
-          for (int r = 0; r < N; ++r) {
-            if (d == 0) acc[l][r] = fma(T.G[d][r * N + c], u[l][c], acc[l][r]);
-            else acc[r][l] = fma(T.G[d][r * N + c], u[c][l], acc[r][l]);
-          }
+          for (int c = 0; c < N; ++c) y = fma(T.G[d][r * N + c], (d == 0) ? u[l][c] : u[c][l], y);
+          if (d == 0) acc[l][r] = y; else acc[r][l] = y;
+        }
     }
-    CTA_SYNC(); // GN is reused by the next direction
+    __syncthreads(); // GN is reused by the next direction
   }
   if (valid) {
 #pragma unroll
@@ -322,76 +249,61 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N + CartCfg<N>::PAD, (N == 5) 
   // ---- z sweep: this thread owns the n lines (i, j = s) ----
   if (valid) {
 #pragma unroll
-    for (int i = 0; i < N; ++i)
+    for (int i = 0; i < N; ++i) {
+      double g0 = 0.0, g1 = 0.0;
 #pragma unroll
-      for (int k = 0; k < N; ++k) u[i][k] = U[lc * CS + k * PS + i + N * s]; // reuse the plane registers: u[i][k] = line i at height k
-    double g0[N], g1[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) { g0[i] = T.fd[0][0] * u[i][0]; g1[i] = T.fd[1][0] * u[i][0]; }
-#pragma unroll
-    for (int k = 1; k < N; ++k)
-#pragma unroll
-      for (int i = 0; i < N; ++i) { g0[i] = fma(T.fd[0][k], u[i][k], g0[i]); g1[i] = fma(T.fd[1][k], u[i][k], g1[i]); }
-#pragma unroll
-    for (int i = 0; i < N; ++i) { GN[(lc * 2 + 0) * N2 + i + N * s] = g0[i]; GN[(lc * 2 + 1) * N2 + i + N * s] = g1[i]; }
+      for (int k = 0; k < N; ++k) {
+        const double x = U[lc * CS + k * PS + i + N * s];
+        u[i][k] = x; // reuse the plane registers: u[i][k] = value of line i at height k
+        g0 = fma(T.fd[0][k], x, g0); g1 = fma(T.fd[1][k], x, g1);
+      }
+      GN[(lc * 2 + 0) * N2 + i + N * s] = g0;
+      GN[(lc * 2 + 1) * N2 + i + N * s] = g1;
+    }
   }
-  CTA_SYNC(); // Tt planes and z traces visible
+  __syncthreads(); // Tt planes and z traces visible
   if (valid) {
-    // all five lines (i, j = s) at once: acc[i][k] = partial result, u[i][k] = src values of the line
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-#pragma unroll
-      for (int k = 0; k < N; ++k) acc[i][k] = Tt[lc * CS + k * PS + i + N * s];
+    int nbl[2], slot[2]; bool inb[2];
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
-      const int nbl = nbS[lc * 6 + 4 + side] - (int)b0;
-      const bool inb = (nbl >= 0 && nbl < B);
-      const int slot = slotS[lc * 6 + 4 + side];
-      double vn[N], tt[N];
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        double gn;
-        if (inb) {
-          const int endn = side ? 0 : N - 1;
-          vn[i] = U[nbl * CS + endn * PS + i + N * s];
-          gn = GN[(nbl * 2 + (side ^ 1)) * N2 + i + N * s];
-        } else {
-          vn[i] = HV[slot * N2 + i + N * s]; gn = HG[slot * N2 + i + N * s];
-        }
-        tt[i] = fma(side ? 0.5 : -0.5, gn, T.tau_hat[2] * vn[i]);
-      }
-#pragma unroll
-      for (int k = 0; k < N; ++k)
-#pragma unroll
-        for (int i = 0; i < N; ++i) acc[i][k] = fma(T.P[2][side][k], vn[i], acc[i][k]);
-#pragma unroll
-      for (int k = 0; k < N; ++k)
-#pragma unroll
-        for (int i = 0; i < N; ++i) acc[i][k] = fma(T.Q[2][side][k], tt[i], acc[i][k]);
+      nbl[side] = nbS[lc * 6 + 4 + side] - (int)b0;
+      inb[side] = (nbl[side] >= 0 && nbl[side] < B);
+      slot[side] = slotS[lc * 6 + 4 + side];
     }
 #pragma unroll
-    for (int c = 0; c < N; ++c)
+    for (int i = 0; i < N; ++i) {
+      double w[N];
 #pragma unroll
-      for (int i = 0; i < N; ++i)
+      for (int k = 0; k < N; ++k) w[k] = Tt[lc * CS + k * PS + i + N * s];
 #pragma unroll
-        for (int r = 0; r < N; ++r) acc[i][r] = fma(T.G[2][r * N + c], u[i][c], acc[i][r]);
-    // mass matrix along z (this thread owns the whole lines): u <- M acc
+      for (int side = 0; side < 2; ++side) {
+        double vn, gn;
+        if (inb[side]) {
+          const int endn = side ? 0 : N - 1;
+          vn = U[nbl[side] * CS + endn * PS + i + N * s];
+          gn = GN[(nbl[side] * 2 + (side ^ 1)) * N2 + i + N * s];
+        } else {
+          vn = HV[slot[side] * N2 + i + N * s]; gn = HG[slot[side] * N2 + i + N * s];
+        }
+        const double tt = fma(side ? 0.5 : -0.5, gn, T.tau_hat[2] * vn);
 #pragma unroll
-    for (int i = 0; i < N; ++i)
+        for (int k = 0; k < N; ++k) { w[k] = fma(T.P[2][side][k], vn, w[k]); w[k] = fma(T.Q[2][side][k], tt, w[k]); }
+      }
 #pragma unroll
-      for (int r = 0; r < N; ++r) u[i][r] = T.M[r * N] * acc[i][0];
+      for (int r = 0; r < N; ++r)
 #pragma unroll
-    for (int c = 1; c < N; ++c)
+        for (int c = 0; c < N; ++c) w[r] = fma(T.G[2][r * N + c], u[i][c], w[r]);
+      // mass matrix along z, in place (this thread owns the whole line)
 #pragma unroll
-      for (int i = 0; i < N; ++i)
+      for (int r = 0; r < N; ++r) {
+        double y = 0.0;
 #pragma unroll
-        for (int r = 0; r < N; ++r) u[i][r] = fma(T.M[r * N + c], acc[i][c], u[i][r]);
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-#pragma unroll
-      for (int r = 0; r < N; ++r) Tt[lc * CS + r * PS + i + N * s] = u[i][r];
+        for (int c = 0; c < N; ++c) y = fma(T.M[r * N + c], w[c], y);
+        Tt[lc * CS + r * PS + i + N * s] = y;
+      }
+    }
   }
-  CTA_SYNC();
+  __syncthreads();
   // ---- mass matrices along x and y on the register plane, staged into U ----
   if (valid) {
 #pragma unroll
@@ -401,58 +313,42 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N + CartCfg<N>::PAD, (N == 5) 
 #pragma unroll
     for (int j = 0; j < N; ++j)
 #pragma unroll
-      for (int r = 0; r < N; ++r) acc[j][r] = T.M[r * N] * u[j][0];
+      for (int r = 0; r < N; ++r) {
+        double y = 0.0;
 #pragma unroll
-    for (int c = 1; c < N; ++c)
+        for (int c = 0; c < N; ++c) y = fma(T.M[r * N + c], u[j][c], y);
+        acc[j][r] = y;
+      }
 #pragma unroll
-      for (int j = 0; j < N; ++j)
+    for (int i = 0; i < N; ++i)
 #pragma unroll
-        for (int r = 0; r < N; ++r) acc[j][r] = fma(T.M[r * N + c], u[j][c], acc[j][r]);
+      for (int r = 0; r < N; ++r) {
+        double y = 0.0;
 #pragma unroll
-    for (int r = 0; r < N; ++r)
-#pragma unroll
-      for (int i = 0; i < N; ++i) u[r][i] = T.M[r * N] * acc[0][i];
-#pragma unroll
-    for (int c = 1; c < N; ++c)
-#pragma unroll
-      for (int r = 0; r < N; ++r)
-#pragma unroll
-        for (int i = 0; i < N; ++i) u[r][i] = fma(T.M[r * N + c], acc[c][i], u[r][i]);
-#pragma unroll
-    for (int r = 0; r < N; ++r)
-#pragma unroll
-      for (int i = 0; i < N; ++i) U[lc * CS + s * PS + i + N * r] = u[r][i];
-  }
-  // park the prefetched tables of the next batch
-  if (has_next) {
-    int * nbN = nbS2 + (cur ^ 1) * B * 6;
-#pragma unroll
-    for (int q = 0; q < (B * 6 + NT - 1) / NT; ++q) { const int i = t + q * NT; if (i < B * 6) nbN[i] = pre_nb[q]; }
-    if (t < A.H) hlS2[(cur ^ 1) * A.H + t] = pre_hl;
-    if (t == 0) cntS[cur ^ 1] = pre_cnt;
+        for (int c = 0; c < N; ++c) y = fma(T.M[r * N + c], acc[c][i], y);
+        U[lc * CS + s * PS + i + N * r] = y;
+      }
   }
   if (use_tma) {
     // result batch is contiguous in dst: one TMA bulk store (or FP64 add-reduction for vmult_add)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    CTA_SYNC();
-    if (t == 0) tma_store_1d(A.dst + b0 * N3, U, bytes, A.add != 0); // returns when the source has been read
-  } else {
-    CTA_SYNC();
-    // ---- coalesced store ----
-    for (int i = t; i < nvalid * N3; i += NT) {
-      const int c = i / N3, rem = i % N3, k = rem / N2, e = rem % N2;
-      const double v = U[c * CS + k * PS + e];
-      if (A.add) A.dst[b0 * N3 + i] += v; else A.dst[b0 * N3 + i] = v;
-    }
+    __syncthreads();
+    if (t == 0) tma_store_1d(A.dst + b0 * N3, U, bytes, A.add != 0);
+    return;
   }
-  CTA_SYNC(); // U, staging and the parked tables are ready for the next batch
-  } // persistent loop
+  __syncthreads();
+  // ---- coalesced store ----
+  for (int i = t; i < nvalid * N3; i += NT) {
+    const int c = i / N3, rem = i % N3, k = rem / N2, e = rem % N2;
+    const double v = U[c * CS + k * PS + e];
+    if (A.add) A.dst[b0 * N3 + i] += v; else A.dst[b0 * N3 + i] = v;
+  }
 }
 
 struct CartPlan
 {
   int n = 0, B = 0, H = 0, n_batches = 0;
-  int2 * d_halo = nullptr; int4 * d_cnt = nullptr; int n_sm = 148;
+  int2 * d_halo = nullptr; int32_t * d_cnt = nullptr;
   int32_t * d_interior = nullptr, * d_boundary = nullptr; int n_interior = 0, n_boundary = 0;
   size_t smem = 0;
   std::vector<char> tables; // CartTables<n> of this operator (depends on h and tau)
@@ -504,17 +400,11 @@ void launch_n(const DeviceOperator & op, const CartPlan & plan, double * dst, co
   if (!configured) { CUDA_CHECK(cudaFuncSetAttribute(vmult_cartesian_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)); configured = true; }
   CartArgs A;
   A.nb = op.nb; A.halo = plan.d_halo; A.halo_cnt = plan.d_cnt; A.src = src; A.ghost = op.ghost; A.dst = dst;
-  A.n_owned = op.n_owned; A.H = plan.H; A.add = add ? 1 : 0; A.n_sm = plan.n_sm;
+  A.n_owned = op.n_owned; A.H = plan.H; A.add = add ? 1 : 0;
   A.batches = which == 0 ? nullptr : (which == 1 ? plan.d_interior : plan.d_boundary);
   A.n_items = which == 0 ? plan.n_batches : (which == 1 ? plan.n_interior : plan.n_boundary);
   if (A.n_items == 0) return;
-  static int ctas_per_sm = 0;
-  if (ctas_per_sm == 0) {
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, vmult_cartesian_kernel<N>, B * N + CartCfg<N>::PAD, plan.smem));
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-  }
-  const int grid = std::min(A.n_items, plan.n_sm * ctas_per_sm);
-  vmult_cartesian_kernel<N><<<grid, B * N + CartCfg<N>::PAD, plan.smem, stream>>>(T, A);
+  vmult_cartesian_kernel<N><<<A.n_items, B * N, plan.smem, stream>>>(T, A);
   CUDA_CHECK(cudaGetLastError());
 }
 } // namespace
@@ -555,22 +445,15 @@ size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh)
   }
   P.H = std::max(P.H, 1);
   const int N2 = N * N, PS = N2 | 1, CS = N * PS;
-  P.smem = ((size_t)2 * P.B * CS + (size_t)P.B * 2 * N2 + (size_t)2 * P.H * N2) * sizeof(double) + (size_t)2 * P.H * sizeof(int2) + (size_t)P.B * 18 * sizeof(int) + 64 + 32;
-  if (P.smem > 227 * 1024 - 1024 || P.H > P.B * N) { delete Pp; return 0; } // does not fit: caller falls back to the general kernel
+  P.smem = ((size_t)2 * P.B * CS + (size_t)P.B * 2 * N2 + (size_t)2 * P.H * N2) * sizeof(double) + (size_t)P.H * sizeof(int2) + (size_t)P.B * 12 * sizeof(int) + 16;
+  if (P.smem > 227 * 1024 - 1024) { delete Pp; return 0; } // does not fit: caller falls back to the general kernel
   std::vector<int2> flat((size_t)P.n_batches * P.H, make_int2(0, 0));
-  std::vector<int4> cnt(P.n_batches);
-  for (int b = 0; b < P.n_batches; ++b) {
-    std::stable_sort(lists[b].begin(), lists[b].end(), [](const int2 & x, const int2 & y) { return ((x.x & 7) >> 1) < ((y.x & 7) >> 1); });
-    int c[3] = {0, 0, 0};
-    for (auto & e : lists[b]) c[(e.x & 7) >> 1]++;
-    cnt[b] = make_int4(c[0], c[1], c[2], 0);
-    std::copy(lists[b].begin(), lists[b].end(), flat.begin() + (size_t)b * P.H);
-  }
+  std::vector<int32_t> cnt(P.n_batches);
+  for (int b = 0; b < P.n_batches; ++b) { cnt[b] = (int32_t)lists[b].size(); std::copy(lists[b].begin(), lists[b].end(), flat.begin() + (size_t)b * P.H); }
   CUDA_CHECK(cudaMalloc(&P.d_halo, flat.size() * sizeof(int2)));
   CUDA_CHECK(cudaMemcpy(P.d_halo, flat.data(), flat.size() * sizeof(int2), cudaMemcpyHostToDevice));
-  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&P.n_sm, cudaDevAttrMultiProcessorCount, dev); if (P.n_sm < 1) P.n_sm = 148; }
-  CUDA_CHECK(cudaMalloc(&P.d_cnt, cnt.size() * sizeof(int4)));
-  CUDA_CHECK(cudaMemcpy(P.d_cnt, cnt.data(), cnt.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMalloc(&P.d_cnt, cnt.size() * sizeof(int32_t)));
+  CUDA_CHECK(cudaMemcpy(P.d_cnt, cnt.data(), cnt.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   P.n_interior = (int)interior.size(); P.n_boundary = (int)boundary.size();
   if (mesh.world > 1) {
     if (P.n_interior) { CUDA_CHECK(cudaMalloc(&P.d_interior, interior.size() * 4)); CUDA_CHECK(cudaMemcpy(P.d_interior, interior.data(), interior.size() * 4, cudaMemcpyHostToDevice)); }
