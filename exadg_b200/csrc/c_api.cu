@@ -638,6 +638,49 @@ int exadg_b200_nccl_init(exadg_b200_operator * op, const char * id128)
   });
 }
 
+// ---- host-only view of the partition / halo plan (no CUDA call): used by the world_size-2 gloo tests ----
+struct exadg_b200_plan { HostMesh mesh; };
+
+int exadg_b200_plan_create(const exadg_b200_hypercube_desc * desc, exadg_b200_plan ** out)
+{
+  return guarded([&]() {
+    if (!desc || !out) throw std::invalid_argument("null argument");
+    HypercubeDesc hd;
+    hd.n_sub = desc->n_subdivisions; hd.refine = desc->n_refinements; hd.mapping_degree = desc->mapping_degree < 1 ? 1 : desc->mapping_degree;
+    hd.deformation = desc->deformation; hd.frequency = desc->frequency;
+    for (int f = 0; f < 6; ++f) hd.bc[f] = desc->boundary[f];
+    hd.rank = desc->rank; hd.world = desc->world < 1 ? 1 : desc->world;
+    std::unique_ptr<exadg_b200_plan> p(new exadg_b200_plan);
+    p->mesh = make_hypercube(hd);
+    *out = p.release();
+    return EXADG_B200_OK;
+  });
+}
+int exadg_b200_plan_destroy(exadg_b200_plan * p) { delete p; return EXADG_B200_OK; }
+int exadg_b200_plan_sizes(const exadg_b200_plan * p, int64_t * n_owned, int64_t * n_ghost, int64_t * global_offset, int * n_peers)
+{
+  if (!p) return EXADG_B200_ERR_ARG;
+  if (n_owned) *n_owned = p->mesh.n_owned; if (n_ghost) *n_ghost = p->mesh.n_ghost;
+  if (global_offset) *global_offset = p->mesh.global_offset; if (n_peers) *n_peers = (int)p->mesh.peers.size();
+  return EXADG_B200_OK;
+}
+int exadg_b200_plan_peer(const exadg_b200_plan * p, int i, int * peer_rank, int64_t * n_send, int64_t * recv_begin, int64_t * recv_count, int32_t * send_cells)
+{
+  if (!p || i < 0 || i >= (int)p->mesh.peers.size()) return EXADG_B200_ERR_ARG;
+  const PeerPlan & pp = p->mesh.peers[i];
+  if (peer_rank) *peer_rank = pp.rank; if (n_send) *n_send = (int64_t)pp.send_cells.size();
+  if (recv_begin) *recv_begin = pp.recv_begin; if (recv_count) *recv_count = pp.recv_count;
+  if (send_cells) std::memcpy(send_cells, pp.send_cells.data(), pp.send_cells.size() * sizeof(int32_t));
+  return EXADG_B200_OK;
+}
+int exadg_b200_plan_tables(const exadg_b200_plan * p, int32_t * neighbors, int64_t * ghost_global_ids)
+{
+  if (!p) return EXADG_B200_ERR_ARG;
+  if (neighbors) std::memcpy(neighbors, p->mesh.nb.data(), p->mesh.nb.size() * sizeof(int32_t));
+  if (ghost_global_ids) std::memcpy(ghost_global_ids, p->mesh.ghost_global.data(), p->mesh.ghost_global.size() * sizeof(int64_t));
+  return EXADG_B200_OK;
+}
+
 int exadg_b200_halo_n_peers(const exadg_b200_operator * op) { return op ? (int)op->mesh.peers.size() : -1; }
 int exadg_b200_halo_peer(const exadg_b200_operator * op, int i, int * peer_rank, int64_t * send_cells, int64_t * recv_begin, int64_t * recv_cells)
 {

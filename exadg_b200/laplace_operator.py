@@ -322,3 +322,34 @@ def fp64_peak():
     a, b = C.c_double(), C.c_double()
     _check(_lib().exadg_b200_fp64_peak(C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+class PartitionPlan:
+    """Host-only partition / halo plan of a hypercube grid (no GPU needed): what MatrixFree's
+    Utilities::MPI::Partitioner holds for the ghost import of src (SURVEY 8e)."""
+
+    def __init__(self, n_subdivisions, n_refinements, rank, world, boundary=(0,) * 6):
+        L = _lib()
+        d = _desc(1, n_subdivisions, n_refinements, 1, 0.0, 2, boundary, 1.0, rank, world, False)
+        h = C.c_void_p()
+        _check(L.exadg_b200_plan_create(C.byref(d), C.byref(h)))
+        self._h = h
+        no, ng, off, npeer = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int()
+        _check(L.exadg_b200_plan_sizes(h, C.byref(no), C.byref(ng), C.byref(off), C.byref(npeer)))
+        self.n_owned, self.n_ghost, self.global_offset = no.value, ng.value, off.value
+        self.neighbors = np.zeros((self.n_owned, 6), dtype=np.int32)
+        self.ghost_global_ids = np.zeros(self.n_ghost, dtype=np.int64)
+        _check(L.exadg_b200_plan_tables(h, self.neighbors.ctypes.data_as(C.POINTER(C.c_int32)),
+                                        self.ghost_global_ids.ctypes.data_as(C.POINTER(C.c_int64))))
+        self.peers = []
+        for i in range(npeer.value):
+            r, ns, rb, rc = C.c_int(), C.c_int64(), C.c_int64(), C.c_int64()
+            _check(L.exadg_b200_plan_peer(h, i, C.byref(r), C.byref(ns), C.byref(rb), C.byref(rc), None))
+            cells = np.zeros(ns.value, dtype=np.int32)
+            _check(L.exadg_b200_plan_peer(h, i, None, None, None, None, cells.ctypes.data_as(C.POINTER(C.c_int32))))
+            self.peers.append(dict(rank=r.value, send_cells=cells, recv_begin=rb.value, recv_count=rc.value))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _lib().exadg_b200_plan_destroy(h)

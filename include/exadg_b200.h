@@ -143,6 +143,15 @@ int exadg_b200_ghost_global_ids(const exadg_b200_operator *op, int64_t *ids_host
 double *exadg_b200_ghost_buffer(exadg_b200_operator *op);        /* device, [n_ghost][(k+1)^3] */
 int exadg_b200_halo_pack(exadg_b200_operator *op, int i, const double *src, double *send_buffer); /* device buffers */
 
+/* Host-only view of the partition and halo plan of a hypercube grid (no CUDA call is made): the p4est-style
+ * partition (I/grid/grid_utilities.h:188-207), the owned cells each peer needs and the ghost ordering. */
+typedef struct exadg_b200_plan exadg_b200_plan;
+int exadg_b200_plan_create(const exadg_b200_hypercube_desc *desc, exadg_b200_plan **plan);
+int exadg_b200_plan_destroy(exadg_b200_plan *plan);
+int exadg_b200_plan_sizes(const exadg_b200_plan *plan, int64_t *n_owned, int64_t *n_ghost, int64_t *global_offset, int *n_peers);
+int exadg_b200_plan_peer(const exadg_b200_plan *plan, int i, int *peer_rank, int64_t *n_send, int64_t *recv_begin, int64_t *recv_count, int32_t *send_cells);
+int exadg_b200_plan_tables(const exadg_b200_plan *plan, int32_t *neighbors, int64_t *ghost_global_ids);
+
 /* FP64 pipe microbenchmarks used for the roofline denominators (DFMA and DMMA rates) */
 int exadg_b200_fp64_peak(double *dfma_tflops, double *dmma_tflops);
 

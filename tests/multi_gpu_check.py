@@ -1,0 +1,72 @@
+"""Multi-GPU parity check (run under torchrun, one rank per GPU): the partitioned vmult / CG must match the
+single-partition run of the same library (which the -m gpu tests pin against the oracle).
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tests/multi_gpu_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import exadg_b200  # noqa: E402
+from exadg_b200.laplace_operator import nccl_unique_id  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    nccl_id = bytes(idt.cpu().numpy().tobytes())
+    ok = True
+    for (degree, n_sub, refine, deformation, bc) in [(4, 3, 2, 0.0, (0,) * 6), (3, 1, 3, 0.1, (0,) * 6), (2, 2, 2, 0.15, (1, 2, 1, 1, 1, 1)), (5, 1, 2, 0.0, (0,) * 6)]:
+        op = exadg_b200.LaplaceOperator.hypercube(degree, n_sub, refine, 1, deformation, 2, bc, 1.0, rank=rank, world=world)
+        op.init_nccl(nccl_id)
+        n3 = (degree + 1) ** 3
+        n_global = op.n()
+        g = torch.Generator().manual_seed(123)
+        x_global = (torch.rand(n_global, dtype=torch.float64, generator=g) * 2 - 1)
+        lo = (n_global // n3) * rank // world * n3
+        src = x_global[lo:lo + op.local_size()].cuda()
+        dst = op.initialize_dof_vector()
+        op.vmult(dst, src)
+        # reference: the whole problem on this GPU alone
+        ref = exadg_b200.LaplaceOperator.hypercube(degree, n_sub, refine, 1, deformation, 2, bc, 1.0)
+        y_ref = ref.initialize_dof_vector()
+        ref.vmult(y_ref, x_global.cuda())
+        err = (dst - y_ref[lo:lo + op.local_size()]).norm() / y_ref.norm()
+        # CG with Jacobi: iteration counts equal to the single-partition solve
+        its = None
+        if bc != (0,) * 6:
+            b = y_ref.clone()
+            s1 = exadg_b200.KrylovSolverCG(ref, exadg_b200.JacobiPreconditioner(ref), exadg_b200.SolverData(2000, 1e-20, 1e-8))
+            x1 = ref.initialize_dof_vector()
+            n1 = s1.solve(x1, b)
+            s2 = exadg_b200.KrylovSolverCG(op, exadg_b200.JacobiPreconditioner(op), exadg_b200.SolverData(2000, 1e-20, 1e-8))
+            x2 = op.initialize_dof_vector()
+            n2 = s2.solve(x2, b[lo:lo + op.local_size()].clone())
+            its = (n1, n2)
+            ok &= abs(n1 - n2) <= 1
+            ok &= ((x2 - x1[lo:lo + op.local_size()]).norm() / x1.norm()).item() < 1e-6
+        flag = torch.tensor([err.item()], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print("k=%d cells=%d^3 deformation=%g bc=%s cartesian_path=%d ghosts(rank0)=%d max rel err %.3e cg its %s"
+                  % (degree, n_sub << refine, deformation, bc, op.is_cartesian_path, op.n_cells_ghost, flag.item(), its), flush=True)
+        ok &= flag.item() < 1e-12
+        del op, ref
+    dist.barrier()
+    if rank == 0:
+        print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
