@@ -19,15 +19,18 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        idt.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
-    dist.broadcast(idt, 0)
-    nccl_id = bytes(idt.cpu().numpy().tobytes())
+    def fresh_nccl_id():
+        # one unique id per communicator (an id cannot be reused for a second ncclCommInitRank)
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        return bytes(idt.cpu().numpy().tobytes())
+
     ok = True
     for (degree, n_sub, refine, deformation, bc) in [(4, 3, 2, 0.0, (0,) * 6), (3, 1, 3, 0.1, (0,) * 6), (2, 2, 2, 0.15, (1, 2, 1, 1, 1, 1)), (5, 1, 2, 0.0, (0,) * 6)]:
         op = exadg_b200.LaplaceOperator.hypercube(degree, n_sub, refine, 1, deformation, 2, bc, 1.0, rank=rank, world=world)
-        op.init_nccl(nccl_id)
+        op.init_nccl(fresh_nccl_id())
         n3 = (degree + 1) ** 3
         n_global = op.n()
         g = torch.Generator().manual_seed(123)
