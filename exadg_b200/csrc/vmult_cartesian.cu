@@ -82,7 +82,7 @@ __device__ __forceinline__ void tma_store_1d(void * gdst, const void * smem_src,
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-template<int N> struct CartCfg { static constexpr int B = (N >= 4) ? 32 : 64; };
+template<int N> struct CartCfg { static constexpr int B = (N >= 6) ? 16 : ((N >= 4) ? 32 : 64); };
 
 template<int N>
 __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_cartesian_kernel(const __grid_constant__ CartTables<N> T, const CartArgs A)
@@ -409,7 +409,7 @@ void launch_n(const DeviceOperator & op, const CartPlan & plan, double * dst, co
 }
 } // namespace
 
-bool cartesian_supported(int n) { return n >= 2 && n <= 5; }
+bool cartesian_supported(int n) { return n >= 2 && n <= 8; }
 
 template<int N>
 void store_tables(CartPlan & P, const DeviceOperator & op)
@@ -427,7 +427,7 @@ size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh)
   CartPlan & P = *Pp;
   P.n = op.n;
   const int N = op.n;
-  P.B = (N >= 4) ? 32 : 64;
+  P.B = (N >= 6) ? 16 : ((N >= 4) ? 32 : 64);
   P.n_batches = (int)((mesh.n_owned + P.B - 1) / P.B);
   std::vector<std::vector<int2>> lists(P.n_batches);
   std::vector<int32_t> interior, boundary;
@@ -464,6 +464,9 @@ size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh)
     case 3: store_tables<3>(P, op); break;
     case 4: store_tables<4>(P, op); break;
     case 5: store_tables<5>(P, op); break;
+    case 6: store_tables<6>(P, op); break;
+    case 7: store_tables<7>(P, op); break;
+    case 8: store_tables<8>(P, op); break;
     default: delete Pp; return 0;
   }
   op.cart_plan = Pp;
@@ -489,7 +492,10 @@ void launch_vmult_cartesian_part(const DeviceOperator & op, double * dst, const 
     case 3: launch_n<3>(op, *plan, dst, src, add, which, stream); break;
     case 4: launch_n<4>(op, *plan, dst, src, add, which, stream); break;
     case 5: launch_n<5>(op, *plan, dst, src, add, which, stream); break;
-    default: throw std::runtime_error("Cartesian fast path supports degrees 1..4");
+    case 6: launch_n<6>(op, *plan, dst, src, add, which, stream); break;
+    case 7: launch_n<7>(op, *plan, dst, src, add, which, stream); break;
+    case 8: launch_n<8>(op, *plan, dst, src, add, which, stream); break;
+    default: throw std::runtime_error("Cartesian fast path supports degrees 1..7");
   }
 }
 

@@ -35,7 +35,7 @@ def gpu_vmult(op, x):
 @pytest.mark.parametrize("grid", [(1, 2), (3, 1)])
 def test_vmult_cartesian_periodic(degree, grid):
     op, ref = make_pair(degree, *grid)
-    assert op.is_cartesian_path == (1 if degree <= 4 else 0)
+    assert op.is_cartesian_path == 1
     x = synthetic_vector(ref.n_dofs)
     assert rel(gpu_vmult(op, x), ref.vmult(x)) < TOL
 
