@@ -51,8 +51,10 @@ __device__ __forceinline__ void sweep(const double * __restrict__ M, const doubl
 
 // MODE 0: dst (+)= A src.  MODE 1: diagonal (unit vectors column by column, neighbour function zero:
 // do_face_int_integral, laplace_operator.cpp:165-191; operator_base.cpp:1552-1616).
+// resident CTAs per SM the register allocation is tuned for (measured per degree on B200, curved periodic box)
+template<int N> struct GenCfg { static constexpr int MIN_BLOCKS = (N == 5 || N == 7) ? 2 : 4; };
 template<int N, int CPB, int MODE>
-__global__ void __launch_bounds__(N * N * CPB) vmult_general_kernel(const __grid_constant__ GenTables<N> T, const GenArgs A)
+__global__ void __launch_bounds__(N * N * CPB, GenCfg<N>::MIN_BLOCKS) vmult_general_kernel(const __grid_constant__ GenTables<N> T, const GenArgs A)
 {
   constexpr int NP = N | 1;          // odd x-extent: conflict-free 64-bit shared accesses in every direction
   constexpr int SZ = NP * N * N;
