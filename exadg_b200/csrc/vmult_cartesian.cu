@@ -21,6 +21,7 @@
 // exchanged through shared memory; traces of cells outside the batch (host-precomputed list) are
 // computed once per batch from global memory/L2.  Every DoF of dst is written once, coalesced.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "operator.cuh"
@@ -345,6 +346,403 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
   }
 }
 
+
+// =====================================================================================================
+// Pipelined variant (used for n = 5): persistent CTAs of 4 warps on 24-cell batches.
+//  * 24 cells x 5 planes = 120 plane threads = 4 warps: one warp per SM sub-partition, so the FP64 pipes of the
+//    four sub-partitions carry equal work (5-warp CTAs load them 2:1:1:1 and stall at every barrier);
+//  * 3 CTAs per SM (<= 75 KB shared memory, <= 168 registers) instead of 2;
+//  * the lines of out-of-batch neighbours are fetched one sweep ahead into registers (x lines at the end of the
+//    previous batch, y lines before the x sweep, z lines before the y sweep) and reduced to traces into one
+//    shared buffer that is reused by the three directions: their latency hides behind the FP64 work;
+//  * the bulk copy (TMA) of the next batch starts as soon as the z sweep has consumed the current one; the result
+//    is finished in place in Tt and leaves through one TMA bulk store.
+// =====================================================================================================
+template<int N> struct PipeCfg { static constexpr int B = 24; static constexpr int NT = 128; static constexpr int E = 5; };
+
+struct PipeArgs
+{
+  const int32_t * nb;        // [owned][6]
+  const int2 * halo;         // [n_batches][HL] (lc<<3|f, neighbour cell), sorted by direction
+  const int4 * halo_cnt;     // [n_batches] numbers of x-, y-, z-face entries
+  const int32_t * batches;   // optional list of batch ids
+  const double * src; const double * ghost; double * dst;
+  int64_t n_owned; int n_items; int HL; int HD; int add;
+};
+
+// lines (direction D) of the neighbour cells of entries e0 + grp + q * n_grp (q < E) -> registers
+template<int N, int D, int E>
+__device__ __forceinline__ void pipe_load(double (&x)[E][N], const int2 * hl, int e0, int e1, int grp, int n_grp, int ab, const double * src, const double * ghost, int64_t n_owned)
+{
+  constexpr int N2 = N * N, N3 = N2 * N;
+  constexpr int sd = (D == 0) ? 1 : (D == 1 ? N : N2);
+  constexpr int s1 = (D == 0) ? N : 1, s2 = (D == 2) ? N : N2;
+  const int off = (ab % N) * s1 + (ab / N) * s2;
+#pragma unroll
+  for (int q = 0; q < E; ++q) {
+    const int e = e0 + grp + q * n_grp;
+    if (e < e1) {
+      const int2 h = hl[e];
+      const double * line = ((h.y < n_owned) ? src + (size_t)h.y * N3 : ghost + (size_t)(h.y - n_owned) * N3) + off;
+#pragma unroll
+      for (int i = 0; i < N; ++i) x[q][i] = line[i * sd];
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) x[q][i] = 0.0; // defined on every path: the registers are dead until the next load
+    }
+  }
+}
+// registers -> end value / end derivative in the trace buffer (slot = index within the direction's entry list)
+template<int N, int E, typename Tab>
+__device__ __forceinline__ void pipe_reduce(const Tab & T, const double (&x)[E][N], const int2 * hl, int e0, int e1, int grp, int n_grp, int ab, double * HV, double * HG)
+{
+  constexpr int N2 = N * N;
+#pragma unroll
+  for (int q = 0; q < E; ++q) {
+    const int e = e0 + grp + q * n_grp;
+    if (e < e1) {
+      const int2 h = hl[e];
+      double g0 = T.fd[0][0] * x[q][0], g1 = T.fd[1][0] * x[q][0];
+#pragma unroll
+      for (int i = 1; i < N; ++i) { g0 = fma(T.fd[0][i], x[q][i], g0); g1 = fma(T.fd[1][i], x[q][i], g1); }
+      const bool sp = !(h.x & 1); // the neighbour is entered through the side opposite to ours
+      HV[(e - e0) * N2 + ab] = sp ? x[q][N - 1] : x[q][0];
+      HG[(e - e0) * N2 + ab] = sp ? g1 : g0;
+    }
+  }
+}
+// entries beyond the pipelined depth (irregular batches only): fetched and reduced on the spot
+template<int N, int D, typename Tab>
+__device__ __forceinline__ void pipe_rest(const Tab & T, const int2 * hl, int e0, int e_from, int e1, int grp, int n_grp, int ab, const double * src, const double * ghost,
+                                          int64_t n_owned, double * HV, double * HG)
+{
+  for (int eb = e_from; eb < e1; eb += n_grp) {
+    double x[1][N];
+    pipe_load<N, D, 1>(x, hl, eb, e1, grp, n_grp, ab, src, ghost, n_owned);
+    const int e = eb + grp;
+    if (e < e1) {
+      constexpr int N2 = N * N;
+      const int2 h = hl[e];
+      double g0 = T.fd[0][0] * x[0][0], g1 = T.fd[1][0] * x[0][0];
+#pragma unroll
+      for (int i = 1; i < N; ++i) { g0 = fma(T.fd[0][i], x[0][i], g0); g1 = fma(T.fd[1][i], x[0][i], g1); }
+      const bool sp = !(h.x & 1);
+      HV[(e - e0) * N2 + ab] = sp ? x[0][N - 1] : x[0][0];
+      HG[(e - e0) * N2 + ab] = sp ? g1 : g0;
+    }
+  }
+}
+
+#define PIPE_SYNC() asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory")
+
+template<int N>
+__global__ void __launch_bounds__(PipeCfg<N>::NT, 3) vmult_cartesian_pipe_kernel(const __grid_constant__ CartTables<N> T, const PipeArgs A)
+{
+  constexpr int B = PipeCfg<N>::B, NT = PipeCfg<N>::NT, E = PipeCfg<N>::E;
+  constexpr int N2 = N * N, N3 = N2 * N;
+  static_assert((N2 & 1) == 1, "pipelined kernel: odd n (contiguous cells, TMA)");
+  constexpr int NGRP = NT / N2;
+  extern __shared__ __align__(128) double smem[];
+  double * U = smem;                   // [B][N3] src values of the batch (TMA destination)
+  double * Tt = U + B * N3;            // [B][N3] partial results, finally the result (TMA source)
+  double * GN = Tt + B * N3;           // [B][2][N2] own end derivatives of the current direction
+  double * HV = GN + B * 2 * N2;       // [HD][N2] end values of out-of-batch neighbours, current direction
+  double * HG = HV + (size_t)A.HD * N2; // [HD][N2] end derivatives
+  int2 * hl2 = reinterpret_cast<int2 *>(HG + (size_t)A.HD * N2); // [2][HL] halo lists (current / next batch)
+  int * nb2 = reinterpret_cast<int *>(hl2 + 2 * A.HL);           // [2][B][6] neighbour tables
+  int * slotS = nb2 + 2 * B * 6;                                 // [B][6] index of the face in its direction's entry list
+  int4 * cntS = reinterpret_cast<int4 *>((reinterpret_cast<uintptr_t>(slotS + B * 6) + 15) & ~uintptr_t(15)); // [2]
+  uint64_t * bar = reinterpret_cast<uint64_t *>(cntS + 2);
+
+  const int t = threadIdx.x, lc = t / N, s = t % N;
+  const int grp = t / N2, ab = t % N2;
+  const bool hthread = grp < NGRP;
+  uint32_t upar = 0;
+  if (t == 0) mbar_init(bar, 1);
+  auto batch_of = [&](int it) { return A.batches ? A.batches[it] : it; };
+  double hx[E][N]; // lines of out-of-batch neighbours, one sweep ahead
+
+  // ---- prologue: tables, bulk copy and x lines of the first batch ----
+  int cur = 0;
+  if ((int)blockIdx.x < A.n_items) {
+    const int bt = batch_of(blockIdx.x);
+    const int64_t c0 = (int64_t)bt * B;
+    const int nv = (int)min((int64_t)B, A.n_owned - c0);
+    const int4 hc0 = A.halo_cnt[bt];
+    if (t == 0) cntS[0] = hc0;
+    for (int i = t; i < B * 6; i += NT) nb2[i] = (i / 6 < nv) ? A.nb[c0 * 6 + i] : -1;
+    for (int i = t; i < hc0.x + hc0.y + hc0.z; i += NT) hl2[i] = A.halo[(size_t)bt * A.HL + i];
+  }
+  PIPE_SYNC();
+  if ((int)blockIdx.x < A.n_items) {
+    const int bt = batch_of(blockIdx.x);
+    const int64_t c0 = (int64_t)bt * B;
+    const uint32_t by = (uint32_t)((int)min((int64_t)B, A.n_owned - c0) * N3 * sizeof(double));
+    if (t == 0 && by % 16 == 0) { mbar_expect_tx(bar, by); tma_load_1d(U, A.src + c0 * N3, by, bar); }
+    const int4 c = cntS[0];
+    if (hthread) pipe_load<N, 0, E>(hx, hl2, 0, c.x, grp, NGRP, ab, A.src, A.ghost, A.n_owned);
+  }
+
+  for (int it = blockIdx.x; it < A.n_items; it += gridDim.x, cur ^= 1) {
+    const int batch = batch_of(it);
+    const int64_t b0 = (int64_t)batch * B;
+    const int nvalid = (int)min((int64_t)B, A.n_owned - b0);
+    const bool valid = lc < nvalid;
+    const int2 * hl = hl2 + cur * A.HL;
+    const int * nbS = nb2 + cur * B * 6;
+    const uint32_t bytes = (uint32_t)(nvalid * N3 * sizeof(double));
+    const bool use_tma = (bytes % 16 == 0);
+    const int4 hc = cntS[cur];
+    const int ex = hc.x, ey = hc.x + hc.y, ez = hc.x + hc.y + hc.z;
+
+    // slot table: position of every out-of-batch face in its direction's list
+    for (int e = t; e < ez; e += NT) { const int2 h = hl[e]; const int d = (h.x & 7) >> 1; slotS[(h.x >> 3) * 6 + (h.x & 7)] = e - (d == 0 ? 0 : (d == 1 ? ex : ey)); }
+    if (!use_tma) for (int i = t; i < nvalid * N3; i += NT) U[i] = A.src[b0 * N3 + i]; // ragged last batch
+    // tables of the next batch -> registers
+    const int itn = it + gridDim.x;
+    const bool has_next = itn < A.n_items;
+    int pre_nb[(B * 6 + NT - 1) / NT]; int2 pre_hl = make_int2(0, 0); int4 pre_cnt = make_int4(0, 0, 0, 0);
+    if (has_next) {
+      const int bn = batch_of(itn);
+      const int64_t c0 = (int64_t)bn * B;
+      const int nv = (int)min((int64_t)B, A.n_owned - c0);
+#pragma unroll
+      for (int q = 0; q < (B * 6 + NT - 1) / NT; ++q) { const int i = t + q * NT; pre_nb[q] = (i < B * 6 && i / 6 < nv) ? A.nb[c0 * 6 + i] : -1; }
+      pre_cnt = A.halo_cnt[bn];
+      if (t < A.HL) pre_hl = A.halo[(size_t)bn * A.HL + t];
+    }
+    // x traces (lines were fetched during the previous batch), y lines on their way
+    if (hthread) {
+      pipe_reduce<N, E>(T, hx, hl, 0, ex, grp, NGRP, ab, HV, HG);
+      if (ex > E * NGRP) pipe_rest<N, 0>(T, hl, 0, E * NGRP, ex, grp, NGRP, ab, A.src, A.ghost, A.n_owned, HV, HG);
+      pipe_load<N, 1, E>(hx, hl, ex, ey, grp, NGRP, ab, A.src, A.ghost, A.n_owned);
+    }
+    if (use_tma) { mbar_wait(bar, upar); upar ^= 1; }
+    PIPE_SYNC();
+
+    double u[N][N], acc[N][N];
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) { u[j][i] = U[lc * N3 + s * N2 + i + N * j]; acc[j][i] = 0.0; }
+    }
+    // ---- x and y sweeps on the register plane z = s ----
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      if (valid) {
+        double g0[N], g1[N];
+#pragma unroll
+        for (int l = 0; l < N; ++l) { const double x = (d == 0) ? u[l][0] : u[0][l]; g0[l] = T.fd[0][0] * x; g1[l] = T.fd[1][0] * x; }
+#pragma unroll
+        for (int m = 1; m < N; ++m)
+#pragma unroll
+          for (int l = 0; l < N; ++l) {
+            const double x = (d == 0) ? u[l][m] : u[m][l];
+            g0[l] = fma(T.fd[0][m], x, g0[l]); g1[l] = fma(T.fd[1][m], x, g1[l]);
+          }
+#pragma unroll
+        for (int l = 0; l < N; ++l) { GN[(lc * 2 + 0) * N2 + l + N * s] = g0[l]; GN[(lc * 2 + 1) * N2 + l + N * s] = g1[l]; }
+      }
+      PIPE_SYNC();
+      if (valid) {
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+          const int f = 2 * d + side;
+          const int nbl = nbS[lc * 6 + f] - (int)b0;
+          const bool inb = (nbl >= 0 && nbl < B);
+          const int slot = slotS[lc * 6 + f];
+          const double hs = side ? 0.5 : -0.5; // 1/2 sigma_s
+          double vn[N], tt[N];
+#pragma unroll
+          for (int l = 0; l < N; ++l) {
+            double gn;
+            if (inb) {
+              const int endn = side ? 0 : N - 1; // neighbour's end node facing us
+              vn[l] = (d == 0) ? U[nbl * N3 + s * N2 + endn + N * l] : U[nbl * N3 + s * N2 + l + N * endn];
+              gn = GN[(nbl * 2 + (side ^ 1)) * N2 + l + N * s];
+            } else {
+              vn[l] = HV[slot * N2 + l + N * s]; gn = HG[slot * N2 + l + N * s];
+            }
+            tt[l] = fma(hs, gn, T.tau_hat[d] * vn[l]);
+          }
+#pragma unroll
+          for (int m = 0; m < N; ++m)
+#pragma unroll
+            for (int l = 0; l < N; ++l) {
+              if (d == 0) acc[l][m] = fma(T.P[d][side][m], vn[l], acc[l][m]); else acc[m][l] = fma(T.P[d][side][m], vn[l], acc[m][l]);
+            }
+#pragma unroll
+          for (int m = 0; m < N; ++m)
+#pragma unroll
+            for (int l = 0; l < N; ++l) {
+              if (d == 0) acc[l][m] = fma(T.Q[d][side][m], tt[l], acc[l][m]); else acc[m][l] = fma(T.Q[d][side][m], tt[l], acc[m][l]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < N; ++c)
+#pragma unroll
+          for (int l = 0; l < N; ++l)
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+              if (d == 0) acc[l][r] = fma(T.G[d][r * N + c], u[l][c], acc[l][r]);
+              else acc[r][l] = fma(T.G[d][r * N + c], u[c][l], acc[r][l]);
+            }
+      }
+      PIPE_SYNC(); // traces and GN of this direction are consumed
+      // traces of the next direction from the lines fetched one sweep ago; lines of the direction after that
+      if (hthread) {
+        if (d == 0) {
+          pipe_reduce<N, E>(T, hx, hl, ex, ey, grp, NGRP, ab, HV, HG);
+          if (ey - ex > E * NGRP) pipe_rest<N, 1>(T, hl, ex, ex + E * NGRP, ey, grp, NGRP, ab, A.src, A.ghost, A.n_owned, HV, HG);
+          pipe_load<N, 2, E>(hx, hl, ey, ez, grp, NGRP, ab, A.src, A.ghost, A.n_owned);
+        } else {
+          pipe_reduce<N, E>(T, hx, hl, ey, ez, grp, NGRP, ab, HV, HG);
+          if (ez - ey > E * NGRP) pipe_rest<N, 2>(T, hl, ey, ey + E * NGRP, ez, grp, NGRP, ab, A.src, A.ghost, A.n_owned, HV, HG);
+        }
+      }
+    }
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) Tt[lc * N3 + s * N2 + i + N * j] = acc[j][i];
+    }
+    // ---- z sweep: this thread owns the n lines (i, j = s) ----
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int k = 0; k < N; ++k) u[i][k] = U[lc * N3 + k * N2 + i + N * s];
+      double g0[N], g1[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) { g0[i] = T.fd[0][0] * u[i][0]; g1[i] = T.fd[1][0] * u[i][0]; }
+#pragma unroll
+      for (int k = 1; k < N; ++k)
+#pragma unroll
+        for (int i = 0; i < N; ++i) { g0[i] = fma(T.fd[0][k], u[i][k], g0[i]); g1[i] = fma(T.fd[1][k], u[i][k], g1[i]); }
+#pragma unroll
+      for (int i = 0; i < N; ++i) { GN[(lc * 2 + 0) * N2 + i + N * s] = g0[i]; GN[(lc * 2 + 1) * N2 + i + N * s] = g1[i]; }
+    }
+    PIPE_SYNC(); // Tt planes, z traces (GN and HV/HG) visible
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int k = 0; k < N; ++k) acc[i][k] = Tt[lc * N3 + k * N2 + i + N * s];
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        const int nbl = nbS[lc * 6 + 4 + side] - (int)b0;
+        const bool inb = (nbl >= 0 && nbl < B);
+        const int slot = slotS[lc * 6 + 4 + side];
+        double vn[N], tt[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          double gn;
+          if (inb) {
+            const int endn = side ? 0 : N - 1;
+            vn[i] = U[nbl * N3 + endn * N2 + i + N * s];
+            gn = GN[(nbl * 2 + (side ^ 1)) * N2 + i + N * s];
+          } else {
+            vn[i] = HV[slot * N2 + i + N * s]; gn = HG[slot * N2 + i + N * s];
+          }
+          tt[i] = fma(side ? 0.5 : -0.5, gn, T.tau_hat[2] * vn[i]);
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+#pragma unroll
+          for (int i = 0; i < N; ++i) acc[i][k] = fma(T.P[2][side][k], vn[i], acc[i][k]);
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+#pragma unroll
+          for (int i = 0; i < N; ++i) acc[i][k] = fma(T.Q[2][side][k], tt[i], acc[i][k]);
+      }
+#pragma unroll
+      for (int c = 0; c < N; ++c)
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+          for (int r = 0; r < N; ++r) acc[i][r] = fma(T.G[2][r * N + c], u[i][c], acc[i][r]);
+      // mass matrix along z: u <- M acc
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int r = 0; r < N; ++r) u[i][r] = T.M[r * N] * acc[i][0];
+#pragma unroll
+      for (int c = 1; c < N; ++c)
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+          for (int r = 0; r < N; ++r) u[i][r] = fma(T.M[r * N + c], acc[i][c], u[i][r]);
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int r = 0; r < N; ++r) Tt[lc * N3 + r * N2 + i + N * s] = u[i][r];
+    }
+    PIPE_SYNC(); // U and the trace buffers are dead from here on
+    // park the tables of the next batch and start its bulk copy
+    if (has_next) {
+      int * nbN = nb2 + (cur ^ 1) * B * 6;
+#pragma unroll
+      for (int q = 0; q < (B * 6 + NT - 1) / NT; ++q) { const int i = t + q * NT; if (i < B * 6) nbN[i] = pre_nb[q]; }
+      if (t < A.HL) hl2[(cur ^ 1) * A.HL + t] = pre_hl;
+      if (t == 0) {
+        cntS[cur ^ 1] = pre_cnt;
+        const int64_t c0 = (int64_t)batch_of(itn) * B;
+        const uint32_t by = (uint32_t)((int)min((int64_t)B, A.n_owned - c0) * N3 * sizeof(double));
+        if (by % 16 == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_expect_tx(bar, by); tma_load_1d(U, A.src + c0 * N3, by, bar);
+        }
+      }
+    }
+    // ---- mass matrices along x and y on the register plane, in place in Tt ----
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) u[j][i] = Tt[lc * N3 + s * N2 + i + N * j];
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int r = 0; r < N; ++r) acc[j][r] = T.M[r * N] * u[j][0];
+#pragma unroll
+      for (int c = 1; c < N; ++c)
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+          for (int r = 0; r < N; ++r) acc[j][r] = fma(T.M[r * N + c], u[j][c], acc[j][r]);
+#pragma unroll
+      for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int i = 0; i < N; ++i) u[r][i] = T.M[r * N] * acc[0][i];
+#pragma unroll
+      for (int c = 1; c < N; ++c)
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+          for (int i = 0; i < N; ++i) u[r][i] = fma(T.M[r * N + c], acc[c][i], u[r][i]);
+#pragma unroll
+      for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int i = 0; i < N; ++i) Tt[lc * N3 + s * N2 + i + N * r] = u[r][i];
+    }
+    if (use_tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    PIPE_SYNC(); // result complete, parked tables visible
+    // x lines of the next batch -> registers (consumed at the top of the next iteration)
+    {
+      const int4 cn = has_next ? cntS[cur ^ 1] : make_int4(0, 0, 0, 0);
+      if (hthread) pipe_load<N, 0, E>(hx, hl2 + (cur ^ 1) * A.HL, 0, cn.x, grp, NGRP, ab, A.src, A.ghost, A.n_owned);
+    }
+    if (use_tma) {
+      if (t == 0) tma_store_1d(A.dst + b0 * N3, Tt, bytes, A.add != 0); // returns when the source has been read
+    } else {
+      for (int i = t; i < nvalid * N3; i += NT) { if (A.add) A.dst[b0 * N3 + i] += Tt[i]; else A.dst[b0 * N3 + i] = Tt[i]; }
+    }
+    PIPE_SYNC(); // Tt may be overwritten by the next batch
+  }
+}
+
 struct CartPlan
 {
   int n = 0, B = 0, H = 0, n_batches = 0;
@@ -352,6 +750,8 @@ struct CartPlan
   int32_t * d_interior = nullptr, * d_boundary = nullptr; int n_interior = 0, n_boundary = 0;
   size_t smem = 0;
   std::vector<char> tables; // CartTables<n> of this operator (depends on h and tau)
+  // pipelined kernel (n = 5)
+  bool pipe = false; int HL = 0, HD = 0, n_sm = 148; int4 * d_cnt4 = nullptr;
 };
 
 template<int N>
@@ -407,6 +807,26 @@ void launch_n(const DeviceOperator & op, const CartPlan & plan, double * dst, co
   vmult_cartesian_kernel<N><<<A.n_items, B * N, plan.smem, stream>>>(T, A);
   CUDA_CHECK(cudaGetLastError());
 }
+template<int N>
+void launch_pipe(const DeviceOperator & op, const CartPlan & plan, double * dst, const double * src, bool add, int which, cudaStream_t stream)
+{
+  const CartTables<N> & T = *reinterpret_cast<const CartTables<N> *>(plan.tables.data());
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {
+    CUDA_CHECK(cudaFuncSetAttribute(vmult_cartesian_pipe_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, vmult_cartesian_pipe_kernel<N>, PipeCfg<N>::NT, plan.smem));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+  }
+  PipeArgs A;
+  A.nb = op.nb; A.halo = plan.d_halo; A.halo_cnt = plan.d_cnt4; A.src = src; A.ghost = op.ghost; A.dst = dst;
+  A.n_owned = op.n_owned; A.HL = plan.HL; A.HD = plan.HD; A.add = add ? 1 : 0;
+  A.batches = which == 0 ? nullptr : (which == 1 ? plan.d_interior : plan.d_boundary);
+  A.n_items = which == 0 ? plan.n_batches : (which == 1 ? plan.n_interior : plan.n_boundary);
+  if (A.n_items == 0) return;
+  const int grid = std::min(A.n_items, plan.n_sm * ctas_per_sm);
+  vmult_cartesian_pipe_kernel<N><<<grid, PipeCfg<N>::NT, plan.smem, stream>>>(T, A);
+  CUDA_CHECK(cudaGetLastError());
+}
 } // namespace
 
 bool cartesian_supported(int n) { return n >= 2 && n <= 8; }
@@ -419,6 +839,8 @@ void store_tables(CartPlan & P, const DeviceOperator & op)
   std::memcpy(P.tables.data(), &T, sizeof(T));
 }
 
+static size_t cartesian_plan_create_fallback(DeviceOperator & op, const HostMesh & mesh);
+
 // builds the batch plan (halo lists, interior/boundary batches, tables); returns the dynamic shared
 // memory per CTA, or 0 if the batch does not fit (caller falls back to the general kernel)
 size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh)
@@ -428,6 +850,9 @@ size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh)
   P.n = op.n;
   const int N = op.n;
   P.B = (N >= 6) ? 16 : ((N >= 4) ? 32 : 64);
+  P.pipe = (N == 5) && !getenv("EXADG_B200_NO_PIPE");
+  if (P.pipe) P.B = PipeCfg<5>::B;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&P.n_sm, cudaDevAttrMultiProcessorCount, dev); if (P.n_sm < 1) P.n_sm = 148; }
   P.n_batches = (int)((mesh.n_owned + P.B - 1) / P.B);
   std::vector<std::vector<int2>> lists(P.n_batches);
   std::vector<int32_t> interior, boundary;
@@ -444,8 +869,26 @@ size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh)
     (ghost ? boundary : interior).push_back(b);
   }
   P.H = std::max(P.H, 1);
+  if (P.pipe) {
+    // entries sorted by direction; the trace buffer holds one direction at a time
+    std::vector<int4> cnt4(P.n_batches);
+    for (int b = 0; b < P.n_batches; ++b) {
+      std::stable_sort(lists[b].begin(), lists[b].end(), [](const int2 & x, const int2 & y) { return ((x.x & 7) >> 1) < ((y.x & 7) >> 1); });
+      int c[3] = {0, 0, 0};
+      for (auto & e : lists[b]) c[(e.x & 7) >> 1]++;
+      cnt4[b] = make_int4(c[0], c[1], c[2], 0);
+      P.HD = std::max(P.HD, std::max(c[0], std::max(c[1], c[2])));
+    }
+    P.HL = P.H; P.HD = std::max(P.HD, 1);
+    const int N2p = N * N, N3p = N2p * N;
+    P.smem = ((size_t)2 * P.B * N3p + (size_t)P.B * 2 * N2p + (size_t)2 * P.HD * N2p) * sizeof(double) + (size_t)2 * P.HL * sizeof(int2)
+             + (size_t)P.B * 18 * sizeof(int) + 64 + 16;
+    if (P.smem > 227 * 1024 - 1024 || P.HL > PipeCfg<5>::NT) { P.pipe = false; P.B = 32; delete Pp; return cartesian_plan_create_fallback(op, mesh); }
+    CUDA_CHECK(cudaMalloc(&P.d_cnt4, cnt4.size() * sizeof(int4)));
+    CUDA_CHECK(cudaMemcpy(P.d_cnt4, cnt4.data(), cnt4.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  }
   const int N2 = N * N, PS = N2 | 1, CS = N * PS;
-  P.smem = ((size_t)2 * P.B * CS + (size_t)P.B * 2 * N2 + (size_t)2 * P.H * N2) * sizeof(double) + (size_t)P.H * sizeof(int2) + (size_t)P.B * 12 * sizeof(int) + 16;
+  if (!P.pipe) P.smem = ((size_t)2 * P.B * CS + (size_t)P.B * 2 * N2 + (size_t)2 * P.H * N2) * sizeof(double) + (size_t)P.H * sizeof(int2) + (size_t)P.B * 12 * sizeof(int) + 16;
   if (P.smem > 227 * 1024 - 1024) { delete Pp; return 0; } // does not fit: caller falls back to the general kernel
   std::vector<int2> flat((size_t)P.n_batches * P.H, make_int2(0, 0));
   std::vector<int32_t> cnt(P.n_batches);
@@ -473,11 +916,19 @@ size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh)
   return P.smem;
 }
 
+static size_t cartesian_plan_create_fallback(DeviceOperator & op, const HostMesh & mesh)
+{
+  setenv("EXADG_B200_NO_PIPE", "1", 1); // irregular batches: the 5-warp kernel has no such limits
+  const size_t r = cartesian_plan_create(op, mesh);
+  unsetenv("EXADG_B200_NO_PIPE");
+  return r;
+}
+
 void cartesian_plan_destroy(DeviceOperator & op)
 {
   CartPlan * P = static_cast<CartPlan *>(op.cart_plan);
   if (!P) return;
-  cudaFree(P->d_halo); cudaFree(P->d_cnt); cudaFree(P->d_interior); cudaFree(P->d_boundary);
+  cudaFree(P->d_halo); cudaFree(P->d_cnt); cudaFree(P->d_cnt4); cudaFree(P->d_interior); cudaFree(P->d_boundary);
   delete P;
   op.cart_plan = nullptr;
 }
@@ -491,7 +942,7 @@ void launch_vmult_cartesian_part(const DeviceOperator & op, double * dst, const 
     case 2: launch_n<2>(op, *plan, dst, src, add, which, stream); break;
     case 3: launch_n<3>(op, *plan, dst, src, add, which, stream); break;
     case 4: launch_n<4>(op, *plan, dst, src, add, which, stream); break;
-    case 5: launch_n<5>(op, *plan, dst, src, add, which, stream); break;
+    case 5: if (plan->pipe) launch_pipe<5>(op, *plan, dst, src, add, which, stream); else launch_n<5>(op, *plan, dst, src, add, which, stream); break;
     case 6: launch_n<6>(op, *plan, dst, src, add, which, stream); break;
     case 7: launch_n<7>(op, *plan, dst, src, add, which, stream); break;
     case 8: launch_n<8>(op, *plan, dst, src, add, which, stream); break;
