@@ -850,7 +850,7 @@ size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh)
   P.n = op.n;
   const int N = op.n;
   P.B = (N >= 6) ? 16 : ((N >= 4) ? 32 : 64);
-  P.pipe = (N == 5) && !getenv("EXADG_B200_NO_PIPE");
+  P.pipe = (N == 5) && getenv("EXADG_B200_PIPE") && !getenv("EXADG_B200_NO_PIPE"); // experimental (profiles/r01_notes.md): correct, 9 % slower than the 5-warp kernel
   if (P.pipe) P.B = PipeCfg<5>::B;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&P.n_sm, cudaDevAttrMultiProcessorCount, dev); if (P.n_sm < 1) P.n_sm = 148; }
   P.n_batches = (int)((mesh.n_owned + P.B - 1) / P.B);
