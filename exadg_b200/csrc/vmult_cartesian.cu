@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
       for (int side = 0; side < 2; ++side) {
         const int f = 2 * d + side;
         const int nbl = nbS[lc * 6 + f] - (int)b0;
-        const bool inb = (nbl >= 0 && nbl < B);
+        const bool inb = (nbl >= 0 && nbl < nvalid);
         const int slot = slotS[lc * 6 + f];
         const double hs = side ? 0.5 : -0.5; // 1/2 sigma_s
 #pragma unroll
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
       nbl[side] = nbS[lc * 6 + 4 + side] - (int)b0;
-      inb[side] = (nbl[side] >= 0 && nbl[side] < B);
+      inb[side] = (nbl[side] >= 0 && nbl[side] < nvalid);
       slot[side] = slotS[lc * 6 + 4 + side];
     }
 #pragma unroll
@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(PipeCfg<N>::NT, 3) vmult_cartesian_pipe_kernel
         for (int side = 0; side < 2; ++side) {
           const int f = 2 * d + side;
           const int nbl = nbS[lc * 6 + f] - (int)b0;
-          const bool inb = (nbl >= 0 && nbl < B);
+          const bool inb = (nbl >= 0 && nbl < nvalid);
           const int slot = slotS[lc * 6 + f];
           const double hs = side ? 0.5 : -0.5; // 1/2 sigma_s
           double vn[N], tt[N];
@@ -633,7 +633,7 @@ __global__ void __launch_bounds__(PipeCfg<N>::NT, 3) vmult_cartesian_pipe_kernel
 #pragma unroll
       for (int side = 0; side < 2; ++side) {
         const int nbl = nbS[lc * 6 + 4 + side] - (int)b0;
-        const bool inb = (nbl >= 0 && nbl < B);
+        const bool inb = (nbl >= 0 && nbl < nvalid);
         const int slot = slotS[lc * 6 + 4 + side];
         double vn[N], tt[N];
 #pragma unroll

@@ -28,7 +28,8 @@ def main():
         return bytes(idt.cpu().numpy().tobytes())
 
     ok = True
-    for (degree, n_sub, refine, deformation, bc) in [(4, 3, 2, 0.0, (0,) * 6), (3, 1, 3, 0.1, (0,) * 6), (2, 2, 2, 0.15, (1, 2, 1, 1, 1, 1)), (5, 1, 2, 0.0, (0,) * 6)]:
+    # (4, 5, 0) and (5, 3, 0): partitions that end inside a cell batch (ghost indices directly follow a ragged last batch)
+    for (degree, n_sub, refine, deformation, bc) in [(4, 5, 0, 0.0, (0,) * 6), (5, 3, 0, 0.0, (0,) * 6), (2, 5, 0, 0.0, (0,) * 6), (4, 3, 2, 0.0, (0,) * 6), (3, 1, 3, 0.1, (0,) * 6), (2, 2, 2, 0.15, (1, 2, 1, 1, 1, 1)), (5, 1, 2, 0.0, (0,) * 6)]:
         op = exadg_b200.LaplaceOperator.hypercube(degree, n_sub, refine, 1, deformation, 2, bc, 1.0, rank=rank, world=world)
         op.init_nccl(fresh_nccl_id())
         n3 = (degree + 1) ** 3
