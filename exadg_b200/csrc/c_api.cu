@@ -1,6 +1,7 @@
 // C ABI (include/exadg_b200.h) and the host-side operator object behind it.
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -149,7 +150,12 @@ void finish_setup(exadg_b200_operator * op, double ip_factor, bool force_general
     if (cartesian_plan_create(D, M) == 0) D.cartesian = false;
   }
   CUDA_CHECK(cudaStreamCreateWithFlags(&op->stream, cudaStreamNonBlocking));
-  CUDA_CHECK(cudaStreamCreateWithFlags(&op->comm_stream, cudaStreamNonBlocking));
+  {
+    // the halo exchange must not queue behind the interior-cell kernel: highest priority for its stream
+    int lo = 0, hi = 0;
+    CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_CHECK(cudaStreamCreateWithPriority(&op->comm_stream, cudaStreamNonBlocking, hi));
+  }
   CUDA_CHECK(cudaEventCreateWithFlags(&op->ev_packed, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventCreateWithFlags(&op->ev_halo, cudaEventDisableTiming));
   reducer_init(op->red);
@@ -208,7 +214,9 @@ void apply(exadg_b200_operator * op, double * dst, const double * src, bool add)
   }
   CUDA_CHECK(cudaEventRecord(op->ev_packed, op->stream));
   CUDA_CHECK(cudaStreamWaitEvent(op->comm_stream, op->ev_packed, 0));
+  static const bool skip_exchange = getenv("EXADG_B200_SKIP_EXCHANGE") != nullptr; // timing experiments only (results wrong)
   NcclApi & api = nccl();
+  if (!skip_exchange) {
   api.GroupStart();
   for (size_t i = 0; i < M.peers.size(); ++i) {
     const PeerPlan & p = M.peers[i];
@@ -216,6 +224,7 @@ void apply(exadg_b200_operator * op, double * dst, const double * src, bool add)
     api.Recv(op->dev.ghost + p.recv_begin * n3, (size_t)p.recv_count * n3, NCCL_FLOAT64, p.rank, op->comm, op->comm_stream);
   }
   if (api.GroupEnd() != 0) throw std::runtime_error("NCCL halo exchange failed");
+  }
   CUDA_CHECK(cudaEventRecord(op->ev_halo, op->comm_stream));
   launch_vmult(op, dst, src, add, 1);
   CUDA_CHECK(cudaStreamWaitEvent(op->stream, op->ev_halo, 0));
