@@ -196,8 +196,8 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
           const double x = (d == 0) ? u[l][m] : u[m][l];
           g0 = fma(T.fd[0][m], x, g0); g1 = fma(T.fd[1][m], x, g1);
         }
-        GN[(lc * 2 + 0) * N2 + l + N * s] = g0;
-        GN[(lc * 2 + 1) * N2 + l + N * s] = g1;
+        GN[(0 * B + lc) * N2 + s * N + l] = g0;
+        GN[(1 * B + lc) * N2 + s * N + l] = g1;
       }
     }
     __syncthreads();
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
           if (inb) {
             const int endn = side ? 0 : N - 1; // neighbour's end node facing us
             vn = (d == 0) ? U[nbl * CS + s * PS + endn + N * l] : U[nbl * CS + s * PS + l + N * endn];
-            gn = GN[(nbl * 2 + (side ^ 1)) * N2 + l + N * s];
+            gn = GN[((side ^ 1) * B + nbl) * N2 + s * N + l];
           } else {
             vn = HV[slot * N2 + l + N * s]; gn = HG[slot * N2 + l + N * s];
           }
@@ -247,44 +247,49 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
       for (int i = 0; i < N; ++i) Tt[lc * CS + s * PS + i + N * j] = acc[j][i];
   }
 
-  // ---- z sweep: this thread owns the n lines (i, j = s) ----
-  if (valid) {
+  // ---- z sweep: thread (cell lz = t % B, slice sz = t / B) owns the n lines (i, j = sz).  The thread-to-cell map
+  // differs from the plane sweeps on purpose: consecutive lanes touch consecutive cells (stride n^3, odd), which
+  // makes every shared-memory access of this phase bank-conflict free; nothing is carried over in registers.
+  constexpr bool REMAP_Z = (N != 4); // measured: n = 4 (cell stride 68 doubles) is faster with the plane map
+  const int lz = REMAP_Z ? t % B : lc, sz = REMAP_Z ? t / B : s;
+  const bool validz = (sz < N) && (lz < nvalid);
+  if (validz) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       double g0 = 0.0, g1 = 0.0;
 #pragma unroll
       for (int k = 0; k < N; ++k) {
-        const double x = U[lc * CS + k * PS + i + N * s];
+        const double x = U[lz * CS + k * PS + i + N * sz];
         u[i][k] = x; // reuse the plane registers: u[i][k] = value of line i at height k
         g0 = fma(T.fd[0][k], x, g0); g1 = fma(T.fd[1][k], x, g1);
       }
-      GN[(lc * 2 + 0) * N2 + i + N * s] = g0;
-      GN[(lc * 2 + 1) * N2 + i + N * s] = g1;
+      GN[(0 * B + lz) * N2 + sz * N + i] = g0;
+      GN[(1 * B + lz) * N2 + sz * N + i] = g1;
     }
   }
   __syncthreads(); // Tt planes and z traces visible
-  if (valid) {
+  if (validz) {
     int nbl[2], slot[2]; bool inb[2];
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
-      nbl[side] = nbS[lc * 6 + 4 + side] - (int)b0;
+      nbl[side] = nbS[lz * 6 + 4 + side] - (int)b0;
       inb[side] = (nbl[side] >= 0 && nbl[side] < nvalid);
-      slot[side] = slotS[lc * 6 + 4 + side];
+      slot[side] = slotS[lz * 6 + 4 + side];
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       double w[N];
 #pragma unroll
-      for (int k = 0; k < N; ++k) w[k] = Tt[lc * CS + k * PS + i + N * s];
+      for (int k = 0; k < N; ++k) w[k] = Tt[lz * CS + k * PS + i + N * sz];
 #pragma unroll
       for (int side = 0; side < 2; ++side) {
         double vn, gn;
         if (inb[side]) {
           const int endn = side ? 0 : N - 1;
-          vn = U[nbl[side] * CS + endn * PS + i + N * s];
-          gn = GN[(nbl[side] * 2 + (side ^ 1)) * N2 + i + N * s];
+          vn = U[nbl[side] * CS + endn * PS + i + N * sz];
+          gn = GN[((side ^ 1) * B + nbl[side]) * N2 + sz * N + i];
         } else {
-          vn = HV[slot[side] * N2 + i + N * s]; gn = HG[slot[side] * N2 + i + N * s];
+          vn = HV[slot[side] * N2 + i + N * sz]; gn = HG[slot[side] * N2 + i + N * sz];
         }
         const double tt = fma(side ? 0.5 : -0.5, gn, T.tau_hat[2] * vn);
 #pragma unroll
@@ -300,7 +305,7 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
         double y = 0.0;
 #pragma unroll
         for (int c = 0; c < N; ++c) y = fma(T.M[r * N + c], w[c], y);
-        Tt[lc * CS + r * PS + i + N * s] = y;
+        Tt[lz * CS + r * PS + i + N * sz] = y;
       }
     }
   }
