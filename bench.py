@@ -58,7 +58,7 @@ class ClockSampler:
     def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -172,6 +172,8 @@ def run_gpu(args):
             idt.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         op.init_nccl(bytes(idt.cpu().numpy().tobytes()))
+        if args.halo == "p2p":
+            op.enable_p2p(dist)  # ghost import by NVLink peer-memory stores fused into the pack kernel
     op.use_torch_stream()
     n_local, n_global = op.local_size(), op.n()
     g = torch.Generator(device="cuda").manual_seed(42 + rank)
@@ -240,7 +242,8 @@ def run_gpu(args):
                "config": {"workload": "SIPG Laplace vmult, FE_DGQ(%d), Gauss(%d), periodic %s box, %d^3 cells, %d DoFs, src uniform(-1,1)"
                                       % (degree, degree + 1, "Cartesian" if deformation == 0.0 else "sine-deformed (trilinear)", n_sub << refine, n_global),
                           "l2_policy": "inputs larger than L2 (%.0f MB per vector per GPU)" % (n_local * 8 / 1e6),
-                          "kernel_path": "cartesian" if op.is_cartesian_path else "general", "partition": "p4est-style contiguous Morton ranges, %d rank(s)" % world},
+                          "kernel_path": "cartesian" if op.is_cartesian_path else "general", "partition": "p4est-style contiguous Morton ranges, %d rank(s)" % world,
+                          "halo": "none" if world == 1 else ("NVLink peer-memory stores (CUDA IPC), overlapped with interior cells" if args.halo == "p2p" else "NCCL send/recv, overlapped with interior cells")},
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(key),
                             "peak_source": peak_src, "algorithmic_bytes_per_dof": b_alg, "dofs_per_launch": n_global // world},
                "e2e": {"value": n_global * e2e_steps / e2e_s, "unit": "DoFs/s", "h2d_bytes_per_step": n_global * 8, "d2h_bytes_per_step": n_global * 8,
@@ -260,12 +263,13 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--degree", type=int, default=4)
     ap.add_argument("--mesh", default="cartesian", choices=["cartesian", "curvilinear"])
     ap.add_argument("--cells", type=int, default=0, help="cells per direction (default: the workload of the contract)")
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="ghost import transport for N>1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--fp64-peak", action="store_true", help="also report measured DFMA / DMMA rates")

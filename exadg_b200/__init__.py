@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "exadg_b200_nccl_unique_id", "exadg_b200_nccl_init", "exadg_b200_halo_n_peers", "exadg_b200_halo_peer",
     "exadg_b200_halo_send_list", "exadg_b200_ghost_global_ids", "exadg_b200_ghost_buffer", "exadg_b200_halo_pack",
     "exadg_b200_fp64_peak", "exadg_b200_plan_create", "exadg_b200_plan_destroy", "exadg_b200_plan_sizes", "exadg_b200_plan_peer",
-    "exadg_b200_plan_tables",
+    "exadg_b200_plan_tables", "exadg_b200_p2p_export", "exadg_b200_p2p_connect",
 ]
 
 
@@ -103,6 +103,8 @@ def load_library():
     L.exadg_b200_plan_sizes.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_int)]
     L.exadg_b200_plan_peer.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_int32)]
     L.exadg_b200_plan_tables.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(i64)]
+    L.exadg_b200_p2p_export.argtypes = [vp, C.c_char_p, C.POINTER(i64)]
+    L.exadg_b200_p2p_connect.argtypes = [vp, C.c_char_p, C.POINTER(i64)]
     _lib = L
     return L
 

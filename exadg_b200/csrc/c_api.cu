@@ -61,6 +61,48 @@ __global__ void pack_cells_kernel(const double * __restrict__ src, const int32_t
   }
 }
 
+// ---- NVLink peer-memory halo exchange (no NCCL in the data path) ------------------------------------------
+// Every rank maps its peers' ghost buffers (CUDA IPC).  One kernel gathers the owned cells each peer needs and
+// stores them straight into that peer's ghost range over NVLink (pack + put fused); a signal kernel then
+// publishes the epoch in the peer's flag slot; the consumer's wait kernel (stream-ordered before the cells that
+// touch ghosts) spins on its own flags.  Ghost buffers are double-buffered by epoch parity: a peer can be at most
+// one vmult ahead (it needs our data of that vmult to finish it), so no back-pressure handshake is needed.
+constexpr int MAX_PEERS = 16;
+struct PutArgs
+{
+  const int32_t * cells[MAX_PEERS]; int64_t n_cells[MAX_PEERS]; double * dst[MAX_PEERS];
+  long long * peer_flag[MAX_PEERS]; // slot of this rank in the peer's flag array
+  int peer_rank[MAX_PEERS];
+  int n_peers;
+};
+__global__ void put_cells_kernel(const PutArgs a, const double * __restrict__ src, int n3)
+{
+  const int p = blockIdx.y;
+  const int32_t * __restrict__ cells = a.cells[p];
+  double * __restrict__ dst = a.dst[p]; // peer memory
+  const int64_t total = a.n_cells[p] * n3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i / n3; const int k = (int)(i % n3);
+    dst[i] = src[(int64_t)cells[c] * n3 + k];
+  }
+}
+__global__ void signal_peers_kernel(const PutArgs a, long long epoch)
+{
+  const int p = threadIdx.x;
+  if (p < a.n_peers) {
+    __threadfence_system(); // the stores of put_cells_kernel (previous kernel on this stream) are performed
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(a.peer_flag[p]), "l"(epoch) : "memory");
+  }
+}
+__global__ void wait_peers_kernel(const PutArgs a, const long long * my_flags, long long epoch)
+{
+  const int p = threadIdx.x;
+  if (p < a.n_peers) {
+    long long v;
+    do { asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(my_flags + a.peer_rank[p]) : "memory"); } while (v < epoch);
+  }
+}
+
 // closed-form diagonal on the uniform periodic Cartesian box: A = sum_d c_d (M x M x L_d)  =>
 // A_ii = sum_d c_d M_aa M_bb (L_d)_cc, identical for every cell
 __global__ void cartesian_diagonal_kernel(double * __restrict__ diag, int64_t n_dofs, int n, const double * __restrict__ cell_diag, int add)
@@ -87,6 +129,11 @@ struct exadg_b200_operator
   void * comm = nullptr; bool own_comm = false;
   std::vector<int32_t *> d_send_lists; std::vector<double *> d_send_bufs;
   int32_t * d_interior = nullptr, * d_boundary = nullptr; int64_t n_interior = 0, n_boundary = 0;
+  // peer-memory halo (NVLink): one region [ghost A | ghost B | flags[world]] mapped by all peers
+  bool p2p = false; char * p2p_region = nullptr; size_t p2p_ghost_bytes = 0; long long p2p_epoch = 0;
+  std::vector<void *> p2p_peer_regions; // opened IPC mappings, indexed like mesh.peers
+  std::vector<int64_t> p2p_peer_recv_begin;
+  double * ghost_alloc = nullptr; // the ghost buffer of the NCCL path (dev.ghost points into p2p_region once p2p is on)
   // work vectors
   double * w[4] = {nullptr, nullptr, nullptr, nullptr};
   double * d_cell_diag = nullptr;
@@ -204,8 +251,38 @@ void apply(exadg_b200_operator * op, double * dst, const double * src, bool add)
   if (dst == src) throw std::invalid_argument("dst and src must not alias");
   HostMesh & M = op->mesh;
   if (M.world <= 1 || M.peers.empty()) { launch_vmult(op, dst, src, add, 0); return; }
-  if (!op->comm) throw std::runtime_error("world > 1 requires a communicator (exadg_b200_set_nccl_comm / exadg_b200_nccl_init)");
   const int n3 = op->dev.n * op->dev.n * op->dev.n;
+  if (op->p2p) {
+    const long long epoch = ++op->p2p_epoch;
+    const int buf = (int)(epoch & 1);
+    if (M.peers.size() > (size_t)MAX_PEERS) throw std::runtime_error("too many halo peers");
+    PutArgs a; a.n_peers = (int)M.peers.size();
+    int64_t max_total = 1;
+    for (size_t i = 0; i < M.peers.size(); ++i) {
+      a.cells[i] = op->d_send_lists[i]; a.n_cells[i] = (int64_t)M.peers[i].send_cells.size();
+      char * peer = static_cast<char *>(op->p2p_peer_regions[i]);
+      a.dst[i] = reinterpret_cast<double *>(peer + (size_t)buf * op->p2p_ghost_bytes) + op->p2p_peer_recv_begin[i] * n3;
+      a.peer_flag[i] = reinterpret_cast<long long *>(peer + 2 * op->p2p_ghost_bytes) + M.rank;
+      a.peer_rank[i] = M.peers[i].rank;
+      max_total = std::max<int64_t>(max_total, a.n_cells[i] * n3);
+    }
+    op->dev.ghost = reinterpret_cast<double *>(op->p2p_region + (size_t)buf * op->p2p_ghost_bytes);
+    // src must be complete (work queued on the compute stream) before it is read on the communication stream
+    CUDA_CHECK(cudaEventRecord(op->ev_packed, op->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(op->comm_stream, op->ev_packed, 0));
+    const dim3 grid((unsigned)std::min<int64_t>((max_total + 255) / 256, 64), (unsigned)a.n_peers);
+    put_cells_kernel<<<grid, 256, 0, op->comm_stream>>>(a, src, n3);
+    signal_peers_kernel<<<1, 32, 0, op->comm_stream>>>(a, epoch);
+    wait_peers_kernel<<<1, 32, 0, op->comm_stream>>>(a, reinterpret_cast<const long long *>(op->p2p_region + 2 * op->p2p_ghost_bytes), epoch);
+    op->launches += 3;
+    CUDA_CHECK(cudaEventRecord(op->ev_halo, op->comm_stream));
+    launch_vmult(op, dst, src, add, 1);
+    CUDA_CHECK(cudaStreamWaitEvent(op->stream, op->ev_halo, 0));
+    launch_vmult(op, dst, src, add, 2);
+    CUDA_CHECK(cudaGetLastError());
+    return;
+  }
+  if (!op->comm) throw std::runtime_error("world > 1 requires a communicator (exadg_b200_set_nccl_comm / exadg_b200_nccl_init)");
   for (size_t i = 0; i < M.peers.size(); ++i) {
     const int64_t nc = (int64_t)M.peers[i].send_cells.size();
     const int64_t total = nc * n3;
@@ -456,7 +533,10 @@ int exadg_b200_destroy(exadg_b200_operator * op)
   cudaDeviceSynchronize();
   DeviceOperator & D = op->dev;
   cartesian_plan_destroy(D);
+  if (op->p2p) D.ghost = op->ghost_alloc;
   cudaFree(D.nb); cudaFree(D.face_id); cudaFree(D.face_info); cudaFree(D.cellG); cudaFree(D.faceG); cudaFree(D.tau_f); cudaFree(D.tau_cell); cudaFree(D.ghost);
+  for (auto p : op->p2p_peer_regions) if (p) cudaIpcCloseMemHandle(p);
+  if (op->p2p_region) cudaFree(op->p2p_region);
   for (auto p : op->d_send_lists) cudaFree(p);
   for (auto p : op->d_send_bufs) cudaFree(p);
   cudaFree(op->d_interior); cudaFree(op->d_boundary); cudaFree(op->d_cell_diag);
@@ -688,6 +768,52 @@ int exadg_b200_plan_tables(const exadg_b200_plan * p, int32_t * neighbors, int64
   if (neighbors) std::memcpy(neighbors, p->mesh.nb.data(), p->mesh.nb.size() * sizeof(int32_t));
   if (ghost_global_ids) std::memcpy(ghost_global_ids, p->mesh.ghost_global.data(), p->mesh.ghost_global.size() * sizeof(int64_t));
   return EXADG_B200_OK;
+}
+
+// Peer-memory halo: step 1, allocate the shared region and export its IPC handle and this rank's receive offsets
+int exadg_b200_p2p_export(exadg_b200_operator * op, char * handle64, int64_t * recv_begin_by_rank)
+{
+  return guarded([&]() {
+    if (!op || !handle64 || !recv_begin_by_rank) throw std::invalid_argument("null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    const HostMesh & M = op->mesh;
+    const size_t n3 = (size_t)op->dev.n * op->dev.n * op->dev.n;
+    if (!op->p2p_region) {
+      op->p2p_ghost_bytes = ((size_t)std::max<int64_t>(M.n_ghost, 1) * n3 * sizeof(double) + 255) / 256 * 256;
+      const size_t bytes = 2 * op->p2p_ghost_bytes + (size_t)M.world * sizeof(long long);
+      CUDA_CHECK(cudaMalloc(&op->p2p_region, bytes));
+      CUDA_CHECK(cudaMemset(op->p2p_region, 0, bytes));
+      CUDA_CHECK(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    CUDA_CHECK(cudaIpcGetMemHandle(&h, op->p2p_region));
+    std::memcpy(handle64, &h, 64);
+    for (int r = 0; r < M.world; ++r) recv_begin_by_rank[r] = -1;
+    for (auto & p : M.peers) recv_begin_by_rank[p.rank] = p.recv_begin;
+    return EXADG_B200_OK;
+  });
+}
+// step 2 (after an all-gather of step 1's outputs): map the peers' regions; from now on vmult uses NVLink stores
+int exadg_b200_p2p_connect(exadg_b200_operator * op, const char * handles /*[world][64]*/, const int64_t * recv_begin_table /*[world][world]*/)
+{
+  return guarded([&]() {
+    if (!op || !handles || !recv_begin_table) throw std::invalid_argument("null argument");
+    if (!op->p2p_region) throw std::runtime_error("call exadg_b200_p2p_export first");
+    const HostMesh & M = op->mesh;
+    op->p2p_peer_regions.assign(M.peers.size(), nullptr);
+    op->p2p_peer_recv_begin.assign(M.peers.size(), 0);
+    for (size_t i = 0; i < M.peers.size(); ++i) {
+      const int r = M.peers[i].rank;
+      cudaIpcMemHandle_t h; std::memcpy(&h, handles + (size_t)r * 64, 64);
+      CUDA_CHECK(cudaIpcOpenMemHandle(&op->p2p_peer_regions[i], h, cudaIpcMemLazyEnablePeerAccess));
+      const int64_t rb = recv_begin_table[(size_t)r * M.world + M.rank]; // where rank r stores the cells it receives from us
+      if (rb < 0) throw std::runtime_error("asymmetric halo plan (peer does not expect our cells)");
+      op->p2p_peer_recv_begin[i] = rb;
+    }
+    op->ghost_alloc = op->dev.ghost;
+    op->p2p = true;
+    return EXADG_B200_OK;
+  });
 }
 
 int exadg_b200_halo_n_peers(const exadg_b200_operator * op) { return op ? (int)op->mesh.peers.size() : -1; }

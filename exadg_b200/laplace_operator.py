@@ -201,6 +201,23 @@ class LaplaceOperator:
     def init_nccl(self, id_bytes):
         _check(_lib().exadg_b200_nccl_init(self._h, id_bytes))
 
+    def enable_p2p(self, dist):
+        """Switch the ghost import to NVLink peer-memory stores.  `dist` = initialised torch.distributed (any backend
+        that can all-gather small tensors); only used to hand the IPC handles and receive offsets around."""
+        torch = _torch()
+        world = dist.get_world_size()
+        handle = C.create_string_buffer(64)
+        recv = (C.c_int64 * world)()
+        _check(_lib().exadg_b200_p2p_export(self._h, handle, recv))
+        mine = torch.cat([torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(torch.int64),
+                          torch.tensor(list(recv), dtype=torch.int64)]).cuda()
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        handles = b"".join(bytes(g[:64].cpu().to(torch.uint8).numpy().tobytes()) for g in gathered)
+        table = (C.c_int64 * (world * world))(*[int(v) for g in gathered for v in g[64:].cpu().tolist()])
+        _check(_lib().exadg_b200_p2p_connect(self._h, handles, table))
+        dist.barrier()
+
 
 def nccl_unique_id():
     buf = C.create_string_buffer(128)

@@ -136,6 +136,13 @@ int exadg_b200_set_nccl_comm(exadg_b200_operator *op, void *nccl_comm);
 /* convenience: create the communicator inside the library (id from rank 0, broadcast by the caller) */
 int exadg_b200_nccl_unique_id(char *id128);
 int exadg_b200_nccl_init(exadg_b200_operator *op, const char *id128);
+/* NVLink peer-memory halo (no NCCL in the data path): the pack kernel stores the cells each peer needs straight
+ * into that peer's ghost buffer (CUDA IPC mapping), followed by a release flag; see csrc/c_api.cu.
+ *   1. every rank: exadg_b200_p2p_export -> 64-byte IPC handle + recv_begin_by_rank[world]
+ *   2. all-gather both over the ranks (the caller's transport, e.g. torch.distributed / MPI)
+ *   3. every rank: exadg_b200_p2p_connect(handles[world][64], recv_begin_table[world][world]) */
+int exadg_b200_p2p_export(exadg_b200_operator *op, char *handle64, int64_t *recv_begin_by_rank);
+int exadg_b200_p2p_connect(exadg_b200_operator *op, const char *handles, const int64_t *recv_begin_table);
 int exadg_b200_halo_n_peers(const exadg_b200_operator *op);
 int exadg_b200_halo_peer(const exadg_b200_operator *op, int i, int *peer_rank, int64_t *send_cells, int64_t *recv_cell_begin, int64_t *recv_cells);
 int exadg_b200_halo_send_list(const exadg_b200_operator *op, int i, int32_t *cells_host);

@@ -1,12 +1,12 @@
 """Multi-GPU parity check (run under torchrun, one rank per GPU): the partitioned vmult / CG must match the
-single-partition run of the same library (which the -m gpu tests pin against the oracle).
+single-partition run of the same library (which the -m gpu tests pin against the oracle), for both halo
+transports: NCCL send/recv and NVLink peer-memory stores (CUDA IPC).
 
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tests/multi_gpu_check.py
 """
 import os
 import sys
 
-import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -14,57 +14,74 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import exadg_b200  # noqa: E402
 from exadg_b200.laplace_operator import nccl_unique_id  # noqa: E402
 
+P6 = (0,) * 6
+# (4, 5, 0), (5, 3, 0), (2, 5, 0): partitions that end inside a cell batch (ghost indices directly follow a ragged last batch)
+CASES = [(4, 5, 0, 0.0, P6), (5, 3, 0, 0.0, P6), (2, 5, 0, 0.0, P6), (4, 3, 2, 0.0, P6), (3, 1, 3, 0.1, P6),
+         (2, 2, 2, 0.15, (1, 2, 1, 1, 1, 1)), (5, 1, 2, 0.0, P6)]
+
+
+def fresh_nccl_id(rank):
+    # one unique id per communicator (an id cannot be reused for a second ncclCommInitRank)
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    return bytes(idt.cpu().numpy().tobytes())
+
+
+def check_case(case, transport, rank, world):
+    degree, n_sub, refine, deformation, bc = case
+    op = exadg_b200.LaplaceOperator.hypercube(degree, n_sub, refine, 1, deformation, 2, bc, 1.0, rank=rank, world=world)
+    op.init_nccl(fresh_nccl_id(rank))  # all-reduces of the dot products; ghost import too unless p2p is enabled
+    if transport == "p2p":
+        op.enable_p2p(dist)            # ghost import by NVLink peer-memory stores
+    n3 = (degree + 1) ** 3
+    n_global = op.n()
+    g = torch.Generator().manual_seed(123)
+    x_global = torch.rand(n_global, dtype=torch.float64, generator=g) * 2 - 1
+    lo = (n_global // n3) * rank // world * n3
+    hi = lo + op.local_size()
+    ok = True
+    # reference: the whole problem on this GPU alone
+    ref = exadg_b200.LaplaceOperator.hypercube(degree, n_sub, refine, 1, deformation, 2, bc, 1.0)
+    y_ref = ref.initialize_dof_vector()
+    ref.vmult(y_ref, x_global.cuda())
+    dst = op.initialize_dof_vector()
+    worst = 0.0
+    for rep in range(3):  # repeated: exercises the double-buffered ghost ranges / epochs
+        src = (x_global[lo:hi] * (rep + 1)).cuda()
+        op.vmult(dst, src)
+        worst = max(worst, ((dst - (rep + 1) * y_ref[lo:hi]).norm() / ((rep + 1) * y_ref.norm())).item())
+    its = None
+    if bc != P6:  # CG with Jacobi: iteration counts equal to the single-partition solve
+        b = y_ref.clone()
+        s1 = exadg_b200.KrylovSolverCG(ref, exadg_b200.JacobiPreconditioner(ref), exadg_b200.SolverData(2000, 1e-20, 1e-8))
+        x1 = ref.initialize_dof_vector()
+        n1 = s1.solve(x1, b)
+        s2 = exadg_b200.KrylovSolverCG(op, exadg_b200.JacobiPreconditioner(op), exadg_b200.SolverData(2000, 1e-20, 1e-8))
+        x2 = op.initialize_dof_vector()
+        n2 = s2.solve(x2, b[lo:hi].clone())
+        its = (n1, n2)
+        ok &= abs(n1 - n2) <= 1
+        ok &= ((x2 - x1[lo:hi]).norm() / x1.norm()).item() < 1e-6
+    flag = torch.tensor([worst], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print("%s k=%d cells=%d^3 deformation=%g bc=%s cartesian_path=%d ghosts(rank0)=%d max rel err %.3e cg its %s"
+              % (transport, degree, n_sub << refine, deformation, bc, op.is_cartesian_path, op.n_cells_ghost, flag.item(), its), flush=True)
+    ok &= flag.item() < 1e-12
+    del op, ref
+    return ok
+
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    def fresh_nccl_id():
-        # one unique id per communicator (an id cannot be reused for a second ncclCommInitRank)
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        return bytes(idt.cpu().numpy().tobytes())
-
     ok = True
-    # (4, 5, 0) and (5, 3, 0): partitions that end inside a cell batch (ghost indices directly follow a ragged last batch)
-    for (degree, n_sub, refine, deformation, bc) in [(4, 5, 0, 0.0, (0,) * 6), (5, 3, 0, 0.0, (0,) * 6), (2, 5, 0, 0.0, (0,) * 6), (4, 3, 2, 0.0, (0,) * 6), (3, 1, 3, 0.1, (0,) * 6), (2, 2, 2, 0.15, (1, 2, 1, 1, 1, 1)), (5, 1, 2, 0.0, (0,) * 6)]:
-        op = exadg_b200.LaplaceOperator.hypercube(degree, n_sub, refine, 1, deformation, 2, bc, 1.0, rank=rank, world=world)
-        op.init_nccl(fresh_nccl_id())
-        n3 = (degree + 1) ** 3
-        n_global = op.n()
-        g = torch.Generator().manual_seed(123)
-        x_global = (torch.rand(n_global, dtype=torch.float64, generator=g) * 2 - 1)
-        lo = (n_global // n3) * rank // world * n3
-        src = x_global[lo:lo + op.local_size()].cuda()
-        dst = op.initialize_dof_vector()
-        op.vmult(dst, src)
-        # reference: the whole problem on this GPU alone
-        ref = exadg_b200.LaplaceOperator.hypercube(degree, n_sub, refine, 1, deformation, 2, bc, 1.0)
-        y_ref = ref.initialize_dof_vector()
-        ref.vmult(y_ref, x_global.cuda())
-        err = (dst - y_ref[lo:lo + op.local_size()]).norm() / y_ref.norm()
-        # CG with Jacobi: iteration counts equal to the single-partition solve
-        its = None
-        if bc != (0,) * 6:
-            b = y_ref.clone()
-            s1 = exadg_b200.KrylovSolverCG(ref, exadg_b200.JacobiPreconditioner(ref), exadg_b200.SolverData(2000, 1e-20, 1e-8))
-            x1 = ref.initialize_dof_vector()
-            n1 = s1.solve(x1, b)
-            s2 = exadg_b200.KrylovSolverCG(op, exadg_b200.JacobiPreconditioner(op), exadg_b200.SolverData(2000, 1e-20, 1e-8))
-            x2 = op.initialize_dof_vector()
-            n2 = s2.solve(x2, b[lo:lo + op.local_size()].clone())
-            its = (n1, n2)
-            ok &= abs(n1 - n2) <= 1
-            ok &= ((x2 - x1[lo:lo + op.local_size()]).norm() / x1.norm()).item() < 1e-6
-        flag = torch.tensor([err.item()], device="cuda")
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-        if rank == 0:
-            print("k=%d cells=%d^3 deformation=%g bc=%s cartesian_path=%d ghosts(rank0)=%d max rel err %.3e cg its %s"
-                  % (degree, n_sub << refine, deformation, bc, op.is_cartesian_path, op.n_cells_ghost, flag.item(), its), flush=True)
-        ok &= flag.item() < 1e-12
-        del op, ref
+    for case in CASES:
+        for transport in ("nccl", "p2p"):
+            ok &= check_case(case, transport, rank, world)
     dist.barrier()
     if rank == 0:
         print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL", flush=True)
