@@ -132,7 +132,7 @@ struct exadg_b200_operator
   // peer-memory halo (NVLink): one region [ghost A | ghost B | flags[world]] mapped by all peers
   bool p2p = false; char * p2p_region = nullptr; size_t p2p_ghost_bytes = 0; long long p2p_epoch = 0;
   std::vector<void *> p2p_peer_regions; // opened IPC mappings, indexed like mesh.peers
-  std::vector<int64_t> p2p_peer_recv_begin;
+  std::vector<int64_t> p2p_peer_recv_begin, p2p_peer_ghost_bytes;
   double * ghost_alloc = nullptr; // the ghost buffer of the NCCL path (dev.ghost points into p2p_region once p2p is on)
   // work vectors
   double * w[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -261,8 +261,9 @@ void apply(exadg_b200_operator * op, double * dst, const double * src, bool add)
     for (size_t i = 0; i < M.peers.size(); ++i) {
       a.cells[i] = op->d_send_lists[i]; a.n_cells[i] = (int64_t)M.peers[i].send_cells.size();
       char * peer = static_cast<char *>(op->p2p_peer_regions[i]);
-      a.dst[i] = reinterpret_cast<double *>(peer + (size_t)buf * op->p2p_ghost_bytes) + op->p2p_peer_recv_begin[i] * n3;
-      a.peer_flag[i] = reinterpret_cast<long long *>(peer + 2 * op->p2p_ghost_bytes) + M.rank;
+      const size_t pgb = (size_t)op->p2p_peer_ghost_bytes[i]; // the PEER's buffer size fixes the layout of its region
+      a.dst[i] = reinterpret_cast<double *>(peer + (size_t)buf * pgb) + op->p2p_peer_recv_begin[i] * n3;
+      a.peer_flag[i] = reinterpret_cast<long long *>(peer + 2 * pgb) + M.rank;
       a.peer_rank[i] = M.peers[i].rank;
       max_total = std::max<int64_t>(max_total, a.n_cells[i] * n3);
     }
@@ -790,11 +791,12 @@ int exadg_b200_p2p_export(exadg_b200_operator * op, char * handle64, int64_t * r
     std::memcpy(handle64, &h, 64);
     for (int r = 0; r < M.world; ++r) recv_begin_by_rank[r] = -1;
     for (auto & p : M.peers) recv_begin_by_rank[p.rank] = p.recv_begin;
+    recv_begin_by_rank[M.world] = (int64_t)op->p2p_ghost_bytes; // entry [world]: size of one ghost buffer of this rank
     return EXADG_B200_OK;
   });
 }
 // step 2 (after an all-gather of step 1's outputs): map the peers' regions; from now on vmult uses NVLink stores
-int exadg_b200_p2p_connect(exadg_b200_operator * op, const char * handles /*[world][64]*/, const int64_t * recv_begin_table /*[world][world]*/)
+int exadg_b200_p2p_connect(exadg_b200_operator * op, const char * handles /*[world][64]*/, const int64_t * recv_begin_table /*[world][world+1]*/)
 {
   return guarded([&]() {
     if (!op || !handles || !recv_begin_table) throw std::invalid_argument("null argument");
@@ -802,11 +804,13 @@ int exadg_b200_p2p_connect(exadg_b200_operator * op, const char * handles /*[wor
     const HostMesh & M = op->mesh;
     op->p2p_peer_regions.assign(M.peers.size(), nullptr);
     op->p2p_peer_recv_begin.assign(M.peers.size(), 0);
+    op->p2p_peer_ghost_bytes.assign(M.peers.size(), 0);
     for (size_t i = 0; i < M.peers.size(); ++i) {
       const int r = M.peers[i].rank;
       cudaIpcMemHandle_t h; std::memcpy(&h, handles + (size_t)r * 64, 64);
       CUDA_CHECK(cudaIpcOpenMemHandle(&op->p2p_peer_regions[i], h, cudaIpcMemLazyEnablePeerAccess));
-      const int64_t rb = recv_begin_table[(size_t)r * M.world + M.rank]; // where rank r stores the cells it receives from us
+      const int64_t rb = recv_begin_table[(size_t)r * (M.world + 1) + M.rank]; // where rank r stores the cells it receives from us
+      op->p2p_peer_ghost_bytes[i] = recv_begin_table[(size_t)r * (M.world + 1) + M.world];
       if (rb < 0) throw std::runtime_error("asymmetric halo plan (peer does not expect our cells)");
       op->p2p_peer_recv_begin[i] = rb;
     }

@@ -207,14 +207,14 @@ class LaplaceOperator:
         torch = _torch()
         world = dist.get_world_size()
         handle = C.create_string_buffer(64)
-        recv = (C.c_int64 * world)()
+        recv = (C.c_int64 * (world + 1))()
         _check(_lib().exadg_b200_p2p_export(self._h, handle, recv))
         mine = torch.cat([torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(torch.int64),
                           torch.tensor(list(recv), dtype=torch.int64)]).cuda()
         gathered = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(gathered, mine)
         handles = b"".join(bytes(g[:64].cpu().to(torch.uint8).numpy().tobytes()) for g in gathered)
-        table = (C.c_int64 * (world * world))(*[int(v) for g in gathered for v in g[64:].cpu().tolist()])
+        table = (C.c_int64 * (world * (world + 1)))(*[int(v) for g in gathered for v in g[64:].cpu().tolist()])
         _check(_lib().exadg_b200_p2p_connect(self._h, handles, table))
         dist.barrier()
 

@@ -138,9 +138,9 @@ int exadg_b200_nccl_unique_id(char *id128);
 int exadg_b200_nccl_init(exadg_b200_operator *op, const char *id128);
 /* NVLink peer-memory halo (no NCCL in the data path): the pack kernel stores the cells each peer needs straight
  * into that peer's ghost buffer (CUDA IPC mapping), followed by a release flag; see csrc/c_api.cu.
- *   1. every rank: exadg_b200_p2p_export -> 64-byte IPC handle + recv_begin_by_rank[world]
+ *   1. every rank: exadg_b200_p2p_export -> 64-byte IPC handle + recv_begin_by_rank[world + 1] (last entry: ghost buffer bytes)
  *   2. all-gather both over the ranks (the caller's transport, e.g. torch.distributed / MPI)
- *   3. every rank: exadg_b200_p2p_connect(handles[world][64], recv_begin_table[world][world]) */
+ *   3. every rank: exadg_b200_p2p_connect(handles[world][64], recv_begin_table[world][world + 1]) */
 int exadg_b200_p2p_export(exadg_b200_operator *op, char *handle64, int64_t *recv_begin_by_rank);
 int exadg_b200_p2p_connect(exadg_b200_operator *op, const char *handles, const int64_t *recv_begin_table);
 int exadg_b200_halo_n_peers(const exadg_b200_operator *op);
