@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(PipeCfg<N>::NT, 3) vmult_cartesian_pipe_kernel
             g0[l] = fma(T.fd[0][m], x, g0[l]); g1[l] = fma(T.fd[1][m], x, g1[l]);
           }
 #pragma unroll
-        for (int l = 0; l < N; ++l) { GN[(lc * 2 + 0) * N2 + l + N * s] = g0[l]; GN[(lc * 2 + 1) * N2 + l + N * s] = g1[l]; }
+        for (int l = 0; l < N; ++l) { GN[(0 * B + lc) * N2 + s * N + l] = g0[l]; GN[(1 * B + lc) * N2 + s * N + l] = g1[l]; }
       }
       PIPE_SYNC();
       if (valid) {
@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(PipeCfg<N>::NT, 3) vmult_cartesian_pipe_kernel
             if (inb) {
               const int endn = side ? 0 : N - 1; // neighbour's end node facing us
               vn[l] = (d == 0) ? U[nbl * N3 + s * N2 + endn + N * l] : U[nbl * N3 + s * N2 + l + N * endn];
-              gn = GN[(nbl * 2 + (side ^ 1)) * N2 + l + N * s];
+              gn = GN[((side ^ 1) * B + nbl) * N2 + s * N + l];
             } else {
               vn[l] = HV[slot * N2 + l + N * s]; gn = HG[slot * N2 + l + N * s];
             }
@@ -613,12 +613,15 @@ __global__ void __launch_bounds__(PipeCfg<N>::NT, 3) vmult_cartesian_pipe_kernel
 #pragma unroll
         for (int i = 0; i < N; ++i) Tt[lc * N3 + s * N2 + i + N * j] = acc[j][i];
     }
-    // ---- z sweep: this thread owns the n lines (i, j = s) ----
-    if (valid) {
+    // ---- z sweep: thread (cell lz = t % B, slice sz = t / B) owns the lines (i, j = sz): consecutive lanes touch
+    // consecutive cells (stride n^3, odd) -> bank-conflict free; nothing is carried over in registers ----
+    const int lz = t % B, sz = t / B;
+    const bool validz = (sz < N) && (lz < nvalid);
+    if (validz) {
 #pragma unroll
       for (int i = 0; i < N; ++i)
 #pragma unroll
-        for (int k = 0; k < N; ++k) u[i][k] = U[lc * N3 + k * N2 + i + N * s];
+        for (int k = 0; k < N; ++k) u[i][k] = U[lz * N3 + k * N2 + i + N * sz];
       double g0[N], g1[N];
 #pragma unroll
       for (int i = 0; i < N; ++i) { g0[i] = T.fd[0][0] * u[i][0]; g1[i] = T.fd[1][0] * u[i][0]; }
@@ -627,29 +630,29 @@ __global__ void __launch_bounds__(PipeCfg<N>::NT, 3) vmult_cartesian_pipe_kernel
 #pragma unroll
         for (int i = 0; i < N; ++i) { g0[i] = fma(T.fd[0][k], u[i][k], g0[i]); g1[i] = fma(T.fd[1][k], u[i][k], g1[i]); }
 #pragma unroll
-      for (int i = 0; i < N; ++i) { GN[(lc * 2 + 0) * N2 + i + N * s] = g0[i]; GN[(lc * 2 + 1) * N2 + i + N * s] = g1[i]; }
+      for (int i = 0; i < N; ++i) { GN[(0 * B + lz) * N2 + sz * N + i] = g0[i]; GN[(1 * B + lz) * N2 + sz * N + i] = g1[i]; }
     }
     PIPE_SYNC(); // Tt planes, z traces (GN and HV/HG) visible
-    if (valid) {
+    if (validz) {
 #pragma unroll
       for (int i = 0; i < N; ++i)
 #pragma unroll
-        for (int k = 0; k < N; ++k) acc[i][k] = Tt[lc * N3 + k * N2 + i + N * s];
+        for (int k = 0; k < N; ++k) acc[i][k] = Tt[lz * N3 + k * N2 + i + N * sz];
 #pragma unroll
       for (int side = 0; side < 2; ++side) {
-        const int nbl = nbS[lc * 6 + 4 + side] - (int)b0;
+        const int nbl = nbS[lz * 6 + 4 + side] - (int)b0;
         const bool inb = (nbl >= 0 && nbl < nvalid);
-        const int slot = slotS[lc * 6 + 4 + side];
+        const int slot = slotS[lz * 6 + 4 + side];
         double vn[N], tt[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
           double gn;
           if (inb) {
             const int endn = side ? 0 : N - 1;
-            vn[i] = U[nbl * N3 + endn * N2 + i + N * s];
-            gn = GN[(nbl * 2 + (side ^ 1)) * N2 + i + N * s];
+            vn[i] = U[nbl * N3 + endn * N2 + i + N * sz];
+            gn = GN[((side ^ 1) * B + nbl) * N2 + sz * N + i];
           } else {
-            vn[i] = HV[slot * N2 + i + N * s]; gn = HG[slot * N2 + i + N * s];
+            vn[i] = HV[slot * N2 + i + N * sz]; gn = HG[slot * N2 + i + N * sz];
           }
           tt[i] = fma(side ? 0.5 : -0.5, gn, T.tau_hat[2] * vn[i]);
         }
@@ -682,7 +685,7 @@ __global__ void __launch_bounds__(PipeCfg<N>::NT, 3) vmult_cartesian_pipe_kernel
 #pragma unroll
       for (int i = 0; i < N; ++i)
 #pragma unroll
-        for (int r = 0; r < N; ++r) Tt[lc * N3 + r * N2 + i + N * s] = u[i][r];
+        for (int r = 0; r < N; ++r) Tt[lz * N3 + r * N2 + i + N * sz] = u[i][r];
     }
     PIPE_SYNC(); // U and the trace buffers are dead from here on
     // park the tables of the next batch and start its bulk copy
