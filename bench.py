@@ -143,6 +143,57 @@ def run_reference(args):
     print(json.dumps(out), flush=True)
 
 
+def run_callers(args, op, src, dst, world, rank, barrier, dist):
+    """Secondary lines (not the headline): the callers of vmult on the same workload:
+    cg        - dealii::SolverCG iterations without preconditioner: vmult + fused vector updates, 16 + 56 B/DoF
+    chebyshev - one application of the Chebyshev(5)/point-Jacobi smoother: 4 vmults + fused updates"""
+    import torch
+    import exadg_b200
+    n_global = op.n()
+    if args.mode == "cg":
+        b = op.initialize_dof_vector()
+        op.vmult(b, src)  # consistent right-hand side (the periodic operator is singular)
+        its = max(args.steps, 5)
+        solver = exadg_b200.KrylovSolverCG(op, None, exadg_b200.SolverData(its, 0.0, 0.0))
+        for timed in (False, True):
+            x = op.initialize_dof_vector()
+            barrier()
+            t0 = time.perf_counter()
+            try:
+                solver.solve(x, b)
+            except exadg_b200.ExaDGError:
+                pass  # max_iter reached on purpose: exactly `its` iterations are timed
+            barrier()
+            dt = time.perf_counter() - t0
+        per_it = dt / its
+        b_alg = 16.0 + 56.0
+        label = "CG iteration (dealii::SolverCG restated, no preconditioner): vmult + dot + fused x/g update + d update"
+    else:
+        ch = exadg_b200.ChebyshevSmoother(op, 5, 20.0, 20)
+        reps = max(args.steps // 5, 3)
+        ch.vmult(dst, src)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ch.vmult(dst, src)
+        barrier()
+        per_it = (time.perf_counter() - t0) / reps
+        b_alg = 4 * 16.0 + 3 * 8.0 + 4 * 7 * 8.0
+        label = "Chebyshev(5)/point-Jacobi smoother application: 4 vmults + 5 fused update passes"
+    t = torch.tensor([per_it], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    per_it = t.item()
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = b_alg * (n_global / world) / per_it / 1e9
+        print(json.dumps({"metric": "DoFs/s per " + ("CG iteration" if args.mode == "cg" else "smoother application"), "value": n_global / per_it,
+                          "unit": "DoFs/s", "n_gpus": world, "ms_per_step": per_it * 1e3, "dtype": "f64", "data": "synthetic", "secondary": True,
+                          "config": {"workload": label, "degree": args.degree, "dofs": n_global, "timing": "host clock around the library call (includes one host read of the residual per CG iteration)"},
+                          "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "algorithmic_bytes_per_dof": b_alg,
+                                       "peak_source": peak_src}}), flush=True)
+
+
 def run_gpu(args):
     import torch
     import exadg_b200
@@ -186,6 +237,9 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.mode != "vmult":
+        run_callers(args, op, src, dst, world, rank, barrier, dist)
+        return
     for _ in range(max(args.warmup, 3)):
         op.vmult_async(dst, src)
     barrier()
@@ -269,6 +323,7 @@ def main():
     ap.add_argument("--degree", type=int, default=4)
     ap.add_argument("--mesh", default="cartesian", choices=["cartesian", "curvilinear"])
     ap.add_argument("--cells", type=int, default=0, help="cells per direction (default: the workload of the contract)")
+    ap.add_argument("--mode", default="vmult", choices=["vmult", "cg", "chebyshev"], help="vmult = the headline metric; cg / chebyshev = secondary lines for the callers")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="ghost import transport for N>1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
