@@ -441,7 +441,7 @@ __device__ __forceinline__ void pipe_rest(const Tab & T, const int2 * hl, int e0
 #define PIPE_SYNC() asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory")
 
 template<int N>
-__global__ void __launch_bounds__(PipeCfg<N>::NT, 3) vmult_cartesian_pipe_kernel(const __grid_constant__ CartTables<N> T, const PipeArgs A)
+__global__ void __launch_bounds__(PipeCfg<N>::NT, 2) vmult_cartesian_pipe_kernel(const __grid_constant__ CartTables<N> T, const PipeArgs A)
 {
   constexpr int B = PipeCfg<N>::B, NT = PipeCfg<N>::NT, E = PipeCfg<N>::E;
   constexpr int N2 = N * N, N3 = N2 * N;
@@ -858,7 +858,7 @@ size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh)
   P.n = op.n;
   const int N = op.n;
   P.B = (N >= 6) ? 16 : ((N >= 4) ? 32 : 64);
-  P.pipe = (N == 5) && getenv("EXADG_B200_PIPE") && !getenv("EXADG_B200_NO_PIPE"); // experimental (profiles/r01_notes.md): correct, 9 % slower than the 5-warp kernel
+  P.pipe = (N == 5) && !getenv("EXADG_B200_NO_PIPE"); // pipelined 4-warp kernel (EXADG_B200_NO_PIPE=1: the 5-warp kernel)
   if (P.pipe) P.B = PipeCfg<5>::B;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&P.n_sm, cudaDevAttrMultiProcessorCount, dev); if (P.n_sm < 1) P.n_sm = 148; }
   P.n_batches = (int)((mesh.n_owned + P.B - 1) / P.B);

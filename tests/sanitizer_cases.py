@@ -13,11 +13,11 @@ import exadg_b200  # noqa: E402
 
 for (degree, n_sub, refine, deformation, bc) in [(4, 3, 0, 0.0, (0,) * 6), (2, 5, 0, 0.0, (0,) * 6), (3, 1, 1, 0.0, (0,) * 6), (5, 1, 1, 0.0, (0,) * 6),
                                                  (3, 2, 0, 0.1, (0,) * 6), (2, 2, 0, 0.15, (1, 2, 1, 1, 1, 1))]:
-    for pipe in ((False, True) if (degree == 4 and deformation == 0.0) else (False,)):
+    for pipe in ((False, True) if (degree == 4 and deformation == 0.0) else (True,)):
         if pipe:
-            os.environ["EXADG_B200_PIPE"] = "1"
+            os.environ.pop("EXADG_B200_NO_PIPE", None)
         else:
-            os.environ.pop("EXADG_B200_PIPE", None)
+            os.environ["EXADG_B200_NO_PIPE"] = "1"
         op = exadg_b200.LaplaceOperator.hypercube(degree, n_sub, refine, 1, deformation, 2, bc)
         x = torch.rand(op.local_size(), dtype=torch.float64, device="cuda")
         y = op.initialize_dof_vector()
