@@ -363,7 +363,9 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
 //  * the bulk copy (TMA) of the next batch starts as soon as the z sweep has consumed the current one; the result
 //    is finished in place in Tt and leaves through one TMA bulk store.
 // =====================================================================================================
-template<int N> struct PipeCfg { static constexpr int B = 24; static constexpr int NT = 128; static constexpr int E = 5; };
+// n = 5: 24 cells (3 octets of the Morton curve) x 5 planes = 120 of 128 threads; n = 3: 40 cells x 3 planes = 120 of 128 threads.
+// E = neighbour cells per thread group and direction fetched ahead; MINB = resident CTAs the register budget is tuned for.
+template<int N> struct PipeCfg { static constexpr int B = (N == 3) ? 40 : 24; static constexpr int NT = 128; static constexpr int E = (N == 3) ? 3 : 5; static constexpr int MINB = (N == 3) ? 4 : 2; };
 
 struct PipeArgs
 {
@@ -441,7 +443,7 @@ __device__ __forceinline__ void pipe_rest(const Tab & T, const int2 * hl, int e0
 #define PIPE_SYNC() asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory")
 
 template<int N>
-__global__ void __launch_bounds__(PipeCfg<N>::NT, 2) vmult_cartesian_pipe_kernel(const __grid_constant__ CartTables<N> T, const PipeArgs A)
+__global__ void __launch_bounds__(PipeCfg<N>::NT, PipeCfg<N>::MINB) vmult_cartesian_pipe_kernel(const __grid_constant__ CartTables<N> T, const PipeArgs A)
 {
   constexpr int B = PipeCfg<N>::B, NT = PipeCfg<N>::NT, E = PipeCfg<N>::E;
   constexpr int N2 = N * N, N3 = N2 * N;
@@ -858,8 +860,8 @@ size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh)
   P.n = op.n;
   const int N = op.n;
   P.B = (N >= 6) ? 16 : ((N >= 4) ? 32 : 64);
-  P.pipe = (N == 5) && !getenv("EXADG_B200_NO_PIPE"); // pipelined 4-warp kernel (EXADG_B200_NO_PIPE=1: the 5-warp kernel)
-  if (P.pipe) P.B = PipeCfg<5>::B;
+  P.pipe = (N == 5) && !getenv("EXADG_B200_NO_PIPE"); // n = 3 measured slower than the 64-cell kernel (0.99 vs 0.86 ms) // pipelined 4-warp kernel (EXADG_B200_NO_PIPE=1: the 5-warp kernel)
+  if (P.pipe) P.B = (N == 3) ? PipeCfg<3>::B : PipeCfg<5>::B;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&P.n_sm, cudaDevAttrMultiProcessorCount, dev); if (P.n_sm < 1) P.n_sm = 148; }
   P.n_batches = (int)((mesh.n_owned + P.B - 1) / P.B);
   std::vector<std::vector<int2>> lists(P.n_batches);
@@ -891,7 +893,7 @@ size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh)
     const int N2p = N * N, N3p = N2p * N;
     P.smem = ((size_t)2 * P.B * N3p + (size_t)P.B * 2 * N2p + (size_t)2 * P.HD * N2p) * sizeof(double) + (size_t)2 * P.HL * sizeof(int2)
              + (size_t)P.B * 18 * sizeof(int) + 64 + 16;
-    if (P.smem > 227 * 1024 - 1024 || P.HL > PipeCfg<5>::NT) { P.pipe = false; P.B = 32; delete Pp; return cartesian_plan_create_fallback(op, mesh); }
+    if (P.smem > 227 * 1024 - 1024 || P.HL > PipeCfg<5>::NT) { P.pipe = false; P.B = (N >= 4) ? 32 : 64; delete Pp; return cartesian_plan_create_fallback(op, mesh); }
     CUDA_CHECK(cudaMalloc(&P.d_cnt4, cnt4.size() * sizeof(int4)));
     CUDA_CHECK(cudaMemcpy(P.d_cnt4, cnt4.data(), cnt4.size() * sizeof(int4), cudaMemcpyHostToDevice));
   }
@@ -948,7 +950,7 @@ void launch_vmult_cartesian_part(const DeviceOperator & op, double * dst, const 
   if (!plan) throw std::runtime_error("Cartesian plan missing");
   switch (op.n) {
     case 2: launch_n<2>(op, *plan, dst, src, add, which, stream); break;
-    case 3: launch_n<3>(op, *plan, dst, src, add, which, stream); break;
+    case 3: if (plan->pipe) launch_pipe<3>(op, *plan, dst, src, add, which, stream); else launch_n<3>(op, *plan, dst, src, add, which, stream); break;
     case 4: launch_n<4>(op, *plan, dst, src, add, which, stream); break;
     case 5: if (plan->pipe) launch_pipe<5>(op, *plan, dst, src, add, which, stream); else launch_n<5>(op, *plan, dst, src, add, which, stream); break;
     case 6: launch_n<6>(op, *plan, dst, src, add, which, stream); break;
