@@ -596,6 +596,7 @@ __global__ void __launch_bounds__(PipeCfg<N>::NT, PipeCfg<N>::MINB) vmult_cartes
               else acc[r][l] = fma(T.G[d][r * N + c], u[c][l], acc[r][l]);
             }
       }
+      if (d == 1 && t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // previous batch's store has read Tt
       PIPE_SYNC(); // traces and GN of this direction are consumed
       // traces of the next direction from the lines fetched one sweep ago; lines of the direction after that
       if (hthread) {
@@ -745,12 +746,17 @@ __global__ void __launch_bounds__(PipeCfg<N>::NT, PipeCfg<N>::MINB) vmult_cartes
       if (hthread) pipe_load<N, 0, E>(hx, hl2 + (cur ^ 1) * A.HL, 0, cn.x, grp, NGRP, ab, A.src, A.ghost, A.n_owned);
     }
     if (use_tma) {
-      if (t == 0) tma_store_1d(A.dst + b0 * N3, Tt, bytes, A.add != 0); // returns when the source has been read
+      if (t == 0) { // issue only; the wait for the source read sits right before Tt is written again (next batch / kernel end)
+        if (A.add) asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(A.dst + b0 * N3), "r"(smem_u32(Tt)), "r"(bytes) : "memory");
+        else asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(A.dst + b0 * N3), "r"(smem_u32(Tt)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
     } else {
       for (int i = t; i < nvalid * N3; i += NT) { if (A.add) A.dst[b0 * N3 + i] += Tt[i]; else A.dst[b0 * N3 + i] = Tt[i]; }
     }
-    PIPE_SYNC(); // Tt may be overwritten by the next batch
+    // no barrier here: Tt is next written after the y sweep of the following batch, behind the store wait + barriers
   }
+  if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // all bulk stores complete before the CTA exits
 }
 
 struct CartPlan
