@@ -231,14 +231,15 @@ void finish_setup(exadg_b200_operator * op, double ip_factor, bool force_general
 }
 
 // which: 0 all owned cells, 1 cells (batches) that touch no ghost, 2 those that do
-void launch_vmult(exadg_b200_operator * op, double * dst, const double * src, bool add, int which)
+void launch_vmult(exadg_b200_operator * op, double * dst, const double * src, bool add, int which, cudaStream_t stream = nullptr)
 {
-  if (op->dev.cartesian) launch_vmult_cartesian_part(op->dev, dst, src, add, which, op->stream);
-  else if (which == 0) launch_vmult_general(op->dev, dst, src, add, nullptr, 0, op->stream);
+  if (!stream) stream = op->stream;
+  if (op->dev.cartesian) launch_vmult_cartesian_part(op->dev, dst, src, add, which, stream);
+  else if (which == 0) launch_vmult_general(op->dev, dst, src, add, nullptr, 0, stream);
   else {
     const int64_t nc = which == 1 ? op->n_interior : op->n_boundary;
     if (nc == 0) return;
-    launch_vmult_general(op->dev, dst, src, add, which == 1 ? op->d_interior : op->d_boundary, nc, op->stream);
+    launch_vmult_general(op->dev, dst, src, add, which == 1 ? op->d_interior : op->d_boundary, nc, stream);
   }
   op->launches++;
 }
@@ -276,10 +277,12 @@ void apply(exadg_b200_operator * op, double * dst, const double * src, bool add)
     signal_peers_kernel<<<1, 32, 0, op->comm_stream>>>(a, epoch);
     wait_peers_kernel<<<1, 32, 0, op->comm_stream>>>(a, reinterpret_cast<const long long *>(op->p2p_region + 2 * op->p2p_ghost_bytes), epoch);
     op->launches += 3;
+    // cells that touch ghosts run on the (high-priority) communication stream right behind the wait kernel and
+    // overlap with the tail of the interior-cell kernel on the compute stream; the streams join at the end
+    launch_vmult(op, dst, src, add, 2, op->comm_stream);
     CUDA_CHECK(cudaEventRecord(op->ev_halo, op->comm_stream));
     launch_vmult(op, dst, src, add, 1);
     CUDA_CHECK(cudaStreamWaitEvent(op->stream, op->ev_halo, 0));
-    launch_vmult(op, dst, src, add, 2);
     CUDA_CHECK(cudaGetLastError());
     return;
   }
@@ -303,10 +306,10 @@ void apply(exadg_b200_operator * op, double * dst, const double * src, bool add)
   }
   if (api.GroupEnd() != 0) throw std::runtime_error("NCCL halo exchange failed");
   }
+  launch_vmult(op, dst, src, add, 2, op->comm_stream);
   CUDA_CHECK(cudaEventRecord(op->ev_halo, op->comm_stream));
   launch_vmult(op, dst, src, add, 1);
   CUDA_CHECK(cudaStreamWaitEvent(op->stream, op->ev_halo, 0));
-  launch_vmult(op, dst, src, add, 2);
 }
 
 void diagonal(exadg_b200_operator * op, double * diag, bool add)
