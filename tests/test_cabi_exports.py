@@ -70,3 +70,41 @@ def test_no_gpu_means_loud_failure():
     import exadg_b200
     with pytest.raises(exadg_b200.ExaDGError):
         exadg_b200.LaplaceOperator.hypercube(degree=2, n_subdivisions=2)
+
+
+def test_create_rejects_inconsistent_mesh_before_any_cuda_call(lib):
+    """exadg_b200_create validates the arrays a binding passes (status code, no exception across the C ABI)."""
+    import numpy as np
+    import exadg_b200
+    d = exadg_b200.MeshDesc()
+    pts = np.zeros((1, 8, 3))
+    nb = np.full((1, 6), -1, dtype=np.int32)
+    nf = np.zeros((1, 6), dtype=np.uint8)
+    bt = np.zeros((1, 6), dtype=np.uint8)  # says "interior" although there is no neighbour
+    d.degree, d.mapping_degree, d.n_cells_owned, d.n_cells_ghost = 2, 1, 1, 0
+    d.mapping_points = pts.ctypes.data_as(C.POINTER(C.c_double))
+    d.neighbors = nb.ctypes.data_as(C.POINTER(C.c_int32))
+    d.neighbor_face = nf.ctypes.data_as(C.POINTER(C.c_uint8))
+    d.boundary_type = bt.ctypes.data_as(C.POINTER(C.c_uint8))
+    d.ip_factor = 1.0
+    h = C.c_void_p()
+    assert lib.exadg_b200_create(C.byref(d), C.byref(h)) == 1
+    assert b"boundary_type" in lib.exadg_b200_last_error()
+    nb[0, 0] = 7  # out of range
+    bt[:] = 1
+    bt[0, 0] = 0
+    assert lib.exadg_b200_create(C.byref(d), C.byref(h)) == 1
+    assert b"out of range" in lib.exadg_b200_last_error()
+
+
+def test_partition_plan_is_contiguous_and_complete(lib):
+    import exadg_b200
+    world, total, ghosts = 4, 0, 0
+    for r in range(world):
+        p = exadg_b200.PartitionPlan(3, 1, r, world)
+        assert p.global_offset == total
+        total += p.n_owned
+        ghosts += p.n_ghost
+        assert all(pp["rank"] != r for pp in p.peers)
+        assert sum(pp["recv_count"] for pp in p.peers) == p.n_ghost
+    assert total == 6 ** 3 and ghosts > 0
