@@ -223,8 +223,19 @@ def run_gpu(args):
             idt.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         op.init_nccl(bytes(idt.cpu().numpy().tobytes()))
+        halo_used = "nccl"
         if args.halo == "p2p":
-            op.enable_p2p(dist)  # ghost import by NVLink peer-memory stores fused into the pack kernel
+            try:
+                op.enable_p2p(dist)  # ghost import by NVLink peer-memory stores fused into the pack kernel
+                halo_used = "p2p"
+            except Exception as e:  # no peer access on this box: the NCCL transport is equivalent
+                sys.stderr.write("peer-memory halo unavailable (%s); using NCCL send/recv\n" % e)
+        # every rank must use the same transport
+        flag = torch.tensor([1 if halo_used == "p2p" else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if args.halo == "p2p" and flag.item() == 0 and halo_used == "p2p":
+            raise RuntimeError("peer-memory halo enabled on some ranks only")
+        args.halo = halo_used
     op.use_torch_stream()
     n_local, n_global = op.local_size(), op.n()
     g = torch.Generator(device="cuda").manual_seed(42 + rank)
