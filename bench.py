@@ -102,7 +102,7 @@ def cpu_baseline(degree, seconds=12.0, cells_1d=16):
     op = OracleOperator(degree, n_sub, refine, 1, 0.0)
     x = synthetic_vector(op.n_dofs)
     y = np.zeros_like(x)
-    threads = lib().orc_max_threads()
+    threads = len(os.sched_getaffinity(0))  # all host cores (torchrun exports OMP_NUM_THREADS=1; the count is passed explicitly)
     op.vmult_cellwise(x, threads, dst=y)  # warm-up
     best, reps, t_start = float("inf"), 0, time.time()
     while time.time() - t_start < seconds or reps < 3:
@@ -126,7 +126,7 @@ def run_reference(args):
     op = OracleOperator(degree, 1, 5 if degree <= 4 else 4, 1, 0.0)  # 32^3 cells (4.1 M DoFs at k=4)
     x = synthetic_vector(op.n_dofs)
     y = np.zeros_like(x)
-    threads = lib().orc_max_threads()
+    threads = len(os.sched_getaffinity(0))  # all host cores (torchrun exports OMP_NUM_THREADS=1; the count is passed explicitly)
     for _ in range(args.warmup):
         op.vmult_cellwise(x, threads, dst=y)
     t0 = time.perf_counter()
