@@ -360,6 +360,13 @@ double read_scalar(exadg_b200_operator * op, int slot)
   return op->red.host[slot];
 }
 
+// all reduction slots -> pinned host mirror, ordered behind the kernels queued on the operator's stream
+void read_all_scalars(exadg_b200_operator * op)
+{
+  CUDA_CHECK(cudaMemcpyAsync(op->red.host, op->red.result, 8 * sizeof(double), cudaMemcpyDeviceToHost, op->stream));
+  CUDA_CHECK(cudaStreamSynchronize(op->stream));
+}
+
 void cheb_run(exadg_b200_chebyshev * ch, double * x, const double * b, bool zero_start);
 
 void precondition(exadg_b200_operator * op, int precond, const double * inv_diag, exadg_b200_chebyshev * cheb, int slot, double * z, const double * g)
@@ -409,7 +416,7 @@ int cg(exadg_b200_operator * op, double * x, const double * b, int precond, cons
     res = std::sqrt(read_scalar(op, S_RES));
     if (residuals) residuals[it] = res;
     if (alphas) { // Lanczos coefficients for the eigenvalue estimate
-      CUDA_CHECK(cudaMemcpy(op->red.host, op->red.result, 8 * sizeof(double), cudaMemcpyDeviceToHost));
+      read_all_scalars(op);
       alphas->push_back(op->red.host[S_GH] / op->red.host[S_DH]);
     }
     state = check(it, res);
@@ -417,11 +424,11 @@ int cg(exadg_b200_operator * op, double * x, const double * b, int precond, cons
     if (precond != EXADG_B200_PRECOND_NONE) {
       precondition(op, precond, inv_diag, cheb, S_NEW, h, g);
       cg_update_d(op->red, S_NEW, S_GH, d, h, n, s); op->launches++;
-      if (betas) { CUDA_CHECK(cudaMemcpy(op->red.host, op->red.result, 8 * sizeof(double), cudaMemcpyDeviceToHost)); betas->push_back(op->red.host[S_NEW] / op->red.host[S_GH]); }
+      if (betas) { read_all_scalars(op); betas->push_back(op->red.host[S_NEW] / op->red.host[S_GH]); }
       std::swap(S_GH, S_NEW);
     } else {
       cg_update_d(op->red, S_RES, S_GH, d, g, n, s); op->launches++;
-      if (betas) { CUDA_CHECK(cudaMemcpy(op->red.host, op->red.result, 8 * sizeof(double), cudaMemcpyDeviceToHost)); betas->push_back(op->red.host[S_RES] / op->red.host[S_GH]); }
+      if (betas) { read_all_scalars(op); betas->push_back(op->red.host[S_RES] / op->red.host[S_GH]); }
       std::swap(S_GH, S_RES);
     }
   }

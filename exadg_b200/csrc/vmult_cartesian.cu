@@ -855,18 +855,20 @@ void store_tables(CartPlan & P, const DeviceOperator & op)
   std::memcpy(P.tables.data(), &T, sizeof(T));
 }
 
-static size_t cartesian_plan_create_fallback(DeviceOperator & op, const HostMesh & mesh);
+static size_t plan_create(DeviceOperator & op, const HostMesh & mesh, bool allow_pipe);
 
 // builds the batch plan (halo lists, interior/boundary batches, tables); returns the dynamic shared
 // memory per CTA, or 0 if the batch does not fit (caller falls back to the general kernel)
-size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh)
+size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh) { return plan_create(op, mesh, true); }
+
+static size_t plan_create(DeviceOperator & op, const HostMesh & mesh, bool allow_pipe)
 {
   CartPlan * Pp = new CartPlan;
   CartPlan & P = *Pp;
   P.n = op.n;
   const int N = op.n;
   P.B = (N >= 6) ? 16 : ((N >= 4) ? 32 : 64);
-  P.pipe = (N == 5) && !getenv("EXADG_B200_NO_PIPE"); // n = 3 measured slower than the 64-cell kernel (0.99 vs 0.86 ms) // pipelined 4-warp kernel (EXADG_B200_NO_PIPE=1: the 5-warp kernel)
+  P.pipe = allow_pipe && (N == 5) && !getenv("EXADG_B200_NO_PIPE"); // n = 3 measured slower than the 64-cell kernel (0.99 vs 0.86 ms) // pipelined 4-warp kernel (EXADG_B200_NO_PIPE=1: the 5-warp kernel)
   if (P.pipe) P.B = (N == 3) ? PipeCfg<3>::B : PipeCfg<5>::B;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&P.n_sm, cudaDevAttrMultiProcessorCount, dev); if (P.n_sm < 1) P.n_sm = 148; }
   P.n_batches = (int)((mesh.n_owned + P.B - 1) / P.B);
@@ -899,7 +901,7 @@ size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh)
     const int N2p = N * N, N3p = N2p * N;
     P.smem = ((size_t)2 * P.B * N3p + (size_t)P.B * 2 * N2p + (size_t)2 * P.HD * N2p) * sizeof(double) + (size_t)2 * P.HL * sizeof(int2)
              + (size_t)P.B * 18 * sizeof(int) + 64 + 16;
-    if (P.smem > 227 * 1024 - 1024 || P.HL > PipeCfg<5>::NT) { P.pipe = false; P.B = (N >= 4) ? 32 : 64; delete Pp; return cartesian_plan_create_fallback(op, mesh); }
+    if (P.smem > 227 * 1024 - 1024 || P.HL > PipeCfg<5>::NT) { delete Pp; return plan_create(op, mesh, false); } // irregular batches: the 5-warp kernel has no such limits
     CUDA_CHECK(cudaMalloc(&P.d_cnt4, cnt4.size() * sizeof(int4)));
     CUDA_CHECK(cudaMemcpy(P.d_cnt4, cnt4.data(), cnt4.size() * sizeof(int4), cudaMemcpyHostToDevice));
   }
@@ -930,14 +932,6 @@ size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh)
   }
   op.cart_plan = Pp;
   return P.smem;
-}
-
-static size_t cartesian_plan_create_fallback(DeviceOperator & op, const HostMesh & mesh)
-{
-  setenv("EXADG_B200_NO_PIPE", "1", 1); // irregular batches: the 5-warp kernel has no such limits
-  const size_t r = cartesian_plan_create(op, mesh);
-  unsetenv("EXADG_B200_NO_PIPE");
-  return r;
 }
 
 void cartesian_plan_destroy(DeviceOperator & op)
