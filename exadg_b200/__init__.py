@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = [
     "exadg_b200_chebyshev_set_interval", "exadg_b200_chebyshev_vmult", "exadg_b200_chebyshev_step", "exadg_b200_set_nccl_comm",
     "exadg_b200_nccl_unique_id", "exadg_b200_nccl_init", "exadg_b200_halo_n_peers", "exadg_b200_halo_peer",
     "exadg_b200_halo_send_list", "exadg_b200_ghost_global_ids", "exadg_b200_ghost_buffer", "exadg_b200_halo_pack",
-    "exadg_b200_fp64_peak", "exadg_b200_plan_create", "exadg_b200_plan_destroy", "exadg_b200_plan_sizes", "exadg_b200_plan_peer",
+    "exadg_b200_fp64_peak", "exadg_b200_cartesian_kernel", "exadg_b200_plan_create", "exadg_b200_plan_destroy", "exadg_b200_plan_sizes", "exadg_b200_plan_peer",
     "exadg_b200_plan_tables", "exadg_b200_p2p_export", "exadg_b200_p2p_connect",
 ]
 
@@ -97,6 +97,7 @@ def load_library():
     L.exadg_b200_ghost_buffer.restype = vp
     L.exadg_b200_ghost_buffer.argtypes = [vp]
     L.exadg_b200_halo_pack.argtypes = [vp, C.c_int, dp, dp]
+    L.exadg_b200_cartesian_kernel.argtypes = [C.c_int]
     L.exadg_b200_fp64_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.exadg_b200_plan_create.argtypes = [C.POINTER(HypercubeDesc), C.POINTER(vp)]
     L.exadg_b200_plan_destroy.argtypes = [vp]
@@ -110,7 +111,7 @@ def load_library():
 
 
 from .laplace_operator import (ChebyshevSmoother, ExaDGError, JacobiPreconditioner, KrylovSolverCG, PartitionPlan,  # noqa: E402
-                               LaplaceOperator, SolverData, fp64_peak)
+                               LaplaceOperator, SolverData, cartesian_kernel, fp64_peak)
 
 __all__ = ["LaplaceOperator", "KrylovSolverCG", "ChebyshevSmoother", "JacobiPreconditioner", "SolverData", "ExaDGError",
-           "fp64_peak", "load_library", "PERIODIC", "DIRICHLET", "NEUMANN"]
+           "fp64_peak", "cartesian_kernel", "load_library", "PERIODIC", "DIRICHLET", "NEUMANN"]

@@ -851,6 +851,8 @@ int exadg_b200_ghost_global_ids(const exadg_b200_operator * op, int64_t * ids)
   std::memcpy(ids, op->mesh.ghost_global.data(), op->mesh.ghost_global.size() * sizeof(int64_t));
   return EXADG_B200_OK;
 }
+int exadg_b200_cartesian_kernel(int variant) { return cartesian_kernel_variant(variant); }
+
 int exadg_b200_fp64_peak(double * dfma_tflops, double * dmma_tflops)
 { return guarded([&]() { fp64_peak(dfma_tflops, dmma_tflops); return EXADG_B200_OK; }); }
 double * exadg_b200_ghost_buffer(exadg_b200_operator * op) { return op ? op->dev.ghost : nullptr; }

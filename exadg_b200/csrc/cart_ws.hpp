@@ -1,0 +1,486 @@
+// Warp-specialised Cartesian vmult (n = 5): four compute warps + two producer warps per CTA.
+//
+// Same operator and the same Kronecker formulation as vmult_cartesian.cu (cell_loop + face_loop of
+// I/operators/operator_base.cpp:1349-1397, fluxes I/poisson/spatial_discretization/laplace_operator.h:180-197):
+//     y = (M x M x M) sum_d c_d (Minv L_d) u
+// What changes is who does what inside the CTA:
+//  * warps 0-3 (compute) own the 24-cell batch exactly like the pipelined kernel (one xy-plane of a cell per thread in
+//    registers for the x/y sweeps and the final M_x M_y, n z-lines per thread for the z sweep), but they no longer touch
+//    global memory: neighbour traces are read branch-free from shared memory through one precomputed index per
+//    (cell, face) - a non-negative value is the in-batch neighbour, a negative one the slot of the trace the producer
+//    prepared;
+//  * warps 4-5 (producers) run one batch ahead: they copy the next batch's index table, fetch the lines of all
+//    out-of-batch neighbour cells (a lane per line, 8 cells = 40 loads in flight per lane) and reduce them to the end
+//    value / end derivative traces in the other half of a double-buffered trace area.  One CTA-wide barrier per batch
+//    hands the buffers over; the compute warps synchronise among themselves on a named barrier.
+//
+// This header is written against a small run-time interface RT (thread ids, barriers, bulk copies), so that the very
+// same body is compiled twice: by nvcc with the PTX implementation (vmult_cartesian_ws.cu) and by g++ with an emulation
+// on OS threads (tests/cpp/ws_emulate.cpp), which checks indexing, barrier placement (ThreadSanitizer) and results
+// against the CPU oracle without a GPU.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+#include "tables.hpp"
+
+#if defined(__CUDACC__)
+#define WS_FN __device__ __forceinline__
+#define WS_UNROLL _Pragma("unroll")
+#else
+#define WS_FN inline
+#define WS_UNROLL
+#endif
+
+namespace exadg_b200
+{
+namespace ws
+{
+struct i2 { int x, y; };
+
+template<int N>
+struct WsTables
+{
+  double G[3][N * N];  // c_d Minv (K + own-side face terms)
+  double Pf[3][2][N];  // c_d Minv (1/2 sigma_s l'(s) - tau_hat_d e_s)   times the neighbour's end value
+  double Qh[3][2][N];  // -c_d 1/2 sigma_s Minv e_s                       times the neighbour's end derivative
+  double M[N * N];
+  double fd[2][N];     // l_j'(s)
+};
+
+template<int N>
+struct WsCfg
+{
+  static constexpr int B = 24;    // cells per batch: 3 octets of the Morton curve, 24 x 5 planes = 120 of 128 compute threads
+  static constexpr int NC = 128;  // compute threads (named barrier 1)
+  static constexpr int NP = 2;    // producer warps (5 or 6 warps per CTA cost the same register allocation)
+  static constexpr int NT = NC + 32 * NP;
+};
+
+struct WsArgs
+{
+  const i2 * halo;          // [n_batches][HL]: (local cell << 3 | face, neighbour cell), out-of-batch faces of the batch
+  const int32_t * cnt;      // [n_batches]
+  const int32_t * nloc;     // [n_batches][B * 6]: >= 0 in-batch neighbour (local index), < 0: -1 - (entry of the halo list)
+  const int32_t * batches;  // optional list of batch ids
+  const double * src; const double * ghost; double * dst;
+  int64_t n_owned; int n_items; int HL; int add;
+};
+
+// shared memory of one CTA in bytes (doubles first, then the int tables, then the mbarrier)
+template<int N>
+inline size_t ws_smem_bytes(int HL)
+{
+  constexpr int B = WsCfg<N>::B, N2 = N * N, N3 = N2 * N;
+  return ((size_t)2 * B * N3 + (size_t)2 * B * N2 + (size_t)4 * HL * N2) * sizeof(double) + (size_t)2 * B * 6 * sizeof(int) + (size_t)HL * sizeof(i2) + 16;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side: 1-D tables and the batch plan
+// ---------------------------------------------------------------------------------------------------------------
+template<int N>
+inline WsTables<N> make_ws_tables(const double h[3], double tau_op)
+{
+  Tables1D tab(N - 1);
+  WsTables<N> T;
+  for (int d = 0; d < 3; ++d) {
+    const real_t cd = (real_t)h[(d + 1) % 3] * h[(d + 2) % 3] / h[d];
+    const real_t tau_hat = (real_t)tau_op * h[d];
+    // 1-D SIPG operator of the cell's own unknowns: K - 1/2 sigma (l' e^T + e l'^T) + tau_hat e e^T at both ends
+    std::vector<real_t> L(tab.K);
+    for (int s = 0; s < 2; ++s) {
+      const real_t sig = s ? 1 : -1; const int end = s ? N - 1 : 0;
+      for (int i = 0; i < N; ++i) { L[i * N + end] -= sig * tab.fd[s][i] / 2; L[end * N + i] -= sig * tab.fd[s][i] / 2; }
+      L[end * N + end] += tau_hat;
+    }
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) {
+        real_t v = 0;
+        for (int m = 0; m < N; ++m) v += tab.Minv[i * N + m] * L[m * N + j];
+        T.G[d][i * N + j] = (double)(cd * v);
+      }
+    // coupling to the neighbour behind end s: + 1/2 sigma l'(s) v_nb  -  e_s (1/2 sigma g_nb + tau_hat v_nb)
+    for (int s = 0; s < 2; ++s) {
+      const real_t sig = s ? 1 : -1; const int end = s ? N - 1 : 0;
+      for (int i = 0; i < N; ++i) {
+        real_t md = 0;
+        for (int m = 0; m < N; ++m) md += tab.Minv[i * N + m] * tab.fd[s][m];
+        T.Pf[d][s][i] = (double)(cd * (sig / 2 * md - tau_hat * tab.Minv[i * N + end]));
+        T.Qh[d][s][i] = (double)(-cd * sig / 2 * tab.Minv[i * N + end]);
+      }
+    }
+  }
+  for (int i = 0; i < N * N; ++i) T.M[i] = (double)tab.M[i];
+  for (int s = 0; s < 2; ++s) for (int i = 0; i < N; ++i) T.fd[s][i] = (double)tab.fd[s][i];
+  return T;
+}
+
+struct WsHostPlan
+{
+  int B = 0, HL = 0, n_batches = 0;
+  std::vector<i2> halo;            // [n_batches][HL]
+  std::vector<int32_t> cnt, nloc;  // [n_batches], [n_batches][B * 6]
+};
+
+// nb: [n_owned][6] local neighbour indices (ghost cells >= n_owned); every face has a neighbour on this path
+inline WsHostPlan ws_build_plan(const int32_t * nb, int64_t n_owned, int B)
+{
+  WsHostPlan P;
+  P.B = B;
+  P.n_batches = (int)((n_owned + B - 1) / B);
+  std::vector<std::vector<i2>> lists(P.n_batches);
+  P.nloc.assign((size_t)P.n_batches * B * 6, 0);
+  P.cnt.assign(P.n_batches, 0);
+  for (int b = 0; b < P.n_batches; ++b) {
+    const int64_t b0 = (int64_t)b * B, b1 = std::min<int64_t>(b0 + B, n_owned);
+    for (int64_t c = b0; c < b1; ++c)
+      for (int f = 0; f < 6; ++f) {
+        const int32_t p = nb[c * 6 + f];
+        int32_t & nl = P.nloc[((size_t)b * B + (size_t)(c - b0)) * 6 + f];
+        if (p >= b0 && p < b1) nl = (int32_t)(p - b0);
+        else { nl = -1 - (int32_t)lists[b].size(); lists[b].push_back(i2{(int)(((c - b0) << 3) | f), p}); }
+      }
+    P.cnt[b] = (int32_t)lists[b].size();
+    P.HL = std::max(P.HL, P.cnt[b]);
+  }
+  P.HL = std::max(P.HL, 1);
+  P.halo.assign((size_t)P.n_batches * P.HL, i2{0, 0});
+  for (int b = 0; b < P.n_batches; ++b) std::copy(lists[b].begin(), lists[b].end(), P.halo.begin() + (size_t)b * P.HL);
+  return P;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// device side (or its emulation): the body of one CTA
+// ---------------------------------------------------------------------------------------------------------------
+
+WS_FN int64_t ws_min(int64_t a, int64_t b) { return a < b ? a : b; }
+
+// producer warp pw: index table + traces of the out-of-batch neighbours of batch bt -> the given halves of the buffers.
+// The rounds of R halo entries are dealt to the producer warps in turn; a warp stages exactly the entries it reduces, so a
+// warp-level barrier orders its accesses to hlS.
+// R = neighbour cells per round (R * n loads in flight per lane)
+template<int N, int R, class RT>
+WS_FN void ws_produce(RT & rt, const WsTables<N> & T, const WsArgs & A, int bt, int pw, int lane, double * TRV, double * TRG, int * nlS, i2 * hlS)
+{
+  constexpr int B = WsCfg<N>::B, NP = WsCfg<N>::NP, N2 = N * N, N3 = N2 * N;
+  const int cnt = A.cnt[bt];
+  for (int i = pw * 32 + lane; i < B * 6; i += 32 * NP) nlS[i] = A.nloc[(size_t)bt * (B * 6) + i];
+  for (int e0 = pw * R; e0 < cnt; e0 += NP * R)
+    if (lane < R && e0 + lane < cnt) hlS[e0 + lane] = A.halo[(size_t)bt * A.HL + e0 + lane];
+  rt.sync_producer(pw);
+  const bool act = lane < N2;
+  const int ab = act ? lane : 0; // line within the face; the spare lanes shadow line 0 and store nothing
+  for (int e0 = pw * R; e0 < cnt; e0 += NP * R) {
+    double x[R][N];
+    int hx[R];
+    WS_UNROLL
+    for (int q = 0; q < R; ++q) {
+      const int e = e0 + q;
+      if (e < cnt) { // warp-uniform
+        const i2 h = hlS[e];
+        hx[q] = h.x;
+        const int D = (h.x & 7) >> 1;
+        const int sd = (D == 0) ? 1 : (D == 1 ? N : N2);
+        const int s1 = (D == 0) ? N : 1, s2 = (D == 2) ? N : N2;
+        const double * line = ((h.y < A.n_owned) ? A.src + (size_t)h.y * N3 : A.ghost + (size_t)(h.y - A.n_owned) * N3) + (ab % N) * s1 + (ab / N) * s2;
+        WS_UNROLL
+        for (int i = 0; i < N; ++i) x[q][i] = line[i * sd];
+      } else {
+        hx[q] = 0;
+        WS_UNROLL
+        for (int i = 0; i < N; ++i) x[q][i] = 0.0;
+      }
+    }
+    WS_UNROLL
+    for (int q = 0; q < R; ++q) {
+      const int e = e0 + q;
+      if (e < cnt) {
+        double g, v;
+        if (!(hx[q] & 1)) { // our lower face: the neighbour is entered through its upper end (warp-uniform)
+          g = T.fd[1][0] * x[q][0];
+          WS_UNROLL
+          for (int i = 1; i < N; ++i) g = fma(T.fd[1][i], x[q][i], g);
+          v = x[q][N - 1];
+        } else {
+          g = T.fd[0][0] * x[q][0];
+          WS_UNROLL
+          for (int i = 1; i < N; ++i) g = fma(T.fd[0][i], x[q][i], g);
+          v = x[q][0];
+        }
+        if (act) { TRV[e * N2 + ab] = v; TRG[e * N2 + ab] = g; }
+      }
+    }
+  }
+}
+
+template<int N, int R, class RT>
+WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
+{
+  constexpr int B = WsCfg<N>::B, NC = WsCfg<N>::NC;
+  constexpr int N2 = N * N, N3 = N2 * N;
+  static_assert((N2 & 1) == 1, "odd n: contiguous cells in shared memory are conflict-free and bulk-copyable");
+  static_assert(B * N <= NC, "one thread per cell plane");
+  double * const smem = rt.smem();
+  const int trs = A.HL * N2;                   // doubles per trace array
+  constexpr int OFF_T = B * N3;                // partial results, finally the result (bulk-store source)
+  constexpr int OFF_GN = 2 * B * N3;           // [2][B][N2] own end derivatives of the current direction
+  constexpr int OFF_TR = OFF_GN + 2 * B * N2;  // [2 buffers][values, derivatives][HL][N2] traces of out-of-batch neighbours
+  double * const U = smem;                     // [B][N3] src values of the batch (bulk-copy destination)
+  double * const Tt = smem + OFF_T;
+  double * const GN = smem + OFF_GN;
+  int * const nl2 = reinterpret_cast<int *>(smem + OFF_TR + 4 * trs); // [2][B * 6]
+  i2 * const hlS = reinterpret_cast<i2 *>(nl2 + 2 * B * 6);           // [HL] producer-private copy of the halo list
+  void * const bar = hlS + A.HL;
+
+  const int t = rt.tid();
+  const bool producer = t >= NC;
+  if (t == 0) rt.bar_init(bar);
+  rt.sync_all();
+  const int first = rt.cta(), step = rt.ncta();
+  if (first >= A.n_items) return;
+  const int lc = t / N, s = t % N;    // plane layout
+  const int lz = t % B, sz = t / B;   // z-line layout: consecutive lanes = consecutive cells (stride n^3, odd -> conflict-free)
+
+  // ---- prologue: traces + index table of the first batch, its bulk copy ----
+  {
+    const int bt = A.batches ? A.batches[first] : first;
+    if (producer) ws_produce<N, R>(rt, T, A, bt, (t - NC) / 32, (t - NC) % 32, smem + OFF_TR, smem + OFF_TR + trs, nl2, hlS);
+    else if (t == 0) {
+      const int64_t c0 = (int64_t)bt * B;
+      const uint32_t by = (uint32_t)((int)ws_min(B, A.n_owned - c0) * N3 * sizeof(double));
+      if (by % 16 == 0) rt.load_issue(bar, U, A.src + c0 * N3, by);
+    }
+  }
+  rt.sync_all();
+
+  // The two roles run their own loops over the same batch sequence and meet at the CTA-wide barrier once per batch.
+  if (producer) {
+    int buf = 0;
+    for (int it = first; it < A.n_items; it += step, buf ^= 1) {
+      const int itn = it + step;
+      if (itn < A.n_items) {
+        const int bn = A.batches ? A.batches[itn] : itn;
+        ws_produce<N, R>(rt, T, A, bn, (t - NC) / 32, (t - NC) % 32, smem + OFF_TR + (buf ^ 1) * 2 * trs, smem + OFF_TR + (buf ^ 1) * 2 * trs + trs, nl2 + (buf ^ 1) * B * 6, hlS);
+      }
+      rt.sync_all(); // hand-over: traces / index table of the next batch are complete, those of this batch are free
+    }
+    return;
+  }
+  int buf = 0;
+  for (int it = first; it < A.n_items; it += step, buf ^= 1) {
+    const int itn = it + step;
+    const bool has_next = itn < A.n_items;
+    {
+      const int batch = A.batches ? A.batches[it] : it;
+      const int64_t b0 = (int64_t)batch * B;
+      const int nvalid = (int)ws_min(B, A.n_owned - b0);
+      const uint32_t bytes = (uint32_t)(nvalid * N3 * sizeof(double));
+      const bool use_tma = (bytes % 16 == 0);
+      const bool valid = lc < nvalid;               // also false for t >= B * N
+      const bool validz = (sz < N) && (lz < nvalid);
+      const int * nlS = nl2 + buf * B * 6;
+      const int off_trv = OFF_TR + buf * 2 * trs, off_trg = off_trv + trs;
+
+      int nlp[4] = {0, 0, 0, 0};
+      if (valid) {
+        WS_UNROLL
+        for (int f = 0; f < 4; ++f) nlp[f] = nlS[lc * 6 + f];
+      }
+      if (use_tma) rt.load_wait(bar);
+      else {
+        for (int i = t; i < nvalid * N3; i += NC) U[i] = A.src[b0 * N3 + i]; // ragged last batch
+        rt.sync_compute();
+      }
+
+      double u[N][N], acc[N][N];
+      if (valid) {
+        WS_UNROLL
+        for (int j = 0; j < N; ++j)
+          WS_UNROLL
+          for (int i = 0; i < N; ++i) { u[j][i] = U[lc * N3 + s * N2 + i + N * j]; acc[j][i] = 0.0; }
+      }
+      // ---- x and y sweeps on the register plane z = s ----
+      WS_UNROLL
+      for (int d = 0; d < 2; ++d) {
+        if (valid) {
+          double g0[N], g1[N];
+          WS_UNROLL
+          for (int l = 0; l < N; ++l) { const double x = (d == 0) ? u[l][0] : u[0][l]; g0[l] = T.fd[0][0] * x; g1[l] = T.fd[1][0] * x; }
+          WS_UNROLL
+          for (int m = 1; m < N; ++m)
+            WS_UNROLL
+            for (int l = 0; l < N; ++l) {
+              const double x = (d == 0) ? u[l][m] : u[m][l];
+              g0[l] = fma(T.fd[0][m], x, g0[l]); g1[l] = fma(T.fd[1][m], x, g1[l]);
+            }
+          WS_UNROLL
+          for (int l = 0; l < N; ++l) { GN[(0 * B + lc) * N2 + s * N + l] = g0[l]; GN[(1 * B + lc) * N2 + s * N + l] = g1[l]; }
+        }
+        rt.sync_compute();
+        if (valid) {
+          WS_UNROLL
+          for (int side = 0; side < 2; ++side) {
+            const int nl = nlp[2 * d + side];
+            const bool inb = nl >= 0;
+            const int e = -1 - nl;
+            const int endn = side ? 0 : N - 1; // the neighbour's end node facing us
+            const int voff = inb ? nl * N3 + s * N2 + (d == 0 ? endn : N * endn) : off_trv + e * N2 + N * s;
+            const int vstr = (inb && d == 0) ? N : 1;
+            const int goff = inb ? OFF_GN + ((side ^ 1) * B + nl) * N2 + s * N : off_trg + e * N2 + N * s;
+            double vn[N], gn[N];
+            WS_UNROLL
+            for (int l = 0; l < N; ++l) { vn[l] = smem[voff + l * vstr]; gn[l] = smem[goff + l]; }
+            WS_UNROLL
+            for (int m = 0; m < N; ++m)
+              WS_UNROLL
+              for (int l = 0; l < N; ++l) {
+                if (d == 0) acc[l][m] = fma(T.Pf[d][side][m], vn[l], acc[l][m]); else acc[m][l] = fma(T.Pf[d][side][m], vn[l], acc[m][l]);
+              }
+            WS_UNROLL
+            for (int m = 0; m < N; ++m)
+              WS_UNROLL
+              for (int l = 0; l < N; ++l) {
+                if (d == 0) acc[l][m] = fma(T.Qh[d][side][m], gn[l], acc[l][m]); else acc[m][l] = fma(T.Qh[d][side][m], gn[l], acc[m][l]);
+              }
+          }
+          WS_UNROLL
+          for (int c = 0; c < N; ++c)
+            WS_UNROLL
+            for (int l = 0; l < N; ++l)
+              WS_UNROLL
+              for (int r = 0; r < N; ++r) {
+                if (d == 0) acc[l][r] = fma(T.G[d][r * N + c], u[l][c], acc[l][r]);
+                else acc[r][l] = fma(T.G[d][r * N + c], u[c][l], acc[r][l]);
+              }
+        }
+        if (d == 1 && t == 0) rt.store_wait_read(); // the previous batch's bulk store has read Tt
+        rt.sync_compute();                          // GN of this direction is consumed
+      }
+      if (valid) {
+        WS_UNROLL
+        for (int j = 0; j < N; ++j)
+          WS_UNROLL
+          for (int i = 0; i < N; ++i) Tt[lc * N3 + s * N2 + i + N * j] = acc[j][i];
+      }
+      // ---- z sweep: thread (cell lz, slice sz) owns the lines (i, j = sz) ----
+      int nlz[2] = {0, 0};
+      if (validz) {
+        nlz[0] = nlS[lz * 6 + 4]; nlz[1] = nlS[lz * 6 + 5];
+        WS_UNROLL
+        for (int i = 0; i < N; ++i)
+          WS_UNROLL
+          for (int k = 0; k < N; ++k) u[i][k] = U[lz * N3 + k * N2 + i + N * sz];
+        double g0[N], g1[N];
+        WS_UNROLL
+        for (int i = 0; i < N; ++i) { g0[i] = T.fd[0][0] * u[i][0]; g1[i] = T.fd[1][0] * u[i][0]; }
+        WS_UNROLL
+        for (int k = 1; k < N; ++k)
+          WS_UNROLL
+          for (int i = 0; i < N; ++i) { g0[i] = fma(T.fd[0][k], u[i][k], g0[i]); g1[i] = fma(T.fd[1][k], u[i][k], g1[i]); }
+        WS_UNROLL
+        for (int i = 0; i < N; ++i) { GN[(0 * B + lz) * N2 + sz * N + i] = g0[i]; GN[(1 * B + lz) * N2 + sz * N + i] = g1[i]; }
+      }
+      rt.sync_compute(); // Tt planes and z end derivatives visible
+      if (validz) {
+        WS_UNROLL
+        for (int i = 0; i < N; ++i)
+          WS_UNROLL
+          for (int k = 0; k < N; ++k) acc[i][k] = Tt[lz * N3 + k * N2 + i + N * sz];
+        WS_UNROLL
+        for (int side = 0; side < 2; ++side) {
+          const int nl = nlz[side];
+          const bool inb = nl >= 0;
+          const int e = -1 - nl;
+          const int endn = side ? 0 : N - 1;
+          const int voff = inb ? nl * N3 + endn * N2 + N * sz : off_trv + e * N2 + N * sz;
+          const int goff = inb ? OFF_GN + ((side ^ 1) * B + nl) * N2 + sz * N : off_trg + e * N2 + N * sz;
+          double vn[N], gn[N];
+          WS_UNROLL
+          for (int i = 0; i < N; ++i) { vn[i] = smem[voff + i]; gn[i] = smem[goff + i]; }
+          WS_UNROLL
+          for (int k = 0; k < N; ++k)
+            WS_UNROLL
+            for (int i = 0; i < N; ++i) acc[i][k] = fma(T.Pf[2][side][k], vn[i], acc[i][k]);
+          WS_UNROLL
+          for (int k = 0; k < N; ++k)
+            WS_UNROLL
+            for (int i = 0; i < N; ++i) acc[i][k] = fma(T.Qh[2][side][k], gn[i], acc[i][k]);
+        }
+        WS_UNROLL
+        for (int c = 0; c < N; ++c)
+          WS_UNROLL
+          for (int i = 0; i < N; ++i)
+            WS_UNROLL
+            for (int r = 0; r < N; ++r) acc[i][r] = fma(T.G[2][r * N + c], u[i][c], acc[i][r]);
+        // mass matrix along z: u <- M acc
+        WS_UNROLL
+        for (int i = 0; i < N; ++i)
+          WS_UNROLL
+          for (int r = 0; r < N; ++r) u[i][r] = T.M[r * N] * acc[i][0];
+        WS_UNROLL
+        for (int c = 1; c < N; ++c)
+          WS_UNROLL
+          for (int i = 0; i < N; ++i)
+            WS_UNROLL
+            for (int r = 0; r < N; ++r) u[i][r] = fma(T.M[r * N + c], acc[i][c], u[i][r]);
+        WS_UNROLL
+        for (int i = 0; i < N; ++i)
+          WS_UNROLL
+          for (int r = 0; r < N; ++r) Tt[lz * N3 + r * N2 + i + N * sz] = u[i][r];
+      }
+      rt.sync_compute(); // U is dead from here on
+      if (has_next && t == 0) {
+        const int64_t c0 = (int64_t)(A.batches ? A.batches[itn] : itn) * B;
+        const uint32_t by = (uint32_t)((int)ws_min(B, A.n_owned - c0) * N3 * sizeof(double));
+        if (by % 16 == 0) { rt.fence_async(); rt.load_issue(bar, U, A.src + c0 * N3, by); }
+      }
+      // ---- mass matrices along x and y on the register plane, in place in Tt ----
+      if (valid) {
+        WS_UNROLL
+        for (int j = 0; j < N; ++j)
+          WS_UNROLL
+          for (int i = 0; i < N; ++i) u[j][i] = Tt[lc * N3 + s * N2 + i + N * j];
+        WS_UNROLL
+        for (int j = 0; j < N; ++j)
+          WS_UNROLL
+          for (int r = 0; r < N; ++r) acc[j][r] = T.M[r * N] * u[j][0];
+        WS_UNROLL
+        for (int c = 1; c < N; ++c)
+          WS_UNROLL
+          for (int j = 0; j < N; ++j)
+            WS_UNROLL
+            for (int r = 0; r < N; ++r) acc[j][r] = fma(T.M[r * N + c], u[j][c], acc[j][r]);
+        WS_UNROLL
+        for (int r = 0; r < N; ++r)
+          WS_UNROLL
+          for (int i = 0; i < N; ++i) u[r][i] = T.M[r * N] * acc[0][i];
+        WS_UNROLL
+        for (int c = 1; c < N; ++c)
+          WS_UNROLL
+          for (int r = 0; r < N; ++r)
+            WS_UNROLL
+            for (int i = 0; i < N; ++i) u[r][i] = fma(T.M[r * N + c], acc[c][i], u[r][i]);
+        WS_UNROLL
+        for (int r = 0; r < N; ++r)
+          WS_UNROLL
+          for (int i = 0; i < N; ++i) Tt[lc * N3 + s * N2 + i + N * r] = u[r][i];
+      }
+      if (use_tma) {
+        rt.fence_async();
+        rt.sync_compute(); // result complete
+        if (t == 0) rt.store_issue(A.dst + b0 * N3, Tt, bytes, A.add != 0); // read of Tt awaited before the next batch writes it
+      } else {
+        rt.sync_compute();
+        for (int i = t; i < nvalid * N3; i += NC) { if (A.add) A.dst[b0 * N3 + i] += Tt[i]; else A.dst[b0 * N3 + i] = Tt[i]; }
+      }
+    }
+    rt.sync_all(); // hand-over: traces / index table of the next batch are complete, those of this batch are free
+  }
+  if (t == 0) rt.store_wait_all(); // all bulk stores complete before the CTA exits
+}
+
+} // namespace ws
+} // namespace exadg_b200

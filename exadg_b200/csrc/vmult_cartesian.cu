@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "cart_ws.hpp"
 #include "operator.cuh"
 
 namespace exadg_b200
@@ -768,7 +769,13 @@ struct CartPlan
   std::vector<char> tables; // CartTables<n> of this operator (depends on h and tau)
   // pipelined kernel (n = 5)
   bool pipe = false; int HL = 0, HD = 0, n_sm = 148; int4 * d_cnt4 = nullptr;
+  // warp-specialised kernel (n = 5, same 24-cell batches): vmult_cartesian_ws.cu
+  void * ws = nullptr;
 };
+
+// kernel of the fast path for n = 5: 0 pipelined 4-warp kernel, 1 / 2 warp-specialised kernel with producer depth 8 / 12
+// (EXADG_B200_CART_KERNEL=ws / ws12)
+int g_cart_kernel = -1;
 
 template<int N>
 CartTables<N> make_cart_tables(const DeviceOperator & op)
@@ -846,6 +853,14 @@ void launch_pipe(const DeviceOperator & op, const CartPlan & plan, double * dst,
 } // namespace
 
 bool cartesian_supported(int n) { return n >= 2 && n <= 8; }
+
+int cartesian_kernel_variant(int set)
+{
+  if (g_cart_kernel < 0) { const char * e = getenv("EXADG_B200_CART_KERNEL"); g_cart_kernel = (e && std::strcmp(e, "ws") == 0) ? 1 : ((e && std::strcmp(e, "ws12") == 0) ? 2 : 0); }
+  const int previous = g_cart_kernel;
+  if (set >= 0) g_cart_kernel = set;
+  return previous;
+}
 
 template<int N>
 void store_tables(CartPlan & P, const DeviceOperator & op)
@@ -930,6 +945,10 @@ static size_t plan_create(DeviceOperator & op, const HostMesh & mesh, bool allow
     case 8: store_tables<8>(P, op); break;
     default: delete Pp; return 0;
   }
+  if (P.pipe && P.B == ws::WsCfg<5>::B) {
+    // optional second kernel for the same batches; stays null if the batches are too irregular for it or anything goes wrong
+    try { P.ws = ws_plan_create(op, mesh); } catch (const std::exception &) { P.ws = nullptr; cudaGetLastError(); }
+  }
   op.cart_plan = Pp;
   return P.smem;
 }
@@ -939,6 +958,7 @@ void cartesian_plan_destroy(DeviceOperator & op)
   CartPlan * P = static_cast<CartPlan *>(op.cart_plan);
   if (!P) return;
   cudaFree(P->d_halo); cudaFree(P->d_cnt); cudaFree(P->d_cnt4); cudaFree(P->d_interior); cudaFree(P->d_boundary);
+  ws_plan_destroy(P->ws);
   delete P;
   op.cart_plan = nullptr;
 }
@@ -952,7 +972,12 @@ void launch_vmult_cartesian_part(const DeviceOperator & op, double * dst, const 
     case 2: launch_n<2>(op, *plan, dst, src, add, which, stream); break;
     case 3: if (plan->pipe) launch_pipe<3>(op, *plan, dst, src, add, which, stream); else launch_n<3>(op, *plan, dst, src, add, which, stream); break;
     case 4: launch_n<4>(op, *plan, dst, src, add, which, stream); break;
-    case 5: if (plan->pipe) launch_pipe<5>(op, *plan, dst, src, add, which, stream); else launch_n<5>(op, *plan, dst, src, add, which, stream); break;
+    case 5:
+      if (plan->ws && which == 0 && cartesian_kernel_variant(-1) >= 1) // interior/boundary launches of the multi-GPU path: pipelined kernel until verified on >= 2 GPUs
+        ws_launch(op, plan->ws, dst, src, add, nullptr, plan->n_batches, plan->n_sm, cartesian_kernel_variant(-1) == 2 ? 12 : 8, stream);
+      else if (plan->pipe) launch_pipe<5>(op, *plan, dst, src, add, which, stream);
+      else launch_n<5>(op, *plan, dst, src, add, which, stream);
+      break;
     case 6: launch_n<6>(op, *plan, dst, src, add, which, stream); break;
     case 7: launch_n<7>(op, *plan, dst, src, add, which, stream); break;
     case 8: launch_n<8>(op, *plan, dst, src, add, which, stream); break;

@@ -1,0 +1,129 @@
+// Warp-specialised Cartesian vmult for n = 5 (k = 4): device side of cart_ws.hpp - the PTX run-time interface (named
+// barriers, mbarrier + 1-D bulk copies), the kernel wrapper, the device copy of the batch plan and the launch.
+// The CTA body itself lives in cart_ws.hpp and is also compiled for the CPU emulation (tests/cpp/ws_emulate.cpp).
+#include <cstring>
+
+#include "cart_ws.hpp"
+#include "operator.cuh"
+
+namespace exadg_b200
+{
+namespace
+{
+using namespace ws;
+
+__device__ __forceinline__ uint32_t s32(const void * p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct DeviceRT
+{
+  double * base;
+  uint32_t parity;
+  __device__ __forceinline__ double * smem() const { return base; }
+  __device__ __forceinline__ int tid() const { return (int)threadIdx.x; }
+  __device__ __forceinline__ int cta() const { return (int)blockIdx.x; }
+  __device__ __forceinline__ int ncta() const { return (int)gridDim.x; }
+  __device__ __forceinline__ void bar_init(void * bar)
+  {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __device__ __forceinline__ void sync_all() { asm volatile("bar.sync 2, %0;" ::"n"(WsCfg<5>::NT) : "memory"); } // reached from both roles' loops
+  __device__ __forceinline__ void sync_compute() { asm volatile("bar.sync 1, %0;" ::"n"(WsCfg<5>::NC) : "memory"); }
+  __device__ __forceinline__ void sync_producer(int) { __syncwarp(); }
+  // global -> shared bulk copy, completion on the mbarrier (SASS: UBLKCP)
+  __device__ __forceinline__ void load_issue(void * bar, double * dst, const double * src, uint32_t bytes)
+  {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)), "l"(src), "r"(bytes), "r"(s32(bar)) : "memory");
+  }
+  __device__ __forceinline__ void load_wait(void * bar)
+  {
+    uint32_t done;
+    do {
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(s32(bar)), "r"(parity) : "memory");
+    } while (!done);
+    parity ^= 1;
+  }
+  __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+  // shared -> global bulk copy (plain store, or FP64 add-reduction for vmult_add)
+  __device__ __forceinline__ void store_issue(double * g, const double * s, uint32_t bytes, bool add)
+  {
+    if (add) asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(g), "r"(s32(s)), "r"(bytes) : "memory");
+    else asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(s32(s)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  __device__ __forceinline__ void store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+  __device__ __forceinline__ void store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+};
+
+template<int N, int R>
+__global__ void __launch_bounds__(WsCfg<N>::NT, 2) vmult_cartesian_ws_kernel(const __grid_constant__ WsTables<N> T, const WsArgs A)
+{
+  extern __shared__ __align__(128) double ws_shared[];
+  DeviceRT rt{ws_shared, 0u};
+  ws_cta<N, R>(rt, T, A);
+}
+
+constexpr size_t WS_MAX_SMEM = 228 * 1024 / 2 - 1024; // half of an SM's shared memory minus the per-CTA reservation
+
+struct WsDevPlan
+{
+  i2 * d_halo = nullptr; int32_t * d_cnt = nullptr, * d_nloc = nullptr;
+  int HL = 0, n_batches = 0, ctas_per_sm = 0;
+  size_t smem = 0;
+  WsTables<5> T;
+};
+} // namespace
+
+bool ws_supported(int n) { return n == 5; }
+
+// device copy of the batch plan; nullptr if the batches are too irregular for the double-buffered trace area
+void * ws_plan_create(const DeviceOperator & op, const HostMesh & mesh)
+{
+  if (!ws_supported(op.n)) return nullptr;
+  const WsHostPlan H = ws_build_plan(mesh.nb.data(), mesh.n_owned, WsCfg<5>::B);
+  const size_t smem = ws_smem_bytes<5>(H.HL);
+  if (smem > WS_MAX_SMEM) return nullptr; // two CTAs per SM are what the kernel is built for
+  WsDevPlan * P = new WsDevPlan;
+  P->HL = H.HL; P->n_batches = H.n_batches; P->smem = smem;
+  P->T = make_ws_tables<5>(op.h, op.tau_hat);
+  CUDA_CHECK(cudaMalloc(&P->d_halo, H.halo.size() * sizeof(i2)));
+  CUDA_CHECK(cudaMemcpy(P->d_halo, H.halo.data(), H.halo.size() * sizeof(i2), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMalloc(&P->d_cnt, H.cnt.size() * sizeof(int32_t)));
+  CUDA_CHECK(cudaMemcpy(P->d_cnt, H.cnt.data(), H.cnt.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMalloc(&P->d_nloc, H.nloc.size() * sizeof(int32_t)));
+  CUDA_CHECK(cudaMemcpy(P->d_nloc, H.nloc.data(), H.nloc.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaFuncSetAttribute(vmult_cartesian_ws_kernel<5, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_MAX_SMEM)); // same for every operator
+  CUDA_CHECK(cudaFuncSetAttribute(vmult_cartesian_ws_kernel<5, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_MAX_SMEM));
+  int occ12 = 0;
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&P->ctas_per_sm, vmult_cartesian_ws_kernel<5, 8>, WsCfg<5>::NT, smem));
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ12, vmult_cartesian_ws_kernel<5, 12>, WsCfg<5>::NT, smem));
+  P->ctas_per_sm = std::min(P->ctas_per_sm, occ12);
+  if (P->ctas_per_sm < 1) { ws_plan_destroy(P); return nullptr; }
+  return P;
+}
+
+void ws_plan_destroy(void * p)
+{
+  WsDevPlan * P = static_cast<WsDevPlan *>(p);
+  if (!P) return;
+  cudaFree(P->d_halo); cudaFree(P->d_cnt); cudaFree(P->d_nloc);
+  delete P;
+}
+
+// batches: optional list of batch ids (interior / boundary launches of the multi-GPU path), n_items its length (or all batches)
+// depth: neighbour cells per producer round (8 or 12)
+void ws_launch(const DeviceOperator & op, const void * p, double * dst, const double * src, bool add, const int32_t * batches, int n_items, int n_sm, int depth, cudaStream_t stream)
+{
+  const WsDevPlan * P = static_cast<const WsDevPlan *>(p);
+  if (n_items == 0) return;
+  WsArgs A;
+  A.halo = P->d_halo; A.cnt = P->d_cnt; A.nloc = P->d_nloc; A.batches = batches;
+  A.src = src; A.ghost = op.ghost; A.dst = dst; A.n_owned = op.n_owned; A.n_items = n_items; A.HL = P->HL; A.add = add ? 1 : 0;
+  const int grid = std::min(n_items, n_sm * P->ctas_per_sm);
+  if (depth == 12) vmult_cartesian_ws_kernel<5, 12><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A);
+  else vmult_cartesian_ws_kernel<5, 8><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+} // namespace exadg_b200

@@ -341,6 +341,12 @@ def fp64_peak():
     return a.value, b.value
 
 
+def cartesian_kernel(variant=-1):
+    """Kernel of the affine fast path for degree 4: 0 pipelined 4-warp kernel, 1 warp-specialised kernel; -1 only queries.
+    Process-wide tuning switch (no reference counterpart); returns the previous value."""
+    return _lib().exadg_b200_cartesian_kernel(int(variant))
+
+
 class PartitionPlan:
     """Host-only partition / halo plan of a hypercube grid (no GPU needed): what MatrixFree's
     Utilities::MPI::Partitioner holds for the ghost import of src (SURVEY 8e)."""
