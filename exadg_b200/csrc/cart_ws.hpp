@@ -10,8 +10,9 @@
 //    (cell, face) - a non-negative value is the in-batch neighbour, a negative one the slot of the trace the producer
 //    prepared;
 //  * warps 4-5 (producers) run one batch ahead: they copy the next batch's index table, fetch the lines of all
-//    out-of-batch neighbour cells (a lane per line, 8 cells = 40 loads in flight per lane) and reduce them to the end
-//    value / end derivative traces in the other half of a double-buffered trace area.  One CTA-wide barrier per batch
+//    out-of-batch neighbour cells (a lane per line, R cells = 5 R loads in flight per lane; the halo list is sorted by
+//    direction so that the strides are compile-time constants) and reduce them to the end value / end derivative
+//    traces in the other half of a double-buffered trace area.  One CTA-wide barrier per batch
 //    hands the buffers over; the compute warps synchronise among themselves on a named barrier.
 //
 // This header is written against a small run-time interface RT (thread ids, barriers, bulk copies), so that the very
@@ -58,12 +59,13 @@ struct WsCfg
   static constexpr int NC = 128;  // compute threads (named barrier 1)
   static constexpr int NP = 2;    // producer warps (5 or 6 warps per CTA cost the same register allocation)
   static constexpr int NT = NC + 32 * NP;
+  static constexpr int HLMAX = 64; // halo entries per batch the producers can stage (two per lane)
 };
 
 struct WsArgs
 {
-  const i2 * halo;          // [n_batches][HL]: (local cell << 3 | face, neighbour cell), out-of-batch faces of the batch
-  const int32_t * cnt;      // [n_batches]
+  const i2 * halo;          // [n_batches][HL]: (local cell << 3 | face, neighbour cell), out-of-batch faces of the batch, x faces first, then y, z
+  const int32_t * cnt;      // [n_batches] numbers of x, y, z entries packed as x | y << 10 | z << 20
   const int32_t * nloc;     // [n_batches][B * 6]: >= 0 in-batch neighbour (local index), < 0: -1 - (entry of the halo list)
   const int32_t * batches;  // optional list of batch ids
   const double * src; const double * ghost; double * dst;
@@ -75,7 +77,8 @@ template<int N>
 inline size_t ws_smem_bytes(int HL)
 {
   constexpr int B = WsCfg<N>::B, N2 = N * N, N3 = N2 * N;
-  return ((size_t)2 * B * N3 + (size_t)2 * B * N2 + (size_t)4 * HL * N2) * sizeof(double) + (size_t)2 * B * 6 * sizeof(int) + (size_t)HL * sizeof(i2) + 16;
+  return ((size_t)2 * B * N3 + (size_t)2 * B * N2 + (size_t)4 * HL * N2) * sizeof(double) + (size_t)2 * B * 6 * sizeof(int)
+         + (size_t)WsCfg<N>::NP * WsCfg<N>::HLMAX * sizeof(i2) + 16;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -136,15 +139,17 @@ inline WsHostPlan ws_build_plan(const int32_t * nb, int64_t n_owned, int B)
   P.cnt.assign(P.n_batches, 0);
   for (int b = 0; b < P.n_batches; ++b) {
     const int64_t b0 = (int64_t)b * B, b1 = std::min<int64_t>(b0 + B, n_owned);
-    for (int64_t c = b0; c < b1; ++c)
-      for (int f = 0; f < 6; ++f) {
-        const int32_t p = nb[c * 6 + f];
-        int32_t & nl = P.nloc[((size_t)b * B + (size_t)(c - b0)) * 6 + f];
-        if (p >= b0 && p < b1) nl = (int32_t)(p - b0);
-        else { nl = -1 - (int32_t)lists[b].size(); lists[b].push_back(i2{(int)(((c - b0) << 3) | f), p}); }
-      }
-    P.cnt[b] = (int32_t)lists[b].size();
-    P.HL = std::max(P.HL, P.cnt[b]);
+    int c[3] = {0, 0, 0};
+    for (int d = 0; d < 3; ++d) // entries sorted by direction: x faces, y faces, z faces
+      for (int64_t cell = b0; cell < b1; ++cell)
+        for (int f = 2 * d; f < 2 * d + 2; ++f) {
+          const int32_t p = nb[cell * 6 + f];
+          int32_t & nl = P.nloc[((size_t)b * B + (size_t)(cell - b0)) * 6 + f];
+          if (p >= b0 && p < b1) nl = (int32_t)(p - b0);
+          else { nl = -1 - (int32_t)lists[b].size(); lists[b].push_back(i2{(int)(((cell - b0) << 3) | f), p}); ++c[d]; }
+        }
+    P.cnt[b] = c[0] | (c[1] << 10) | (c[2] << 20);
+    P.HL = std::max(P.HL, (int)lists[b].size());
   }
   P.HL = std::max(P.HL, 1);
   P.halo.assign((size_t)P.n_batches * P.HL, i2{0, 0});
@@ -158,65 +163,92 @@ inline WsHostPlan ws_build_plan(const int32_t * nb, int64_t n_owned, int B)
 
 WS_FN int64_t ws_min(int64_t a, int64_t b) { return a < b ? a : b; }
 
-// producer warp pw: index table + traces of the out-of-batch neighbours of batch bt -> the given halves of the buffers.
-// The rounds of R halo entries are dealt to the producer warps in turn; a warp stages exactly the entries it reduces, so a
-// warp-level barrier orders its accesses to hlS.
-// R = neighbour cells per round (R * n loads in flight per lane)
-template<int N, int R, class RT>
-WS_FN void ws_produce(RT & rt, const WsTables<N> & T, const WsArgs & A, int bt, int pw, int lane, double * TRV, double * TRG, int * nlS, i2 * hlS)
+WS_FN int ws_count_total(int c) { return (c & 1023) + ((c >> 10) & 1023) + ((c >> 20) & 1023); }
+
+// what a producer lane holds of the batch after next: its packed entry counts and two entries of its halo list
+struct WsPrefetch { i2 h[2]; int c; };
+
+WS_FN void ws_prefetch(const WsArgs & A, int bt, int lane, WsPrefetch & pre)
 {
-  constexpr int B = WsCfg<N>::B, NP = WsCfg<N>::NP, N2 = N * N, N3 = N2 * N;
-  const int cnt = A.cnt[bt];
-  for (int i = pw * 32 + lane; i < B * 6; i += 32 * NP) nlS[i] = A.nloc[(size_t)bt * (B * 6) + i];
-  for (int e0 = pw * R; e0 < cnt; e0 += NP * R)
-    if (lane < R && e0 + lane < cnt) hlS[e0 + lane] = A.halo[(size_t)bt * A.HL + e0 + lane];
-  rt.sync_producer(pw);
-  const bool act = lane < N2;
-  const int ab = act ? lane : 0; // line within the face; the spare lanes shadow line 0 and store nothing
-  for (int e0 = pw * R; e0 < cnt; e0 += NP * R) {
-    double x[R][N];
-    int hx[R];
+  pre.c = A.cnt[bt];
+  const int n = ws_count_total(pre.c);
+  const i2 zero = {0, 0};
+  pre.h[0] = lane < n ? A.halo[(size_t)bt * A.HL + lane] : zero;
+  pre.h[1] = lane + 32 < n ? A.halo[(size_t)bt * A.HL + lane + 32] : zero;
+}
+
+// one round: the lines (direction D) of the neighbour cells of entries e0 .. e0 + R - 1 -> registers -> traces.  All loads
+// are issued before the first use; both end derivatives are computed and the one facing us is selected (no branches).
+template<int N, int R, int D, bool GH>
+WS_FN void ws_round(const WsTables<N> & T, const WsArgs & A, const i2 * hl, int e0, const double * own, const double * gho, int ab, bool act, double * TRV, double * TRG)
+{
+  constexpr int N2 = N * N, N3 = N2 * N;
+  constexpr int sd = (D == 0) ? 1 : (D == 1 ? N : N2); // stride along the line
+  double x[R][N];
+  int side[R];
+  WS_UNROLL
+  for (int q = 0; q < R; ++q) {
+    const i2 h = hl[e0 + q];
+    side[q] = h.x & 1;
+    const double * line = ((!GH || h.y < A.n_owned) ? own : gho) + (size_t)h.y * N3;
     WS_UNROLL
-    for (int q = 0; q < R; ++q) {
-      const int e = e0 + q;
-      if (e < cnt) { // warp-uniform
-        const i2 h = hlS[e];
-        hx[q] = h.x;
-        const int D = (h.x & 7) >> 1;
-        const int sd = (D == 0) ? 1 : (D == 1 ? N : N2);
-        const int s1 = (D == 0) ? N : 1, s2 = (D == 2) ? N : N2;
-        const double * line = ((h.y < A.n_owned) ? A.src + (size_t)h.y * N3 : A.ghost + (size_t)(h.y - A.n_owned) * N3) + (ab % N) * s1 + (ab / N) * s2;
-        WS_UNROLL
-        for (int i = 0; i < N; ++i) x[q][i] = line[i * sd];
-      } else {
-        hx[q] = 0;
-        WS_UNROLL
-        for (int i = 0; i < N; ++i) x[q][i] = 0.0;
-      }
-    }
+    for (int i = 0; i < N; ++i) x[q][i] = line[i * sd];
+  }
+  WS_UNROLL
+  for (int q = 0; q < R; ++q) {
+    double g0 = T.fd[0][0] * x[q][0], g1 = T.fd[1][0] * x[q][0];
     WS_UNROLL
-    for (int q = 0; q < R; ++q) {
-      const int e = e0 + q;
-      if (e < cnt) {
-        double g, v;
-        if (!(hx[q] & 1)) { // our lower face: the neighbour is entered through its upper end (warp-uniform)
-          g = T.fd[1][0] * x[q][0];
-          WS_UNROLL
-          for (int i = 1; i < N; ++i) g = fma(T.fd[1][i], x[q][i], g);
-          v = x[q][N - 1];
-        } else {
-          g = T.fd[0][0] * x[q][0];
-          WS_UNROLL
-          for (int i = 1; i < N; ++i) g = fma(T.fd[0][i], x[q][i], g);
-          v = x[q][0];
-        }
-        if (act) { TRV[e * N2 + ab] = v; TRG[e * N2 + ab] = g; }
-      }
-    }
+    for (int i = 1; i < N; ++i) { g0 = fma(T.fd[0][i], x[q][i], g0); g1 = fma(T.fd[1][i], x[q][i], g1); }
+    // our lower face (side 0): the neighbour is entered through its upper end
+    const double v = side[q] ? x[q][0] : x[q][N - 1];
+    const double g = side[q] ? g0 : g1;
+    if (act) { TRV[(e0 + q) * N2 + ab] = v; TRG[(e0 + q) * N2 + ab] = g; }
   }
 }
 
-template<int N, int R, class RT>
+// entries [e_begin, e_end) of direction D: full rounds of R neighbour cells, then single cells, dealt to the producer warps in turn
+template<int N, int R, int D, bool GH>
+WS_FN void ws_produce_dir(const WsTables<N> & T, const WsArgs & A, const i2 * hl, int e_begin, int e_end, int & round, int pw, int ab, bool act, double * TRV, double * TRG)
+{
+  constexpr int NP = WsCfg<N>::NP, N2 = N * N, N3 = N2 * N;
+  constexpr int s1 = (D == 0) ? N : 1, s2 = (D == 2) ? N : N2; // strides across the face
+  const double * const own = A.src + (ab % N) * s1 + (ab / N) * s2;
+  const double * const gho = GH ? A.ghost - A.n_owned * N3 + (ab % N) * s1 + (ab / N) * s2 : own; // ghost cells are numbered from n_owned
+  int e0 = e_begin;
+  for (; e0 + R <= e_end; e0 += R, ++round)
+    if (round % NP == pw) ws_round<N, R, D, GH>(T, A, hl, e0, own, gho, ab, act, TRV, TRG); // warp-uniform
+  for (; e0 < e_end; ++e0, ++round)
+    if (round % NP == pw) ws_round<N, 1, D, GH>(T, A, hl, e0, own, gho, ab, act, TRV, TRG);
+}
+
+// producer warp pw: index table + traces of the out-of-batch neighbours of batch bt -> the given halves of the buffers.
+// pre holds the halo list of bt (fetched during the previous call) and leaves with that of bt_next (if >= 0); hl is the
+// warp's private staging area, so a warp-level barrier orders its accesses.
+template<int N, int R, bool GH, class RT>
+WS_FN void ws_produce(RT & rt, const WsTables<N> & T, const WsArgs & A, int bt, int bt_next, int pw, int lane, WsPrefetch & pre, double * TRV, double * TRG, int * nlS, i2 * hl)
+{
+  constexpr int B = WsCfg<N>::B, NP = WsCfg<N>::NP, N2 = N * N;
+  constexpr int NL = (B * 6 + 32 * NP - 1) / (32 * NP);
+  const int cx = pre.c & 1023, cy = (pre.c >> 10) & 1023, cz = (pre.c >> 20) & 1023;
+  hl[lane] = pre.h[0]; hl[lane + 32] = pre.h[1];
+  // index table of this batch: loads now, stores after the traces (their latency hides behind the rounds)
+  int nl[NL];
+  WS_UNROLL
+  for (int j = 0; j < NL; ++j) { const int i = pw * 32 + lane + 32 * NP * j; nl[j] = i < B * 6 ? A.nloc[(size_t)bt * (B * 6) + i] : 0; }
+  if (bt_next >= 0) ws_prefetch(A, bt_next, lane, pre);
+  rt.sync_producer(pw);
+  const bool act = lane < N2;
+  const int ab = act ? lane : 0; // line within the face; the spare lanes shadow line 0 and store nothing
+  int round = 0;
+  ws_produce_dir<N, (R > 8 ? 8 : R), 0, GH>(T, A, hl, 0, cx, round, pw, ab, act, TRV, TRG); // 16 x entries, 24 y and 24 z entries on aligned batches
+  ws_produce_dir<N, R, 1, GH>(T, A, hl, cx, cx + cy, round, pw, ab, act, TRV, TRG);
+  ws_produce_dir<N, R, 2, GH>(T, A, hl, cx + cy, cx + cy + cz, round, pw, ab, act, TRV, TRG);
+  WS_UNROLL
+  for (int j = 0; j < NL; ++j) { const int i = pw * 32 + lane + 32 * NP * j; if (i < B * 6) nlS[i] = nl[j]; }
+  // hl is overwritten by the next call only behind the CTA-wide hand-over barrier
+}
+
+template<int N, int R, bool GH, class RT>
 WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
 {
   constexpr int B = WsCfg<N>::B, NC = WsCfg<N>::NC;
@@ -232,8 +264,8 @@ WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
   double * const Tt = smem + OFF_T;
   double * const GN = smem + OFF_GN;
   int * const nl2 = reinterpret_cast<int *>(smem + OFF_TR + 4 * trs); // [2][B * 6]
-  i2 * const hlS = reinterpret_cast<i2 *>(nl2 + 2 * B * 6);           // [HL] producer-private copy of the halo list
-  void * const bar = hlS + A.HL;
+  i2 * const hlS = reinterpret_cast<i2 *>(nl2 + 2 * B * 6);           // [NP][HLMAX] per-warp staging of the halo list
+  void * const bar = hlS + WsCfg<N>::NP * WsCfg<N>::HLMAX;
 
   const int t = rt.tid();
   const bool producer = t >= NC;
@@ -245,10 +277,17 @@ WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
   const int lz = t % B, sz = t / B;   // z-line layout: consecutive lanes = consecutive cells (stride n^3, odd -> conflict-free)
 
   // ---- prologue: traces + index table of the first batch, its bulk copy ----
+  const int pw = producer ? (t - NC) / 32 : 0, lane = t % 32;
+  WsPrefetch pre;
+  pre.c = 0; pre.h[0] = i2{0, 0}; pre.h[1] = i2{0, 0};
   {
     const int bt = A.batches ? A.batches[first] : first;
-    if (producer) ws_produce<N, R>(rt, T, A, bt, (t - NC) / 32, (t - NC) % 32, smem + OFF_TR, smem + OFF_TR + trs, nl2, hlS);
-    else if (t == 0) {
+    if (producer) {
+      const int it1 = first + step;
+      ws_prefetch(A, bt, lane, pre);
+      ws_produce<N, R, GH>(rt, T, A, bt, it1 < A.n_items ? (A.batches ? A.batches[it1] : it1) : -1, pw, lane, pre, smem + OFF_TR, smem + OFF_TR + trs, nl2,
+                           hlS + pw * WsCfg<N>::HLMAX);
+    } else if (t == 0) {
       const int64_t c0 = (int64_t)bt * B;
       const uint32_t by = (uint32_t)((int)ws_min(B, A.n_owned - c0) * N3 * sizeof(double));
       if (by % 16 == 0) rt.load_issue(bar, U, A.src + c0 * N3, by);
@@ -260,10 +299,11 @@ WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
   if (producer) {
     int buf = 0;
     for (int it = first; it < A.n_items; it += step, buf ^= 1) {
-      const int itn = it + step;
+      const int itn = it + step, itnn = itn + step;
       if (itn < A.n_items) {
         const int bn = A.batches ? A.batches[itn] : itn;
-        ws_produce<N, R>(rt, T, A, bn, (t - NC) / 32, (t - NC) % 32, smem + OFF_TR + (buf ^ 1) * 2 * trs, smem + OFF_TR + (buf ^ 1) * 2 * trs + trs, nl2 + (buf ^ 1) * B * 6, hlS);
+        ws_produce<N, R, GH>(rt, T, A, bn, itnn < A.n_items ? (A.batches ? A.batches[itnn] : itnn) : -1, pw, lane, pre, smem + OFF_TR + (buf ^ 1) * 2 * trs,
+                             smem + OFF_TR + (buf ^ 1) * 2 * trs + trs, nl2 + (buf ^ 1) * B * 6, hlS + pw * WsCfg<N>::HLMAX);
       }
       rt.sync_all(); // hand-over: traces / index table of the next batch are complete, those of this batch are free
     }

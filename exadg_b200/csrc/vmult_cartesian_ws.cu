@@ -56,12 +56,13 @@ struct DeviceRT
   __device__ __forceinline__ void store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 };
 
-template<int N, int R>
+// R: neighbour cells per producer round; GH: the partition has ghost cells (src of the neighbours may live in the ghost buffer)
+template<int N, int R, bool GH>
 __global__ void __launch_bounds__(WsCfg<N>::NT, 2) vmult_cartesian_ws_kernel(const __grid_constant__ WsTables<N> T, const WsArgs A)
 {
   extern __shared__ __align__(128) double ws_shared[];
   DeviceRT rt{ws_shared, 0u};
-  ws_cta<N, R>(rt, T, A);
+  ws_cta<N, R, GH>(rt, T, A);
 }
 
 constexpr size_t WS_MAX_SMEM = 228 * 1024 / 2 - 1024; // half of an SM's shared memory minus the per-CTA reservation
@@ -83,7 +84,7 @@ void * ws_plan_create(const DeviceOperator & op, const HostMesh & mesh)
   if (!ws_supported(op.n)) return nullptr;
   const WsHostPlan H = ws_build_plan(mesh.nb.data(), mesh.n_owned, WsCfg<5>::B);
   const size_t smem = ws_smem_bytes<5>(H.HL);
-  if (smem > WS_MAX_SMEM) return nullptr; // two CTAs per SM are what the kernel is built for
+  if (smem > WS_MAX_SMEM || H.HL > WsCfg<5>::HLMAX) return nullptr; // two CTAs per SM are what the kernel is built for
   WsDevPlan * P = new WsDevPlan;
   P->HL = H.HL; P->n_batches = H.n_batches; P->smem = smem;
   P->T = make_ws_tables<5>(op.h, op.tau_hat);
@@ -93,12 +94,15 @@ void * ws_plan_create(const DeviceOperator & op, const HostMesh & mesh)
   CUDA_CHECK(cudaMemcpy(P->d_cnt, H.cnt.data(), H.cnt.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   CUDA_CHECK(cudaMalloc(&P->d_nloc, H.nloc.size() * sizeof(int32_t)));
   CUDA_CHECK(cudaMemcpy(P->d_nloc, H.nloc.data(), H.nloc.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-  CUDA_CHECK(cudaFuncSetAttribute(vmult_cartesian_ws_kernel<5, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_MAX_SMEM)); // same for every operator
-  CUDA_CHECK(cudaFuncSetAttribute(vmult_cartesian_ws_kernel<5, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_MAX_SMEM));
-  int occ12 = 0;
-  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&P->ctas_per_sm, vmult_cartesian_ws_kernel<5, 8>, WsCfg<5>::NT, smem));
-  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ12, vmult_cartesian_ws_kernel<5, 12>, WsCfg<5>::NT, smem));
-  P->ctas_per_sm = std::min(P->ctas_per_sm, occ12);
+  P->ctas_per_sm = 2;
+  auto configure = [&](auto kernel) {
+    int occ = 0;
+    CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_MAX_SMEM)); // same for every operator
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, WsCfg<5>::NT, smem));
+    P->ctas_per_sm = std::min(P->ctas_per_sm, occ);
+  };
+  configure(vmult_cartesian_ws_kernel<5, 8, false>); configure(vmult_cartesian_ws_kernel<5, 12, false>);
+  configure(vmult_cartesian_ws_kernel<5, 8, true>); configure(vmult_cartesian_ws_kernel<5, 12, true>);
   if (P->ctas_per_sm < 1) { ws_plan_destroy(P); return nullptr; }
   return P;
 }
@@ -121,8 +125,14 @@ void ws_launch(const DeviceOperator & op, const void * p, double * dst, const do
   A.halo = P->d_halo; A.cnt = P->d_cnt; A.nloc = P->d_nloc; A.batches = batches;
   A.src = src; A.ghost = op.ghost; A.dst = dst; A.n_owned = op.n_owned; A.n_items = n_items; A.HL = P->HL; A.add = add ? 1 : 0;
   const int grid = std::min(n_items, n_sm * P->ctas_per_sm);
-  if (depth == 12) vmult_cartesian_ws_kernel<5, 12><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A);
-  else vmult_cartesian_ws_kernel<5, 8><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A);
+  const bool gh = op.n_ghost > 0;
+  if (depth == 12) {
+    if (gh) vmult_cartesian_ws_kernel<5, 12, true><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A);
+    else vmult_cartesian_ws_kernel<5, 12, false><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A);
+  } else {
+    if (gh) vmult_cartesian_ws_kernel<5, 8, true><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A);
+    else vmult_cartesian_ws_kernel<5, 8, false><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A);
+  }
   CUDA_CHECK(cudaGetLastError());
 }
 

@@ -1,6 +1,6 @@
 // Kernel tournament for the affine fast path at k = 4 (C ABI only, no Python): times the pipelined kernel (variant 0) and
 // the warp-specialised kernel (variants 1, 2) on the same operator and vectors, and checks that both give the same vmult /
-// vmult_add.  Usage: ws_tournament [n_sub refine [steps [only_variant]]]   (defaults 3 5 = 96^3 cells, 100 steps)
+// vmult_add.  Usage: ws_tournament only_variant|-1 (n_sub refine steps)...   (default: -1 3 5 100 = 96^3 cells, 100 steps)
 //   nvcc -O2 -std=c++17 scripts/ws_tournament.cpp -Iinclude -Lexadg_b200 -lexadg_b200 -Xlinker -rpath='$ORIGIN/../exadg_b200' -o build/ws_tournament
 #include <cuda_runtime.h>
 
@@ -18,16 +18,13 @@
 
 static double rel_diff(const std::vector<double> & a, const std::vector<double> & b)
 {
-  long double d = 0, n = 0;
-  for (size_t i = 0; i < a.size(); ++i) { d += (long double)(a[i] - b[i]) * (a[i] - b[i]); n += (long double)b[i] * b[i]; }
-  return (double)std::sqrt((double)(d / n));
+  double d = 0, n = 0;
+  for (size_t i = 0; i < a.size(); ++i) { d += (a[i] - b[i]) * (a[i] - b[i]); n += b[i] * b[i]; }
+  return std::sqrt(d / n);
 }
 
-int main(int argc, char ** argv)
+static int run_mesh(int n_sub, int refine, int steps, int only)
 {
-  const int n_sub = argc > 1 ? std::atoi(argv[1]) : 3, refine = argc > 2 ? std::atoi(argv[2]) : 5;
-  const int steps = argc > 3 ? std::atoi(argv[3]) : 100;
-  const int only = argc > 4 ? std::atoi(argv[4]) : -1;
   exadg_b200_hypercube_desc d{};
   d.degree = 4; d.n_subdivisions = n_sub; d.n_refinements = refine; d.mapping_degree = 1; d.deformation = 0.0; d.frequency = 2;
   d.ip_factor = 1.0; d.rank = 0; d.world = 1; d.force_general = 0;
@@ -50,8 +47,6 @@ int main(int argc, char ** argv)
   }
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-  const bool check = (n <= 120000000) && only < 0;
-  std::vector<double> y[NV], ya[NV];
   for (int v = 0; v < NV; ++v) {
     if (only >= 0 && v != only) continue;
     exadg_b200_cartesian_kernel(v);
@@ -69,27 +64,38 @@ int main(int argc, char ** argv)
     }
     std::printf("variant %d: %.4f ms/vmult best of %d (mean %.4f)  %.2f GDoF/s\n", v, best, reps, total / reps, n / best * 1e-6);
     std::fflush(stdout);
-    if (check) {
-      y[v].resize(n); ya[v].resize(n);
-      CU(cudaMemcpy(y[v].data(), dst[v], n * sizeof(double), cudaMemcpyDeviceToHost));
-      CK(exadg_b200_vmult_add(op, dst[v], src)); // dst = 2 A src
-      CU(cudaStreamSynchronize(stream));
-      CU(cudaMemcpy(ya[v].data(), dst[v], n * sizeof(double), cudaMemcpyDeviceToHost));
-    }
   }
-  if (check) {
-    std::vector<double> two(y[0]);
-    for (auto & x : two) x *= 2.0;
+  if (only < 0) { // parity: vmult of every variant against variant 0, vmult_add against 2 * vmult
+    std::vector<double> y0(n), y(n);
+    CU(cudaMemcpy(y0.data(), dst[0], n * sizeof(double), cudaMemcpyDeviceToHost));
     for (int v = 1; v < NV; ++v) {
-      std::printf("vmult     rel l2 (variant %d vs 0): %.3e\n", v, rel_diff(y[v], y[0]));
-      std::printf("vmult_add rel l2 (variant %d vs 0): %.3e\n", v, rel_diff(ya[v], ya[0]));
-      std::printf("vmult_add rel l2 (variant %d vs 2*vmult): %.3e\n", v, rel_diff(ya[v], two));
+      CU(cudaMemcpy(y.data(), dst[v], n * sizeof(double), cudaMemcpyDeviceToHost));
+      std::printf("vmult     rel l2 (variant %d vs 0): %.3e\n", v, rel_diff(y, y0));
+      exadg_b200_cartesian_kernel(v);
+      CK(exadg_b200_vmult_add(op, dst[v], src)); // dst = 2 A src through the bulk add-reduction
+      CU(cudaStreamSynchronize(stream));
+      CU(cudaMemcpy(y.data(), dst[v], n * sizeof(double), cudaMemcpyDeviceToHost));
+      for (auto & x : y) x *= 0.5;
+      std::printf("vmult_add rel l2 (variant %d, half of it vs 0): %.3e\n", v, rel_diff(y, y0));
+      std::fflush(stdout);
     }
   }
   exadg_b200_cartesian_kernel(0);
   exadg_b200_free_dof_vector(src);
   for (int v = 0; v < NV; ++v) exadg_b200_free_dof_vector(dst[v]);
   exadg_b200_destroy(op);
+  return 0;
+}
+
+// ws_tournament only_variant (n_sub refine steps)...      e.g.  ws_tournament -1 3 5 100 1 2 5 5 0 5
+int main(int argc, char ** argv)
+{
+  const int only = argc > 1 ? std::atoi(argv[1]) : -1;
+  if (argc < 5) { const int rc = run_mesh(3, 5, 100, only); std::printf("TOURNAMENT DONE\n"); return rc; }
+  for (int a = 2; a + 2 < argc; a += 3) {
+    const int rc = run_mesh(std::atoi(argv[a]), std::atoi(argv[a + 1]), std::atoi(argv[a + 2]), only);
+    if (rc != 0) return rc;
+  }
   std::printf("TOURNAMENT DONE\n");
   return 0;
 }

@@ -106,7 +106,7 @@ void * wse_create(int n_sub, int refine, int rank, int world, double ip_factor)
   E->T = make_ws_tables<N>(E->mesh.h, tk * ip_factor * N * N);
   for (int b = 0; b < E->plan.n_batches; ++b) {
     bool ghost = false;
-    for (int e = 0; e < E->plan.cnt[b]; ++e) ghost |= (E->plan.halo[(size_t)b * E->plan.HL + e].y >= E->mesh.n_owned);
+    for (int e = 0; e < ws_count_total(E->plan.cnt[b]); ++e) ghost |= (E->plan.halo[(size_t)b * E->plan.HL + e].y >= E->mesh.n_owned);
     (ghost ? E->boundary : E->interior).push_back(b);
   }
   return E;
@@ -131,6 +131,7 @@ int wse_vmult(void * h, const double * src, const double * ghost, double * dst, 
   A.n_items = wse_n_batches(h, which);
   A.src = src; A.ghost = ghost; A.dst = dst; A.n_owned = E->mesh.n_owned; A.HL = E->plan.HL; A.add = add;
   if (A.n_items == 0) return 0;
+  if (E->plan.HL > WsCfg<N>::HLMAX) return -1; // the library falls back to the pipelined kernel
   n_ctas = std::min(n_ctas, A.n_items);
   int errors = 0;
   for (int cta = 0; cta < n_ctas; ++cta) {
@@ -142,7 +143,10 @@ int wse_vmult(void * h, const double * src, const double * ghost, double * dst, 
     for (int p = 0; p < WsCfg<N>::NP; ++p) pthread_barrier_init(&C.bp[p], nullptr, 32);
     std::vector<std::thread> threads;
     for (int t = 0; t < WsCfg<N>::NT; ++t)
-      threads.emplace_back([&, t]() { HostRT rt{&C, t}; ws_cta<N, WSE_R>(rt, E->T, A); });
+      threads.emplace_back([&, t]() {
+        HostRT rt{&C, t};
+        if (E->mesh.n_ghost > 0) ws_cta<N, WSE_R, true>(rt, E->T, A); else ws_cta<N, WSE_R, false>(rt, E->T, A);
+      });
     for (auto & th : threads) th.join();
     pthread_barrier_destroy(&C.ba); pthread_barrier_destroy(&C.bc); for (int p = 0; p < WsCfg<N>::NP; ++p) pthread_barrier_destroy(&C.bp[p]);
     errors += C.errors.load() + (C.st_pending ? 1 : 0);

@@ -60,8 +60,11 @@ def _run(lib, n_sub, refine, rank, world, x_global, n_ctas, add=False, split=Fal
             err += lib.wse_vmult(h, _ptr(src), _ptr(ghost), _ptr(dst), int(add), n_ctas, 2)
         else:
             err = lib.wse_vmult(h, _ptr(src), _ptr(ghost), _ptr(dst), int(add), n_ctas, 0)
+        if lib.wse_halo_max(h) > 64:  # too irregular for the producers' staging area: the library keeps the pipelined kernel
+            assert err < 0
+            return None, off * N3, (off + n_owned) * N3
         assert err == 0, "bulk-copy protocol violated"
-        assert lib.wse_smem_bytes(h) <= 113 * 1024 or lib.wse_halo_max(h) > 64
+        assert lib.wse_smem_bytes(h) <= 113 * 1024
         return dst, off * N3, (off + n_owned) * N3
     finally:
         lib.wse_destroy(h)
@@ -88,16 +91,21 @@ def test_emulated_kernel_add(emu):
     assert np.linalg.norm(y - ref) / np.linalg.norm(ref) < 1e-13
 
 
-@pytest.mark.parametrize("n_sub,refine,world", [(3, 1, 2), (1, 2, 3), (5, 0, 2)])
-def test_emulated_kernel_partitions(emu, n_sub, refine, world):
-    """ragged partitions (odd cell counts: no bulk copy for the last batch), ghost cells, interior/boundary launches"""
+@pytest.mark.parametrize("n_sub,refine,world,expect_supported", [(1, 3, 2, 2), (1, 3, 4, 4), (3, 2, 2, 2), (5, 0, 2, 1), (3, 1, 2, 1), (1, 3, 3, 1)])
+def test_emulated_kernel_partitions(emu, n_sub, refine, world, expect_supported):
+    """partitions with ghost cells, interior/boundary launches, ragged last batches; partitions that cut through the octets of the
+    Morton curve have more than 64 out-of-batch faces per batch and are left to the pipelined kernel"""
     n = (n_sub << refine) ** 3 * N3
     x = np.random.default_rng(9).uniform(-1, 1, n)
     ref = _oracle(n_sub, refine, x)
+    supported = 0
     for rank in range(world):
         for split in (False, True):
             y, lo, hi = _run(emu, n_sub, refine, rank, world, x, 2, split=split)
-            assert np.linalg.norm(y - ref[lo:hi]) / np.linalg.norm(ref) < 1e-13
+            if y is not None:
+                supported += 1
+                assert np.linalg.norm(y - ref[lo:hi]) / np.linalg.norm(ref) < 1e-13
+    assert supported == 2 * expect_supported
 
 
 def test_emulated_kernel_thread_sanitizer(tmp_path):
