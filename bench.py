@@ -301,13 +301,23 @@ def run_gpu(args):
         # so its average launch duration is ms / steps, measured with CUDA events on the launching stream
         achieved = b_alg * (n_global / world) * args.steps / (ms * 1e-3) / 1e9
         key = "k%d_%s" % (degree, args.mesh)
+        kernel = "general (stored metrics)"
+        if op.is_cartesian_path:
+            kernel = "cartesian"
+            if degree == 4:
+                variant = exadg_b200.cartesian_kernel()
+                kernel = ("warp-specialised vmult_cartesian_ws_kernel<5,%d>" % (12 if variant == 2 else 8)) if variant >= 1 else "pipelined vmult_cartesian_pipe_kernel<5>"
+                if variant >= 1:
+                    key += "_ws"
+                    if world > 1:
+                        kernel += " for the interior batches, pipelined kernel for the batches with ghost neighbours"
         out = {"metric": METRIC if degree == 4 else METRIC.replace("k=4", "k=%d" % degree), "value": value, "unit": "DoFs/s", "n_gpus": world,
                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": "SIPG Laplace vmult, FE_DGQ(%d), Gauss(%d), periodic %s box, %d^3 cells, %d DoFs, src uniform(-1,1)"
                                       % (degree, degree + 1, "Cartesian" if deformation == 0.0 else "sine-deformed (trilinear)", n_sub << refine, n_global),
                           "l2_policy": "inputs larger than L2 (%.0f MB per vector per GPU)" % (n_local * 8 / 1e6),
-                          "kernel_path": "cartesian" if op.is_cartesian_path else "general", "partition": "p4est-style contiguous Morton ranges, %d rank(s)" % world,
+                          "kernel_path": "cartesian" if op.is_cartesian_path else "general", "kernel": kernel, "partition": "p4est-style contiguous Morton ranges, %d rank(s)" % world,
                           "halo": "none" if world == 1 else ("NVLink peer-memory stores (CUDA IPC), overlapped with interior cells" if args.halo == "p2p" else "NCCL send/recv, overlapped with interior cells")},
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(key),
                             "peak_source": peak_src, "algorithmic_bytes_per_dof": b_alg, "dofs_per_launch": n_global // world},

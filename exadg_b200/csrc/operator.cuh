@@ -46,7 +46,7 @@ void launch_diagonal_general(const DeviceOperator & op, double * diag, bool add,
 
 // ---- vmult_cartesian.cu ----
 bool cartesian_supported(int n);
-// selects the n = 5 kernel of the fast path (0 pipelined, 1 / 2 warp-specialised with producer depth 8 / 12; -1 only queries); returns the previous value
+// selects the n = 5 kernel of the fast path (0 pipelined, 1 (default) / 2 warp-specialised with producer depth 8 / 12; -1 only queries); returns the previous value
 int cartesian_kernel_variant(int set);
 size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh);
 void cartesian_plan_destroy(DeviceOperator & op);
@@ -57,7 +57,8 @@ void launch_vmult_cartesian_part(const DeviceOperator & op, double * dst, const 
 bool ws_supported(int n);
 void * ws_plan_create(const DeviceOperator & op, const HostMesh & mesh);
 void ws_plan_destroy(void * plan);
-void ws_launch(const DeviceOperator & op, const void * plan, double * dst, const double * src, bool add, const int32_t * batches, int n_items, int n_sm, int depth, cudaStream_t stream);
+void ws_launch(const DeviceOperator & op, const void * plan, double * dst, const double * src, bool add, const int32_t * batches, int n_items, int n_sm, int depth, bool gh,
+               cudaStream_t stream);
 
 // ---- microbench.cu ----
 void fp64_peak(double * dfma_tflops, double * dmma_tflops);

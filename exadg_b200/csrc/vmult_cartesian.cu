@@ -773,8 +773,8 @@ struct CartPlan
   void * ws = nullptr;
 };
 
-// kernel of the fast path for n = 5: 0 pipelined 4-warp kernel, 1 / 2 warp-specialised kernel with producer depth 8 / 12
-// (EXADG_B200_CART_KERNEL=ws / ws12)
+// kernel of the fast path for n = 5: 0 pipelined 4-warp kernel, 1 (default) / 2 warp-specialised kernel with producer depth 8 / 12
+// (EXADG_B200_CART_KERNEL=pipe / ws / ws12)
 int g_cart_kernel = -1;
 
 template<int N>
@@ -856,7 +856,7 @@ bool cartesian_supported(int n) { return n >= 2 && n <= 8; }
 
 int cartesian_kernel_variant(int set)
 {
-  if (g_cart_kernel < 0) { const char * e = getenv("EXADG_B200_CART_KERNEL"); g_cart_kernel = (e && std::strcmp(e, "ws") == 0) ? 1 : ((e && std::strcmp(e, "ws12") == 0) ? 2 : 0); }
+  if (g_cart_kernel < 0) { const char * e = getenv("EXADG_B200_CART_KERNEL"); g_cart_kernel = (e && std::strcmp(e, "pipe") == 0) ? 0 : ((e && std::strcmp(e, "ws12") == 0) ? 2 : 1); }
   const int previous = g_cart_kernel;
   if (set >= 0) g_cart_kernel = set;
   return previous;
@@ -972,12 +972,19 @@ void launch_vmult_cartesian_part(const DeviceOperator & op, double * dst, const 
     case 2: launch_n<2>(op, *plan, dst, src, add, which, stream); break;
     case 3: if (plan->pipe) launch_pipe<3>(op, *plan, dst, src, add, which, stream); else launch_n<3>(op, *plan, dst, src, add, which, stream); break;
     case 4: launch_n<4>(op, *plan, dst, src, add, which, stream); break;
-    case 5:
-      if (plan->ws && which == 0 && cartesian_kernel_variant(-1) >= 1) // interior/boundary launches of the multi-GPU path: pipelined kernel until verified on >= 2 GPUs
-        ws_launch(op, plan->ws, dst, src, add, nullptr, plan->n_batches, plan->n_sm, cartesian_kernel_variant(-1) == 2 ? 12 : 8, stream);
+    case 5: {
+      // warp-specialised kernel for full launches of an unpartitioned mesh and for the interior launch of a partition (no ghost
+      // reads by construction: the very kernel instantiation that is verified on one GPU); the batches that touch ghost cells
+      // stay on the pipelined kernel until the ghost path of the warp-specialised kernel has run on >= 2 GPUs
+      const int variant = cartesian_kernel_variant(-1);
+      const bool ws_ok = plan->ws && variant >= 1 && (which == 1 || (which == 0 && op.n_ghost == 0));
+      if (ws_ok)
+        ws_launch(op, plan->ws, dst, src, add, which == 1 ? plan->d_interior : nullptr, which == 1 ? plan->n_interior : plan->n_batches, plan->n_sm,
+                  variant == 2 ? 12 : 8, false, stream);
       else if (plan->pipe) launch_pipe<5>(op, *plan, dst, src, add, which, stream);
       else launch_n<5>(op, *plan, dst, src, add, which, stream);
       break;
+    }
     case 6: launch_n<6>(op, *plan, dst, src, add, which, stream); break;
     case 7: launch_n<7>(op, *plan, dst, src, add, which, stream); break;
     case 8: launch_n<8>(op, *plan, dst, src, add, which, stream); break;

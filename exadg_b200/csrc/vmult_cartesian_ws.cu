@@ -116,8 +116,9 @@ void ws_plan_destroy(void * p)
 }
 
 // batches: optional list of batch ids (interior / boundary launches of the multi-GPU path), n_items its length (or all batches)
-// depth: neighbour cells per producer round (8 or 12)
-void ws_launch(const DeviceOperator & op, const void * p, double * dst, const double * src, bool add, const int32_t * batches, int n_items, int n_sm, int depth, cudaStream_t stream)
+// depth: neighbour cells per producer round (8 or 12); gh: the selected batches may have neighbours in the ghost buffer
+void ws_launch(const DeviceOperator & op, const void * p, double * dst, const double * src, bool add, const int32_t * batches, int n_items, int n_sm, int depth, bool gh,
+               cudaStream_t stream)
 {
   const WsDevPlan * P = static_cast<const WsDevPlan *>(p);
   if (n_items == 0) return;
@@ -125,7 +126,6 @@ void ws_launch(const DeviceOperator & op, const void * p, double * dst, const do
   A.halo = P->d_halo; A.cnt = P->d_cnt; A.nloc = P->d_nloc; A.batches = batches;
   A.src = src; A.ghost = op.ghost; A.dst = dst; A.n_owned = op.n_owned; A.n_items = n_items; A.HL = P->HL; A.add = add ? 1 : 0;
   const int grid = std::min(n_items, n_sm * P->ctas_per_sm);
-  const bool gh = op.n_ghost > 0;
   if (depth == 12) {
     if (gh) vmult_cartesian_ws_kernel<5, 12, true><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A);
     else vmult_cartesian_ws_kernel<5, 12, false><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A);

@@ -342,7 +342,8 @@ def fp64_peak():
 
 
 def cartesian_kernel(variant=-1):
-    """Kernel of the affine fast path for degree 4: 0 pipelined 4-warp kernel, 1 warp-specialised kernel; -1 only queries.
+    """Kernel of the affine fast path for degree 4: 0 pipelined 4-warp kernel, 1 (default) / 2 warp-specialised kernel with
+    producer depth 8 / 12; -1 only queries.
     Process-wide tuning switch (no reference counterpart); returns the previous value."""
     return _lib().exadg_b200_cartesian_kernel(int(variant))
 
