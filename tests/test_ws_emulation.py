@@ -83,6 +83,19 @@ def test_emulated_kernel_matches_oracle(emu, n_sub, refine, n_ctas):
     assert np.linalg.norm(y - ref) / np.linalg.norm(ref) < 1e-13
 
 
+@pytest.mark.parametrize("n_sub,refine,world", [(3, 2, 1), (1, 4, 1), (3, 3, 1), (3, 3, 2), (1, 4, 8)])
+def test_plan_of_octet_aligned_meshes_fits_two_ctas_per_sm(emu, n_sub, refine, world):
+    """24-cell batches = 3 octets of the Morton curve: at most 64 out-of-batch faces, 111 KB of shared memory per CTA"""
+    for rank in range(world):
+        h = emu.wse_create(n_sub, refine, rank, world, 1.0)
+        try:
+            assert emu.wse_halo_max(h) == 64
+            assert emu.wse_smem_bytes(h) <= 228 * 1024 // 2 - 1024
+            assert emu.wse_n_batches(h, 1) + emu.wse_n_batches(h, 2) == emu.wse_n_batches(h, 0)
+        finally:
+            emu.wse_destroy(h)
+
+
 def test_emulated_kernel_add(emu):
     n = 4 ** 3 * N3
     x = np.random.default_rng(8).uniform(-1, 1, n)
