@@ -977,10 +977,12 @@ void launch_vmult_cartesian_part(const DeviceOperator & op, double * dst, const 
       // reads by construction: the very kernel instantiation that is verified on one GPU); the batches that touch ghost cells
       // stay on the pipelined kernel until the ghost path of the warp-specialised kernel has run on >= 2 GPUs
       const int variant = cartesian_kernel_variant(-1);
-      const bool ws_ok = plan->ws && variant >= 1 && (which == 1 || (which == 0 && op.n_ghost == 0));
+      static const bool ws_ghost = getenv("EXADG_B200_WS_GHOST") != nullptr; // verification switch: ghost path of the warp-specialised kernel (tests/multi_gpu_check.py)
+      const bool with_ghosts = which == 2 || (which == 0 && op.n_ghost > 0);
+      const bool ws_ok = plan->ws && variant >= 1 && (!with_ghosts || ws_ghost);
       if (ws_ok)
-        ws_launch(op, plan->ws, dst, src, add, which == 1 ? plan->d_interior : nullptr, which == 1 ? plan->n_interior : plan->n_batches, plan->n_sm,
-                  variant == 2 ? 12 : 8, false, stream);
+        ws_launch(op, plan->ws, dst, src, add, which == 0 ? nullptr : (which == 1 ? plan->d_interior : plan->d_boundary),
+                  which == 0 ? plan->n_batches : (which == 1 ? plan->n_interior : plan->n_boundary), plan->n_sm, variant == 2 ? 12 : 8, with_ghosts, stream);
       else if (plan->pipe) launch_pipe<5>(op, *plan, dst, src, add, which, stream);
       else launch_n<5>(op, *plan, dst, src, add, which, stream);
       break;

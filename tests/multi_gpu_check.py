@@ -3,6 +3,10 @@ single-partition run of the same library (which the -m gpu tests pin against the
 transports: NCCL send/recv and NVLink peer-memory stores (CUDA IPC).
 
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tests/multi_gpu_check.py
+
+Kernel selection for k = 4 on the affine path: by default the interior batches run on the warp-specialised kernel and the batches with
+ghost neighbours on the pipelined one; EXADG_B200_WS_GHOST=1 routes the latter through the warp-specialised kernel too (its ghost path,
+so far verified on the CPU emulation only), EXADG_B200_CART_KERNEL=pipe uses the pipelined kernel everywhere.
 """
 import os
 import sys
@@ -15,8 +19,9 @@ import exadg_b200  # noqa: E402
 from exadg_b200.laplace_operator import nccl_unique_id  # noqa: E402
 
 P6 = (0,) * 6
+# (4, 1, 3), (4, 1, 4), (4, 3, 3): octet-aligned partitions (the warp-specialised k=4 kernel applies on every rank);
 # (4, 5, 0), (5, 3, 0), (2, 5, 0): partitions that end inside a cell batch (ghost indices directly follow a ragged last batch)
-CASES = [(4, 5, 0, 0.0, P6), (5, 3, 0, 0.0, P6), (2, 5, 0, 0.0, P6), (4, 3, 2, 0.0, P6), (3, 1, 3, 0.1, P6),
+CASES = [(4, 1, 3, 0.0, P6), (4, 1, 4, 0.0, P6), (4, 3, 3, 0.0, P6), (4, 5, 0, 0.0, P6), (5, 3, 0, 0.0, P6), (2, 5, 0, 0.0, P6), (4, 3, 2, 0.0, P6), (3, 1, 3, 0.1, P6),
          (2, 2, 2, 0.15, (1, 2, 1, 1, 1, 1)), (5, 1, 2, 0.0, P6)]
 
 
