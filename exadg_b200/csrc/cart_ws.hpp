@@ -52,12 +52,12 @@ struct WsTables
   double fd[2][N];     // l_j'(s)
 };
 
-template<int N>
+template<int N, int NP_ = 2>
 struct WsCfg
 {
   static constexpr int B = 24;    // cells per batch: 3 octets of the Morton curve, 24 x 5 planes = 120 of 128 compute threads
   static constexpr int NC = 128;  // compute threads (named barrier 1)
-  static constexpr int NP = 2;    // producer warps (5 or 6 warps per CTA cost the same register allocation)
+  static constexpr int NP = NP_;  // producer warps: 2 by default (5 or 6 warps per CTA cost the same register allocation)
   static constexpr int NT = NC + 32 * NP;
   static constexpr int HLMAX = 64; // halo entries per batch the producers can stage (two per lane)
 };
@@ -73,12 +73,12 @@ struct WsArgs
 };
 
 // shared memory of one CTA in bytes (doubles first, then the int tables, then the mbarrier)
-template<int N>
+template<int N, int NP = 2>
 inline size_t ws_smem_bytes(int HL)
 {
   constexpr int B = WsCfg<N>::B, N2 = N * N, N3 = N2 * N;
   return ((size_t)2 * B * N3 + (size_t)2 * B * N2 + (size_t)4 * HL * N2) * sizeof(double) + (size_t)2 * B * 6 * sizeof(int)
-         + (size_t)WsCfg<N>::NP * WsCfg<N>::HLMAX * sizeof(i2) + 16;
+         + (size_t)NP * WsCfg<N>::HLMAX * sizeof(i2) + 16;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -207,10 +207,10 @@ WS_FN void ws_round(const WsTables<N> & T, const WsArgs & A, const i2 * hl, int 
 }
 
 // entries [e_begin, e_end) of direction D: full rounds of R neighbour cells, then single cells, dealt to the producer warps in turn
-template<int N, int R, int D, bool GH>
+template<int N, int R, int D, bool GH, int NP>
 WS_FN void ws_produce_dir(const WsTables<N> & T, const WsArgs & A, const i2 * hl, int e_begin, int e_end, int & round, int pw, int ab, bool act, double * TRV, double * TRG)
 {
-  constexpr int NP = WsCfg<N>::NP, N2 = N * N, N3 = N2 * N;
+  constexpr int N2 = N * N, N3 = N2 * N;
   constexpr int s1 = (D == 0) ? N : 1, s2 = (D == 2) ? N : N2; // strides across the face
   const double * const own = A.src + (ab % N) * s1 + (ab / N) * s2;
   const double * const gho = GH ? A.ghost - A.n_owned * N3 + (ab % N) * s1 + (ab / N) * s2 : own; // ghost cells are numbered from n_owned
@@ -224,10 +224,10 @@ WS_FN void ws_produce_dir(const WsTables<N> & T, const WsArgs & A, const i2 * hl
 // producer warp pw: index table + traces of the out-of-batch neighbours of batch bt -> the given halves of the buffers.
 // pre holds the halo list of bt (fetched during the previous call) and leaves with that of bt_next (if >= 0); hl is the
 // warp's private staging area, so a warp-level barrier orders its accesses.
-template<int N, int R, bool GH, class RT>
+template<int N, int R, bool GH, int NP, class RT>
 WS_FN void ws_produce(RT & rt, const WsTables<N> & T, const WsArgs & A, int bt, int bt_next, int pw, int lane, WsPrefetch & pre, double * TRV, double * TRG, int * nlS, i2 * hl)
 {
-  constexpr int B = WsCfg<N>::B, NP = WsCfg<N>::NP, N2 = N * N;
+  constexpr int B = WsCfg<N>::B, N2 = N * N;
   constexpr int NL = (B * 6 + 32 * NP - 1) / (32 * NP);
   const int cx = pre.c & 1023, cy = (pre.c >> 10) & 1023, cz = (pre.c >> 20) & 1023;
   hl[lane] = pre.h[0]; hl[lane + 32] = pre.h[1];
@@ -240,15 +240,15 @@ WS_FN void ws_produce(RT & rt, const WsTables<N> & T, const WsArgs & A, int bt, 
   const bool act = lane < N2;
   const int ab = act ? lane : 0; // line within the face; the spare lanes shadow line 0 and store nothing
   int round = 0;
-  ws_produce_dir<N, (R > 8 ? 8 : R), 0, GH>(T, A, hl, 0, cx, round, pw, ab, act, TRV, TRG); // 16 x entries, 24 y and 24 z entries on aligned batches
-  ws_produce_dir<N, R, 1, GH>(T, A, hl, cx, cx + cy, round, pw, ab, act, TRV, TRG);
-  ws_produce_dir<N, R, 2, GH>(T, A, hl, cx + cy, cx + cy + cz, round, pw, ab, act, TRV, TRG);
+  ws_produce_dir<N, (R > 8 ? 8 : R), 0, GH, NP>(T, A, hl, 0, cx, round, pw, ab, act, TRV, TRG); // 16 x entries, 24 y and 24 z entries on aligned batches
+  ws_produce_dir<N, R, 1, GH, NP>(T, A, hl, cx, cx + cy, round, pw, ab, act, TRV, TRG);
+  ws_produce_dir<N, R, 2, GH, NP>(T, A, hl, cx + cy, cx + cy + cz, round, pw, ab, act, TRV, TRG);
   WS_UNROLL
   for (int j = 0; j < NL; ++j) { const int i = pw * 32 + lane + 32 * NP * j; if (i < B * 6) nlS[i] = nl[j]; }
   // hl is overwritten by the next call only behind the CTA-wide hand-over barrier
 }
 
-template<int N, int R, bool GH, class RT>
+template<int N, int R, bool GH, int NP, class RT>
 WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
 {
   constexpr int B = WsCfg<N>::B, NC = WsCfg<N>::NC;
@@ -265,7 +265,7 @@ WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
   double * const GN = smem + OFF_GN;
   int * const nl2 = reinterpret_cast<int *>(smem + OFF_TR + 4 * trs); // [2][B * 6]
   i2 * const hlS = reinterpret_cast<i2 *>(nl2 + 2 * B * 6);           // [NP][HLMAX] per-warp staging of the halo list
-  void * const bar = hlS + WsCfg<N>::NP * WsCfg<N>::HLMAX;
+  void * const bar = hlS + NP * WsCfg<N>::HLMAX;
 
   const int t = rt.tid();
   const bool producer = t >= NC;
@@ -285,7 +285,7 @@ WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
     if (producer) {
       const int it1 = first + step;
       ws_prefetch(A, bt, lane, pre);
-      ws_produce<N, R, GH>(rt, T, A, bt, it1 < A.n_items ? (A.batches ? A.batches[it1] : it1) : -1, pw, lane, pre, smem + OFF_TR, smem + OFF_TR + trs, nl2,
+      ws_produce<N, R, GH, NP>(rt, T, A, bt, it1 < A.n_items ? (A.batches ? A.batches[it1] : it1) : -1, pw, lane, pre, smem + OFF_TR, smem + OFF_TR + trs, nl2,
                            hlS + pw * WsCfg<N>::HLMAX);
     } else if (t == 0) {
       const int64_t c0 = (int64_t)bt * B;
@@ -297,18 +297,20 @@ WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
 
   // The two roles run their own loops over the same batch sequence and meet at the CTA-wide barrier once per batch.
   if (producer) {
+    rt.role_producer(); // register re-allocation between the roles where the run-time interface implements it
     int buf = 0;
     for (int it = first; it < A.n_items; it += step, buf ^= 1) {
       const int itn = it + step, itnn = itn + step;
       if (itn < A.n_items) {
         const int bn = A.batches ? A.batches[itn] : itn;
-        ws_produce<N, R, GH>(rt, T, A, bn, itnn < A.n_items ? (A.batches ? A.batches[itnn] : itnn) : -1, pw, lane, pre, smem + OFF_TR + (buf ^ 1) * 2 * trs,
+        ws_produce<N, R, GH, NP>(rt, T, A, bn, itnn < A.n_items ? (A.batches ? A.batches[itnn] : itnn) : -1, pw, lane, pre, smem + OFF_TR + (buf ^ 1) * 2 * trs,
                              smem + OFF_TR + (buf ^ 1) * 2 * trs + trs, nl2 + (buf ^ 1) * B * 6, hlS + pw * WsCfg<N>::HLMAX);
       }
       rt.sync_all(); // hand-over: traces / index table of the next batch are complete, those of this batch are free
     }
     return;
   }
+  rt.role_compute();
   int buf = 0;
   for (int it = first; it < A.n_items; it += step, buf ^= 1) {
     const int itn = it + step;

@@ -46,7 +46,7 @@ void launch_diagonal_general(const DeviceOperator & op, double * diag, bool add,
 
 // ---- vmult_cartesian.cu ----
 bool cartesian_supported(int n);
-// selects the n = 5 kernel of the fast path (0 pipelined, 1 (default) / 2 warp-specialised with producer depth 8 / 12; -1 only queries); returns the previous value
+// selects the n = 5 kernel of the fast path (0 pipelined, 1 (default) / 2 warp-specialised with producer depth 8 / 12, 3 with 4 producer warps; -1 only queries); returns the previous value
 int cartesian_kernel_variant(int set);
 size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh);
 void cartesian_plan_destroy(DeviceOperator & op);

@@ -773,8 +773,8 @@ struct CartPlan
   void * ws = nullptr;
 };
 
-// kernel of the fast path for n = 5: 0 pipelined 4-warp kernel, 1 (default) / 2 warp-specialised kernel with producer depth 8 / 12
-// (EXADG_B200_CART_KERNEL=pipe / ws / ws12)
+// kernel of the fast path for n = 5: 0 pipelined 4-warp kernel, 1 (default) / 2 warp-specialised kernel with producer depth 8 / 12,
+// 3 warp-specialised kernel with 4 producer warps and register re-allocation (EXADG_B200_CART_KERNEL=pipe / ws / ws12 / ws4p)
 int g_cart_kernel = -1;
 
 template<int N>
@@ -856,7 +856,7 @@ bool cartesian_supported(int n) { return n >= 2 && n <= 8; }
 
 int cartesian_kernel_variant(int set)
 {
-  if (g_cart_kernel < 0) { const char * e = getenv("EXADG_B200_CART_KERNEL"); g_cart_kernel = (e && std::strcmp(e, "pipe") == 0) ? 0 : ((e && std::strcmp(e, "ws12") == 0) ? 2 : 1); }
+  if (g_cart_kernel < 0) { const char * e = getenv("EXADG_B200_CART_KERNEL"); g_cart_kernel = (e && std::strcmp(e, "pipe") == 0) ? 0 : ((e && std::strcmp(e, "ws12") == 0) ? 2 : ((e && std::strcmp(e, "ws4p") == 0) ? 3 : 1)); }
   const int previous = g_cart_kernel;
   if (set >= 0) g_cart_kernel = set;
   return previous;
@@ -982,7 +982,7 @@ void launch_vmult_cartesian_part(const DeviceOperator & op, double * dst, const 
       const bool ws_ok = plan->ws && variant >= 1 && (!with_ghosts || ws_ghost);
       if (ws_ok)
         ws_launch(op, plan->ws, dst, src, add, which == 0 ? nullptr : (which == 1 ? plan->d_interior : plan->d_boundary),
-                  which == 0 ? plan->n_batches : (which == 1 ? plan->n_interior : plan->n_boundary), plan->n_sm, variant == 2 ? 12 : 8, with_ghosts, stream);
+                  which == 0 ? plan->n_batches : (which == 1 ? plan->n_interior : plan->n_boundary), plan->n_sm, variant == 2 ? 12 : (variant == 3 ? 4 : 8), with_ghosts, stream);
       else if (plan->pipe) launch_pipe<5>(op, *plan, dst, src, add, which, stream);
       else launch_n<5>(op, *plan, dst, src, add, which, stream);
       break;

@@ -14,6 +14,9 @@ using namespace ws;
 
 __device__ __forceinline__ uint32_t s32(const void * p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// NT: threads per CTA (CTA-wide barrier); REG: re-allocate registers between the roles (4 compute + 4 producer warps launched
+// with 128 registers per thread: the compute warpgroup grows to 160, the producer warpgroup shrinks to 96)
+template<int NT, bool REG>
 struct DeviceRT
 {
   double * base;
@@ -27,7 +30,9 @@ struct DeviceRT
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(bar)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __device__ __forceinline__ void sync_all() { asm volatile("bar.sync 2, %0;" ::"n"(WsCfg<5>::NT) : "memory"); } // reached from both roles' loops
+  __device__ __forceinline__ void sync_all() { asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory"); } // reached from both roles' loops
+  __device__ __forceinline__ void role_compute() { if (REG) asm volatile("setmaxnreg.inc.sync.aligned.u32 160;"); }
+  __device__ __forceinline__ void role_producer() { if (REG) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;"); }
   __device__ __forceinline__ void sync_compute() { asm volatile("bar.sync 1, %0;" ::"n"(WsCfg<5>::NC) : "memory"); }
   __device__ __forceinline__ void sync_producer(int) { __syncwarp(); }
   // global -> shared bulk copy, completion on the mbarrier (SASS: UBLKCP)
@@ -56,13 +61,14 @@ struct DeviceRT
   __device__ __forceinline__ void store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 };
 
-// R: neighbour cells per producer round; GH: the partition has ghost cells (src of the neighbours may live in the ghost buffer)
-template<int N, int R, bool GH>
-__global__ void __launch_bounds__(WsCfg<N>::NT, 2) vmult_cartesian_ws_kernel(const __grid_constant__ WsTables<N> T, const WsArgs A)
+// R: neighbour cells per producer round; GH: the partition has ghost cells (src of the neighbours may live in the ghost buffer);
+// NP: producer warps (2, or 4 with register re-allocation between the roles - not measured yet)
+template<int N, int R, bool GH, int NP>
+__global__ void __launch_bounds__(WsCfg<N, NP>::NT, 2) vmult_cartesian_ws_kernel(const __grid_constant__ WsTables<N> T, const WsArgs A)
 {
   extern __shared__ __align__(128) double ws_shared[];
-  DeviceRT rt{ws_shared, 0u};
-  ws_cta<N, R, GH>(rt, T, A);
+  DeviceRT<WsCfg<N, NP>::NT, (NP == 4)> rt{ws_shared, 0u};
+  ws_cta<N, R, GH, NP>(rt, T, A);
 }
 
 constexpr size_t WS_MAX_SMEM = 228 * 1024 / 2 - 1024; // half of an SM's shared memory minus the per-CTA reservation
@@ -71,7 +77,7 @@ struct WsDevPlan
 {
   i2 * d_halo = nullptr; int32_t * d_cnt = nullptr, * d_nloc = nullptr;
   int HL = 0, n_batches = 0, ctas_per_sm = 0;
-  size_t smem = 0;
+  size_t smem = 0, smem4 = 0; // smem4: with 4 producer warps (0 if it does not fit)
   WsTables<5> T;
 };
 } // namespace
@@ -95,14 +101,21 @@ void * ws_plan_create(const DeviceOperator & op, const HostMesh & mesh)
   CUDA_CHECK(cudaMalloc(&P->d_nloc, H.nloc.size() * sizeof(int32_t)));
   CUDA_CHECK(cudaMemcpy(P->d_nloc, H.nloc.data(), H.nloc.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   P->ctas_per_sm = 2;
-  auto configure = [&](auto kernel) {
+  auto configure = [&](auto kernel, int threads, size_t bytes) {
     int occ = 0;
     CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_MAX_SMEM)); // same for every operator
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, WsCfg<5>::NT, smem));
-    P->ctas_per_sm = std::min(P->ctas_per_sm, occ);
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, bytes));
+    return occ;
   };
-  configure(vmult_cartesian_ws_kernel<5, 8, false>); configure(vmult_cartesian_ws_kernel<5, 12, false>);
-  configure(vmult_cartesian_ws_kernel<5, 8, true>); configure(vmult_cartesian_ws_kernel<5, 12, true>);
+  P->ctas_per_sm = std::min(P->ctas_per_sm, configure(vmult_cartesian_ws_kernel<5, 8, false, 2>, WsCfg<5>::NT, smem));
+  P->ctas_per_sm = std::min(P->ctas_per_sm, configure(vmult_cartesian_ws_kernel<5, 12, false, 2>, WsCfg<5>::NT, smem));
+  P->ctas_per_sm = std::min(P->ctas_per_sm, configure(vmult_cartesian_ws_kernel<5, 8, true, 2>, WsCfg<5>::NT, smem));
+  P->ctas_per_sm = std::min(P->ctas_per_sm, configure(vmult_cartesian_ws_kernel<5, 12, true, 2>, WsCfg<5>::NT, smem));
+  // experimental variant with 4 producer warps: only if it fits two CTAs per SM as well
+  P->smem4 = ws_smem_bytes<5, 4>(H.HL);
+  if (P->smem4 > WS_MAX_SMEM || configure(vmult_cartesian_ws_kernel<5, 4, false, 4>, WsCfg<5, 4>::NT, P->smem4) < 2
+      || configure(vmult_cartesian_ws_kernel<5, 4, true, 4>, WsCfg<5, 4>::NT, P->smem4) < 2)
+    P->smem4 = 0;
   if (P->ctas_per_sm < 1) { ws_plan_destroy(P); return nullptr; }
   return P;
 }
@@ -116,7 +129,8 @@ void ws_plan_destroy(void * p)
 }
 
 // batches: optional list of batch ids (interior / boundary launches of the multi-GPU path), n_items its length (or all batches)
-// depth: neighbour cells per producer round (8 or 12); gh: the selected batches may have neighbours in the ghost buffer
+// depth: neighbour cells per producer round (8 or 12; 4 selects the variant with 4 producer warps); gh: the selected batches may
+// have neighbours in the ghost buffer
 void ws_launch(const DeviceOperator & op, const void * p, double * dst, const double * src, bool add, const int32_t * batches, int n_items, int n_sm, int depth, bool gh,
                cudaStream_t stream)
 {
@@ -126,12 +140,15 @@ void ws_launch(const DeviceOperator & op, const void * p, double * dst, const do
   A.halo = P->d_halo; A.cnt = P->d_cnt; A.nloc = P->d_nloc; A.batches = batches;
   A.src = src; A.ghost = op.ghost; A.dst = dst; A.n_owned = op.n_owned; A.n_items = n_items; A.HL = P->HL; A.add = add ? 1 : 0;
   const int grid = std::min(n_items, n_sm * P->ctas_per_sm);
-  if (depth == 12) {
-    if (gh) vmult_cartesian_ws_kernel<5, 12, true><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A);
-    else vmult_cartesian_ws_kernel<5, 12, false><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A);
+  if (depth == 4 && P->smem4 > 0) {
+    if (gh) vmult_cartesian_ws_kernel<5, 4, true, 4><<<grid, WsCfg<5, 4>::NT, P->smem4, stream>>>(P->T, A);
+    else vmult_cartesian_ws_kernel<5, 4, false, 4><<<grid, WsCfg<5, 4>::NT, P->smem4, stream>>>(P->T, A);
+  } else if (depth == 12) {
+    if (gh) vmult_cartesian_ws_kernel<5, 12, true, 2><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A);
+    else vmult_cartesian_ws_kernel<5, 12, false, 2><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A);
   } else {
-    if (gh) vmult_cartesian_ws_kernel<5, 8, true><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A);
-    else vmult_cartesian_ws_kernel<5, 8, false><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A);
+    if (gh) vmult_cartesian_ws_kernel<5, 8, true, 2><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A);
+    else vmult_cartesian_ws_kernel<5, 8, false, 2><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A);
   }
   CUDA_CHECK(cudaGetLastError());
 }

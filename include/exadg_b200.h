@@ -160,9 +160,10 @@ int exadg_b200_plan_peer(const exadg_b200_plan *plan, int i, int *peer_rank, int
 int exadg_b200_plan_tables(const exadg_b200_plan *plan, int32_t *neighbors, int64_t *ghost_global_ids);
 
 /* Tuning switch without a reference counterpart: kernel of the affine fast path for degree 4 (0: pipelined 4-warp kernel,
- * 1 (default) / 2: warp-specialised kernel with producer warps fetching 8 / 12 neighbour cells per round; -1 only queries).
+ * 1 (default) / 2: warp-specialised kernel with producer warps fetching 8 / 12 neighbour cells per round, 3: the same with four
+ * producer warps and register re-allocation between the roles (experimental); -1 only queries).
  * Process-wide; returns the previous value. All kernels compute the same operator (OperatorBase::apply,
- * operator_base.cpp:264-310); the environment variable EXADG_B200_CART_KERNEL=pipe / ws / ws12 selects 0 / 1 / 2 at start-up. */
+ * operator_base.cpp:264-310); the environment variable EXADG_B200_CART_KERNEL=pipe / ws / ws12 / ws4p selects 0 / 1 / 2 / 3 at start-up. */
 int exadg_b200_cartesian_kernel(int variant);
 
 /* FP64 pipe microbenchmarks used for the roofline denominators (DFMA and DMMA rates) */

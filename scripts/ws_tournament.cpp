@@ -1,5 +1,5 @@
 // Kernel tournament for the affine fast path at k = 4 (C ABI only, no Python): times the pipelined kernel (variant 0) and
-// the warp-specialised kernel (variants 1, 2) on the same operator and vectors, and checks that both give the same vmult /
+// the warp-specialised kernel (variants 1, 2, 3) on the same operator and vectors, and checks that both give the same vmult /
 // vmult_add.  Usage: ws_tournament only_variant|-1 (n_sub refine steps)...   (default: -1 3 5 100 = 96^3 cells, 100 steps)
 //   nvcc -O2 -std=c++17 scripts/ws_tournament.cpp -Iinclude -Lexadg_b200 -lexadg_b200 -Xlinker -rpath='$ORIGIN/../exadg_b200' -o build/ws_tournament
 #include <cuda_runtime.h>
@@ -35,8 +35,8 @@ static int run_mesh(int n_sub, int refine, int steps, int only)
   CK(exadg_b200_set_stream(op, stream));
   const int64_t n = exadg_b200_local_size(op);
   std::printf("cells %d^3 dofs %lld cartesian_path %d\n", n_sub << refine, (long long)n, exadg_b200_is_cartesian_path(op));
-  constexpr int NV = 3;
-  double * src = nullptr, * dst[NV] = {nullptr, nullptr, nullptr};
+  constexpr int NV = 4; // 0 pipelined, 1 WS depth 8, 2 WS depth 12, 3 WS with 4 producer warps (setmaxnreg)
+  double * src = nullptr, * dst[NV] = {nullptr, nullptr, nullptr, nullptr};
   CK(exadg_b200_initialize_dof_vector(op, &src));
   for (int v = 0; v < NV; ++v) CK(exadg_b200_initialize_dof_vector(op, &dst[v]));
   {

@@ -1,6 +1,6 @@
 // CPU emulation of the warp-specialised Cartesian kernel (exadg_b200/csrc/cart_ws.hpp): the very same CTA body, compiled by g++
 // against a run-time interface made of OS threads, pthread barriers and synchronous copies.  One OS thread per CUDA thread
-// (192 per CTA), CTAs one after the other.  Test infrastructure only (tests/test_ws_emulation.py): it checks indexing,
+// (192 or 256 per CTA), CTAs one after the other.  Test infrastructure only (tests/test_ws_emulation.py): it checks indexing,
 // the barrier protocol (under -fsanitize=thread every unordered shared-memory access is reported) and the results against the
 // CPU oracle, on a machine without a GPU.
 //
@@ -28,11 +28,15 @@ constexpr int N = 5;
 #ifndef WSE_R
 #define WSE_R 8
 #endif
+#ifndef WSE_NP
+#define WSE_NP 2
+#endif
+constexpr int NP = WSE_NP;
 
 struct HostCta
 {
   double * smem = nullptr;
-  pthread_barrier_t ba, bc, bp[WsCfg<N>::NP];
+  pthread_barrier_t ba, bc, bp[NP];
   std::atomic<int> loads{0};
   const double * st_src = nullptr; size_t st_bytes = 0; std::vector<char> snap; bool st_pending = false;
   std::atomic<int> errors{0};
@@ -50,6 +54,8 @@ struct HostRT
   void sync_all() { pthread_barrier_wait(&c->ba); }
   void sync_compute() { pthread_barrier_wait(&c->bc); }
   void sync_producer(int pw) { pthread_barrier_wait(&c->bp[pw]); }
+  void role_compute() {}
+  void role_producer() {}
   void load_issue(void *, double * dst, const double * src, uint32_t bytes)
   {
     if (bytes % 16 != 0) c->errors++;
@@ -117,7 +123,7 @@ int64_t wse_n_ghost(void * h) { return static_cast<Emu *>(h)->mesh.n_ghost; }
 int64_t wse_global_offset(void * h) { return static_cast<Emu *>(h)->mesh.global_offset; }
 void wse_ghost_global(void * h, int64_t * out) { Emu * E = static_cast<Emu *>(h); std::copy(E->mesh.ghost_global.begin(), E->mesh.ghost_global.end(), out); }
 int wse_halo_max(void * h) { return static_cast<Emu *>(h)->plan.HL; }
-int64_t wse_smem_bytes(void * h) { return (int64_t)ws_smem_bytes<N>(static_cast<Emu *>(h)->plan.HL); }
+int64_t wse_smem_bytes(void * h) { return (int64_t)ws_smem_bytes<N, NP>(static_cast<Emu *>(h)->plan.HL); }
 int wse_n_batches(void * h, int which) { Emu * E = static_cast<Emu *>(h); return which == 0 ? E->plan.n_batches : (which == 1 ? (int)E->interior.size() : (int)E->boundary.size()); }
 
 // dst (+)= A src on the batches selected by `which` (0 all, 1 batches without ghost neighbours, 2 batches with), n_ctas persistent CTAs;
@@ -136,19 +142,19 @@ int wse_vmult(void * h, const double * src, const double * ghost, double * dst, 
   int errors = 0;
   for (int cta = 0; cta < n_ctas; ++cta) {
     HostCta C;
-    std::vector<double> smem(ws_smem_bytes<N>(E->plan.HL) / sizeof(double) + 2, -777.0);
+    std::vector<double> smem(ws_smem_bytes<N, NP>(E->plan.HL) / sizeof(double) + 2, -777.0);
     C.smem = smem.data(); C.cta = cta; C.ncta = n_ctas;
-    pthread_barrier_init(&C.ba, nullptr, WsCfg<N>::NT);
+    pthread_barrier_init(&C.ba, nullptr, WsCfg<N, NP>::NT);
     pthread_barrier_init(&C.bc, nullptr, WsCfg<N>::NC);
-    for (int p = 0; p < WsCfg<N>::NP; ++p) pthread_barrier_init(&C.bp[p], nullptr, 32);
+    for (int p = 0; p < NP; ++p) pthread_barrier_init(&C.bp[p], nullptr, 32);
     std::vector<std::thread> threads;
-    for (int t = 0; t < WsCfg<N>::NT; ++t)
+    for (int t = 0; t < WsCfg<N, NP>::NT; ++t)
       threads.emplace_back([&, t]() {
         HostRT rt{&C, t};
-        if (E->mesh.n_ghost > 0) ws_cta<N, WSE_R, true>(rt, E->T, A); else ws_cta<N, WSE_R, false>(rt, E->T, A);
+        if (E->mesh.n_ghost > 0) ws_cta<N, WSE_R, true, NP>(rt, E->T, A); else ws_cta<N, WSE_R, false, NP>(rt, E->T, A);
       });
     for (auto & th : threads) th.join();
-    pthread_barrier_destroy(&C.ba); pthread_barrier_destroy(&C.bc); for (int p = 0; p < WsCfg<N>::NP; ++p) pthread_barrier_destroy(&C.bp[p]);
+    pthread_barrier_destroy(&C.ba); pthread_barrier_destroy(&C.bc); for (int p = 0; p < NP; ++p) pthread_barrier_destroy(&C.bp[p]);
     errors += C.errors.load() + (C.st_pending ? 1 : 0);
   }
   return errors;

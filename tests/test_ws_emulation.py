@@ -1,7 +1,7 @@
 """CPU emulation of the warp-specialised Cartesian kernel (exadg_b200/csrc/cart_ws.hpp) against the oracle.
 
 The CTA body of the CUDA kernel is written against a small run-time interface; tests/cpp/ws_emulate.cpp compiles the same body
-with g++ on OS threads (192 per CTA, pthread barriers, synchronous bulk copies with a late-read check).  This pins the indexing,
+with g++ on OS threads (192 or 256 per CTA, pthread barriers, synchronous bulk copies with a late-read check).  This pins the indexing,
 the producer/consumer protocol and the folded 1-D tables of that kernel to the oracle without a GPU; a second build under
 ThreadSanitizer reports any shared-memory access that the kernel's barriers do not order."""
 import ctypes
@@ -34,10 +34,11 @@ def _build(path, extra):
     return lib
 
 
-@pytest.fixture(scope="module", params=[8, 12], ids=["depth8", "depth12"])
+@pytest.fixture(scope="module", params=[(8, 2), (12, 2), (4, 4)], ids=["depth8", "depth12", "depth4_4producers"])
 def emu(request, tmp_path_factory):
-    """both producer depths the library instantiates (neighbour cells fetched per round)"""
-    return _build(str(tmp_path_factory.mktemp("wse") / ("libwse%d.so" % request.param)), ["-DWSE_R=%d" % request.param])
+    """the kernel instantiations of the library: neighbour cells fetched per producer round, producer warps"""
+    depth, producers = request.param
+    return _build(str(tmp_path_factory.mktemp("wse") / ("libwse%d_%d.so" % request.param)), ["-DWSE_R=%d" % depth, "-DWSE_NP=%d" % producers])
 
 
 def _ptr(a):
