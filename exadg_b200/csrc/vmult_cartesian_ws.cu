@@ -2,6 +2,7 @@
 // barriers, mbarrier + 1-D bulk copies), the kernel wrapper, the device copy of the batch plan and the launch.
 // The CTA body itself lives in cart_ws.hpp and is also compiled for the CPU emulation (tests/cpp/ws_emulate.cpp).
 #include <cstring>
+#include <stdexcept>
 
 #include "cart_ws.hpp"
 #include "operator.cuh"
@@ -92,6 +93,7 @@ void * ws_plan_create(const DeviceOperator & op, const HostMesh & mesh)
   const size_t smem = ws_smem_bytes<5>(H.HL);
   if (smem > WS_MAX_SMEM || H.HL > WsCfg<5>::HLMAX) return nullptr; // two CTAs per SM are what the kernel is built for
   WsDevPlan * P = new WsDevPlan;
+  try {
   P->HL = H.HL; P->n_batches = H.n_batches; P->smem = smem;
   P->T = make_ws_tables<5>(op.h, op.tau_hat);
   CUDA_CHECK(cudaMalloc(&P->d_halo, H.halo.size() * sizeof(i2)));
@@ -112,10 +114,14 @@ void * ws_plan_create(const DeviceOperator & op, const HostMesh & mesh)
   P->ctas_per_sm = std::min(P->ctas_per_sm, configure(vmult_cartesian_ws_kernel<5, 8, true, 2>, WsCfg<5>::NT, smem));
   P->ctas_per_sm = std::min(P->ctas_per_sm, configure(vmult_cartesian_ws_kernel<5, 12, true, 2>, WsCfg<5>::NT, smem));
   // experimental variant with 4 producer warps: only if it fits two CTAs per SM as well
-  P->smem4 = ws_smem_bytes<5, 4>(H.HL);
-  if (P->smem4 > WS_MAX_SMEM || configure(vmult_cartesian_ws_kernel<5, 4, false, 4>, WsCfg<5, 4>::NT, P->smem4) < 2
-      || configure(vmult_cartesian_ws_kernel<5, 4, true, 4>, WsCfg<5, 4>::NT, P->smem4) < 2)
-    P->smem4 = 0;
+  // (a failure here must not take the default kernel down with it)
+  try {
+    P->smem4 = ws_smem_bytes<5, 4>(H.HL);
+    if (P->smem4 > WS_MAX_SMEM || configure(vmult_cartesian_ws_kernel<5, 4, false, 4>, WsCfg<5, 4>::NT, P->smem4) < 2
+        || configure(vmult_cartesian_ws_kernel<5, 4, true, 4>, WsCfg<5, 4>::NT, P->smem4) < 2)
+      P->smem4 = 0;
+  } catch (const std::exception &) { P->smem4 = 0; cudaGetLastError(); }
+  } catch (...) { ws_plan_destroy(P); throw; }
   if (P->ctas_per_sm < 1) { ws_plan_destroy(P); return nullptr; }
   return P;
 }
