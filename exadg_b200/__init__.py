@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = [
     "exadg_b200_set_stream", "exadg_b200_synchronize", "exadg_b200_n", "exadg_b200_local_size", "exadg_b200_n_cells_owned",
     "exadg_b200_n_cells_ghost", "exadg_b200_is_cartesian_path", "exadg_b200_kernel_launches", "exadg_b200_initialize_dof_vector",
     "exadg_b200_free_dof_vector", "exadg_b200_vmult", "exadg_b200_vmult_add", "exadg_b200_vmult_host",
+    "exadg_b200_vmult_host_pipelined", "exadg_b200_host_pipeline_plan",
     "exadg_b200_calculate_diagonal", "exadg_b200_add_diagonal", "exadg_b200_calculate_inverse_diagonal", "exadg_b200_jacobi_vmult",
     "exadg_b200_cg_solve", "exadg_b200_chebyshev_create", "exadg_b200_chebyshev_destroy", "exadg_b200_chebyshev_get",
     "exadg_b200_chebyshev_set_interval", "exadg_b200_chebyshev_vmult", "exadg_b200_chebyshev_step", "exadg_b200_set_nccl_comm",
@@ -76,6 +77,9 @@ def load_library():
     L.exadg_b200_vmult.argtypes = [vp, dp, dp]
     L.exadg_b200_vmult_add.argtypes = [vp, dp, dp]
     L.exadg_b200_vmult_host.argtypes = [vp, vp, vp]
+    L.exadg_b200_vmult_host_pipelined.argtypes = [vp, vp, vp]
+    L.exadg_b200_host_pipeline_plan.argtypes = [C.POINTER(HypercubeDesc), i64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                                C.POINTER(C.c_int32), C.POINTER(C.c_double)]
     L.exadg_b200_calculate_diagonal.argtypes = [vp, dp]
     L.exadg_b200_add_diagonal.argtypes = [vp, dp]
     L.exadg_b200_calculate_inverse_diagonal.argtypes = [vp, dp]
@@ -111,7 +115,7 @@ def load_library():
 
 
 from .laplace_operator import (ChebyshevSmoother, ExaDGError, JacobiPreconditioner, KrylovSolverCG, PartitionPlan,  # noqa: E402
-                               LaplaceOperator, SolverData, cartesian_kernel, fp64_peak)
+                               LaplaceOperator, SolverData, cartesian_kernel, fp64_peak, host_pipeline_plan)
 
 __all__ = ["LaplaceOperator", "KrylovSolverCG", "ChebyshevSmoother", "JacobiPreconditioner", "SolverData", "ExaDGError",
-           "fp64_peak", "cartesian_kernel", "load_library", "PERIODIC", "DIRICHLET", "NEUMANN"]
+           "fp64_peak", "cartesian_kernel", "host_pipeline_plan", "load_library", "PERIODIC", "DIRICHLET", "NEUMANN"]

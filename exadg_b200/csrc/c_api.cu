@@ -7,6 +7,7 @@
 #include <string>
 
 #include "../../include/exadg_b200.h"
+#include "host_pipeline.hpp"
 #include "operator.cuh"
 #include "vector_ops.cuh"
 
@@ -138,6 +139,10 @@ struct exadg_b200_operator
   double * w[4] = {nullptr, nullptr, nullptr, nullptr};
   double * d_cell_diag = nullptr;
   double * d_stage_src = nullptr, * d_stage_dst = nullptr;
+  // pipelined host-buffer vmult (exadg_b200_vmult_host_pipelined)
+  HostPipelinePlan hp; bool hp_built = false;
+  cudaStream_t hp_in = nullptr, hp_out = nullptr; cudaEvent_t hp_start = nullptr;
+  std::vector<cudaEvent_t> hp_ev_in, hp_ev_cmp; int32_t * d_iota = nullptr;
 
   double * work(int i)
   {
@@ -553,6 +558,12 @@ int exadg_b200_destroy(exadg_b200_operator * op)
   cudaFree(op->d_interior); cudaFree(op->d_boundary); cudaFree(op->d_cell_diag);
   for (int i = 0; i < 4; ++i) cudaFree(op->w[i]);
   cudaFree(op->d_stage_src); cudaFree(op->d_stage_dst);
+  cudaFree(op->d_iota);
+  for (auto e : op->hp_ev_in) cudaEventDestroy(e);
+  for (auto e : op->hp_ev_cmp) cudaEventDestroy(e);
+  if (op->hp_start) cudaEventDestroy(op->hp_start);
+  if (op->hp_in) cudaStreamDestroy(op->hp_in);
+  if (op->hp_out) cudaStreamDestroy(op->hp_out);
   reducer_free(op->red);
   if (op->own_comm && op->comm) nccl().CommDestroy(op->comm);
   if (op->ev_packed) cudaEventDestroy(op->ev_packed);
@@ -609,6 +620,98 @@ int exadg_b200_vmult_host(exadg_b200_operator * op, double * dst_host, const dou
     CUDA_CHECK(cudaMemcpyAsync(dst_host, op->d_stage_dst, bytes, cudaMemcpyDeviceToHost, op->stream));
     CUDA_CHECK(cudaStreamSynchronize(op->stream));
     return EXADG_B200_OK;
+  });
+}
+
+// Same result as exadg_b200_vmult_host, but the upload of src, the operator and the download of dst overlap: the vector is cut into
+// contiguous chunks (host_pipeline.hpp), a chunk is applied as soon as the chunks holding its face neighbours have arrived and is
+// downloaded right behind its kernel on a third stream.  Unpartitioned operators only; host buffers should be pinned.
+static int64_t host_pipeline_cells_per_chunk(int batch)
+{
+  // about 1536 cells (three 8^3 blocks of the Morton curve on refined hypercubes), a multiple of the kernels' batch size
+  const int64_t per = std::max<int64_t>(1, (1536 + batch / 2) / batch);
+  return per * batch;
+}
+
+int exadg_b200_vmult_host_pipelined(exadg_b200_operator * op, double * dst_host, const double * src_host)
+{
+  return guarded([&]() {
+    if (!op || !dst_host || !src_host) throw std::invalid_argument("null argument");
+    HostMesh & M = op->mesh;
+    if (M.world > 1 || M.n_ghost > 0) { g_last_error = "the pipelined host-buffer vmult is for unpartitioned operators"; return (int)EXADG_B200_ERR_UNSUPPORTED; }
+    const int n3 = op->dev.n * op->dev.n * op->dev.n;
+    const bool cart = op->dev.cartesian;
+    const int B = cart ? cartesian_batch_size(op->dev) : 1;
+    const size_t bytes = (size_t)op->n_local * sizeof(double);
+    if (!op->hp_built) {
+      op->hp = build_host_pipeline(M.nb.data(), M.n_owned, host_pipeline_cells_per_chunk(B));
+      const int64_t n_units = cart ? (int64_t)cartesian_n_batches(op->dev) : M.n_owned;
+      std::vector<int32_t> iota((size_t)std::max<int64_t>(n_units, 1));
+      for (size_t i = 0; i < iota.size(); ++i) iota[i] = (int32_t)i;
+      CUDA_CHECK(cudaMalloc(&op->d_iota, iota.size() * sizeof(int32_t)));
+      CUDA_CHECK(cudaMemcpy(op->d_iota, iota.data(), iota.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaStreamCreateWithFlags(&op->hp_in, cudaStreamNonBlocking));
+      CUDA_CHECK(cudaStreamCreateWithFlags(&op->hp_out, cudaStreamNonBlocking));
+      CUDA_CHECK(cudaEventCreateWithFlags(&op->hp_start, cudaEventDisableTiming));
+      op->hp_ev_in.assign(op->hp.n_chunks, nullptr); op->hp_ev_cmp.assign(op->hp.n_chunks, nullptr);
+      for (int c = 0; c < op->hp.n_chunks; ++c) {
+        CUDA_CHECK(cudaEventCreateWithFlags(&op->hp_ev_in[c], cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&op->hp_ev_cmp[c], cudaEventDisableTiming));
+      }
+      op->hp_built = true;
+    }
+    const HostPipelinePlan & P = op->hp;
+    if (P.n_chunks == 0) { g_last_error = "the pipelined host-buffer vmult is for unpartitioned operators"; return (int)EXADG_B200_ERR_UNSUPPORTED; }
+    if (!op->d_stage_src) { CUDA_CHECK(cudaMalloc(&op->d_stage_src, std::max<size_t>(bytes, 16))); CUDA_CHECK(cudaMalloc(&op->d_stage_dst, std::max<size_t>(bytes, 16))); }
+    // neither copy stream may overtake earlier work of the operator's stream on the staging vectors
+    CUDA_CHECK(cudaEventRecord(op->hp_start, op->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(op->hp_in, op->hp_start, 0));
+    CUDA_CHECK(cudaStreamWaitEvent(op->hp_out, op->hp_start, 0));
+    auto range = [&](int c, int64_t & c0, int64_t & c1) { c0 = (int64_t)c * P.cells_per_chunk; c1 = std::min<int64_t>(M.n_owned, c0 + P.cells_per_chunk); };
+    size_t next = 0; // next entry of compute_order (its chunks become computable in upload order)
+    for (int32_t b : P.upload_order) {
+      int64_t c0, c1; range(b, c0, c1);
+      CUDA_CHECK(cudaMemcpyAsync(op->d_stage_src + c0 * n3, src_host + c0 * n3, (size_t)(c1 - c0) * n3 * sizeof(double), cudaMemcpyHostToDevice, op->hp_in));
+      CUDA_CHECK(cudaEventRecord(op->hp_ev_in[b], op->hp_in));
+      while (next < P.compute_order.size() && P.ready_chunk[P.compute_order[next]] == b) {
+        const int c = P.compute_order[next++];
+        range(c, c0, c1);
+        CUDA_CHECK(cudaStreamWaitEvent(op->stream, op->hp_ev_in[b], 0)); // uploads complete in order: the last dependency covers the others
+        if (cart) launch_vmult_cartesian_list(op->dev, op->d_stage_dst, op->d_stage_src, false, op->d_iota + c0 / B, (int)((c1 - c0 + B - 1) / B), op->stream);
+        else launch_vmult_general(op->dev, op->d_stage_dst, op->d_stage_src, false, op->d_iota + c0, c1 - c0, op->stream);
+        op->launches++;
+        CUDA_CHECK(cudaEventRecord(op->hp_ev_cmp[c], op->stream));
+        CUDA_CHECK(cudaStreamWaitEvent(op->hp_out, op->hp_ev_cmp[c], 0));
+        CUDA_CHECK(cudaMemcpyAsync(dst_host + c0 * n3, op->d_stage_dst + c0 * n3, (size_t)(c1 - c0) * n3 * sizeof(double), cudaMemcpyDeviceToHost, op->hp_out));
+      }
+    }
+    if (next != P.compute_order.size()) throw std::runtime_error("host pipeline plan incomplete");
+    CUDA_CHECK(cudaStreamSynchronize(op->hp_out));
+    CUDA_CHECK(cudaStreamSynchronize(op->stream));
+    return (int)EXADG_B200_OK;
+  });
+}
+
+// host-only view of that plan (no CUDA call), for the CPU tests: sizes with null arrays, then the three tables of n_chunks entries;
+// model = duration of one call in units of a one-direction transfer (2 = no overlap)
+int exadg_b200_host_pipeline_plan(const exadg_b200_hypercube_desc * desc, int64_t cells_per_chunk, int32_t * n_chunks, int32_t * upload_order, int32_t * compute_order,
+                                  int32_t * ready_chunk, double * model)
+{
+  return guarded([&]() {
+    if (!desc || !n_chunks) throw std::invalid_argument("null argument");
+    HypercubeDesc hd;
+    hd.n_sub = desc->n_subdivisions; hd.refine = desc->n_refinements; hd.mapping_degree = 1;
+    hd.deformation = 0.0; hd.frequency = desc->frequency;
+    for (int f = 0; f < 6; ++f) hd.bc[f] = desc->boundary[f];
+    hd.rank = desc->rank; hd.world = desc->world < 1 ? 1 : desc->world;
+    const HostMesh mesh = make_hypercube(hd);
+    const HostPipelinePlan P = build_host_pipeline(mesh.nb.data(), mesh.n_owned, cells_per_chunk > 0 ? cells_per_chunk : host_pipeline_cells_per_chunk(24));
+    *n_chunks = P.n_chunks;
+    if (upload_order) std::copy(P.upload_order.begin(), P.upload_order.end(), upload_order);
+    if (compute_order) std::copy(P.compute_order.begin(), P.compute_order.end(), compute_order);
+    if (ready_chunk) std::copy(P.ready_chunk.begin(), P.ready_chunk.end(), ready_chunk);
+    if (model) *model = host_pipeline_model(P);
+    return (int)EXADG_B200_OK;
   });
 }
 

@@ -1,0 +1,81 @@
+// Host-side plan of the pipelined host-buffer vmult (exadg_b200_vmult_host_pipelined): PCIe is full duplex, so the upload of src
+// and the download of dst can overlap inside one call if the operator is applied chunk by chunk.  The vector is cut into
+// contiguous chunks of cells; a chunk can be applied as soon as the chunks holding the face neighbours of its cells have been
+// uploaded (the SIPG operator couples a cell with its six neighbours only: face_loop of I/operators/operator_base.cpp:1372-1397).
+// This header decides the upload order and the moment every chunk becomes computable; it is pure host code (CPU-testable through
+// exadg_b200_host_pipeline_plan), the stream / event choreography is in c_api.cu.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <vector>
+
+namespace exadg_b200
+{
+struct HostPipelinePlan
+{
+  int n_chunks = 0;                   // 0: not applicable (ghost neighbours: partitioned operators keep the sequential path)
+  int64_t cells_per_chunk = 0;
+  std::vector<int32_t> upload_order;  // chunk ids in the order they are uploaded
+  std::vector<int32_t> compute_order; // chunk ids in the order they become computable
+  std::vector<int32_t> ready_chunk;   // per chunk: the chunk whose upload completes its dependencies
+};
+
+// nb: [n_owned][6] neighbour cell (or < 0 on the boundary); cells_per_chunk must be a multiple of the kernels' batch size
+inline HostPipelinePlan build_host_pipeline(const int32_t * nb, int64_t n_owned, int64_t cells_per_chunk)
+{
+  HostPipelinePlan P;
+  if (n_owned <= 0 || cells_per_chunk <= 0) return P;
+  const int K = (int)((n_owned + cells_per_chunk - 1) / cells_per_chunk);
+  // dependency sets: chunk a needs chunk b if a cell of a has a neighbour in b
+  std::vector<std::vector<int32_t>> deps(K);
+  for (int a = 0; a < K; ++a) deps[a].push_back(a);
+  for (int64_t c = 0; c < n_owned; ++c) {
+    const int a = (int)(c / cells_per_chunk);
+    for (int f = 0; f < 6; ++f) {
+      const int32_t p = nb[c * 6 + f];
+      if (p < 0) continue;
+      if (p >= n_owned) return P; // ghost cell
+      const int b = (int)(p / cells_per_chunk);
+      if (b != a && (deps[a].empty() || deps[a].back() != b)) deps[a].push_back(b);
+    }
+  }
+  std::vector<std::vector<int32_t>> needed_by(K);
+  for (int a = 0; a < K; ++a) {
+    std::sort(deps[a].begin(), deps[a].end());
+    deps[a].erase(std::unique(deps[a].begin(), deps[a].end()), deps[a].end());
+    for (int32_t b : deps[a]) needed_by[b].push_back(a);
+  }
+  // greedy upload order: complete the chunk that misses the fewest uploads, so that chunks become computable early and steadily
+  P.n_chunks = K; P.cells_per_chunk = cells_per_chunk;
+  P.ready_chunk.assign(K, -1);
+  std::vector<int> missing(K);
+  std::vector<char> uploaded(K, 0);
+  for (int a = 0; a < K; ++a) missing[a] = (int)deps[a].size();
+  auto upload = [&](int b) {
+    if (uploaded[b]) return;
+    uploaded[b] = 1; P.upload_order.push_back(b);
+    for (int32_t a : needed_by[b])
+      if (--missing[a] == 0) { P.ready_chunk[a] = b; P.compute_order.push_back(a); }
+  };
+  while ((int)P.upload_order.size() < K) {
+    int best = -1;
+    for (int a = 0; a < K; ++a)
+      if (missing[a] > 0 && (best < 0 || missing[a] < missing[best])) best = a;
+    if (best < 0) break; // cannot happen: a chunk that is not uploaded misses at least itself
+    for (int32_t b : deps[best]) upload(b);
+  }
+  return P;
+}
+
+// model of the plan: duration of one call in units of the time one direction takes alone (uploads back to back, downloads in
+// compute order as soon as a chunk is computable, compute time neglected); 2.0 = no overlap
+inline double host_pipeline_model(const HostPipelinePlan & P)
+{
+  if (P.n_chunks == 0) return 2.0;
+  std::vector<int> pos(P.n_chunks);
+  for (int i = 0; i < P.n_chunks; ++i) pos[P.upload_order[i]] = i + 1; // time at which the upload of the chunk is complete
+  double t = 0;
+  for (int32_t c : P.compute_order) t = std::max(t, (double)pos[P.ready_chunk[c]]) + 1.0;
+  return t / P.n_chunks;
+}
+} // namespace exadg_b200

@@ -52,6 +52,10 @@ size_t cartesian_plan_create(DeviceOperator & op, const HostMesh & mesh);
 void cartesian_plan_destroy(DeviceOperator & op);
 // which: 0 all cell batches, 1 batches touching no ghost cell, 2 batches touching ghost cells
 void launch_vmult_cartesian_part(const DeviceOperator & op, double * dst, const double * src, bool add, int which, cudaStream_t stream);
+// explicit device list of batch ids (operators without ghost cells): chunks of the pipelined host-buffer vmult
+void launch_vmult_cartesian_list(const DeviceOperator & op, double * dst, const double * src, bool add, const int32_t * list, int n_list, cudaStream_t stream);
+int cartesian_batch_size(const DeviceOperator & op);
+int cartesian_n_batches(const DeviceOperator & op);
 
 // ---- vmult_cartesian_ws.cu (warp-specialised kernel, n = 5) ----
 bool ws_supported(int n);

@@ -814,8 +814,10 @@ CartTables<N> make_cart_tables(const DeviceOperator & op)
   return T;
 }
 
+// list / n_list: explicit batch list (chunked host-buffer vmult); otherwise `which` selects all / interior / boundary batches
 template<int N>
-void launch_n(const DeviceOperator & op, const CartPlan & plan, double * dst, const double * src, bool add, int which, cudaStream_t stream)
+void launch_n(const DeviceOperator & op, const CartPlan & plan, double * dst, const double * src, bool add, int which, cudaStream_t stream, const int32_t * list = nullptr,
+              int n_list = 0)
 {
   constexpr int B = CartCfg<N>::B;
   const CartTables<N> & T = *reinterpret_cast<const CartTables<N> *>(plan.tables.data());
@@ -826,12 +828,14 @@ void launch_n(const DeviceOperator & op, const CartPlan & plan, double * dst, co
   A.n_owned = op.n_owned; A.H = plan.H; A.add = add ? 1 : 0;
   A.batches = which == 0 ? nullptr : (which == 1 ? plan.d_interior : plan.d_boundary);
   A.n_items = which == 0 ? plan.n_batches : (which == 1 ? plan.n_interior : plan.n_boundary);
+  if (list) { A.batches = list; A.n_items = n_list; }
   if (A.n_items == 0) return;
   vmult_cartesian_kernel<N><<<A.n_items, B * N, plan.smem, stream>>>(T, A);
   CUDA_CHECK(cudaGetLastError());
 }
 template<int N>
-void launch_pipe(const DeviceOperator & op, const CartPlan & plan, double * dst, const double * src, bool add, int which, cudaStream_t stream)
+void launch_pipe(const DeviceOperator & op, const CartPlan & plan, double * dst, const double * src, bool add, int which, cudaStream_t stream, const int32_t * list = nullptr,
+                 int n_list = 0)
 {
   const CartTables<N> & T = *reinterpret_cast<const CartTables<N> *>(plan.tables.data());
   static int ctas_per_sm = 0;
@@ -845,6 +849,7 @@ void launch_pipe(const DeviceOperator & op, const CartPlan & plan, double * dst,
   A.n_owned = op.n_owned; A.HL = plan.HL; A.HD = plan.HD; A.add = add ? 1 : 0;
   A.batches = which == 0 ? nullptr : (which == 1 ? plan.d_interior : plan.d_boundary);
   A.n_items = which == 0 ? plan.n_batches : (which == 1 ? plan.n_interior : plan.n_boundary);
+  if (list) { A.batches = list; A.n_items = n_list; }
   if (A.n_items == 0) return;
   const int grid = std::min(A.n_items, plan.n_sm * ctas_per_sm);
   vmult_cartesian_pipe_kernel<N><<<grid, PipeCfg<N>::NT, plan.smem, stream>>>(T, A);
@@ -963,15 +968,40 @@ void cartesian_plan_destroy(DeviceOperator & op)
   op.cart_plan = nullptr;
 }
 
+int cartesian_batch_size(const DeviceOperator & op)
+{
+  const CartPlan * plan = static_cast<const CartPlan *>(op.cart_plan);
+  return plan ? plan->B : 0;
+}
+int cartesian_n_batches(const DeviceOperator & op)
+{
+  const CartPlan * plan = static_cast<const CartPlan *>(op.cart_plan);
+  return plan ? plan->n_batches : 0;
+}
+
+static void launch_cart(const DeviceOperator & op, double * dst, const double * src, bool add, int which, const int32_t * list, int n_list, cudaStream_t stream);
+
 // which: 0 all batches, 1 batches that touch no ghost cell, 2 batches that do
 void launch_vmult_cartesian_part(const DeviceOperator & op, double * dst, const double * src, bool add, int which, cudaStream_t stream)
+{
+  launch_cart(op, dst, src, add, which, nullptr, 0, stream);
+}
+
+// explicit list of batches of an operator without ghost cells (chunks of the pipelined host-buffer vmult)
+void launch_vmult_cartesian_list(const DeviceOperator & op, double * dst, const double * src, bool add, const int32_t * list, int n_list, cudaStream_t stream)
+{
+  if (op.n_ghost > 0) throw std::runtime_error("batch-list launches are for operators without ghost cells");
+  if (n_list > 0) launch_cart(op, dst, src, add, 1, list, n_list, stream);
+}
+
+static void launch_cart(const DeviceOperator & op, double * dst, const double * src, bool add, int which, const int32_t * list, int n_list, cudaStream_t stream)
 {
   const CartPlan * plan = static_cast<const CartPlan *>(op.cart_plan);
   if (!plan) throw std::runtime_error("Cartesian plan missing");
   switch (op.n) {
-    case 2: launch_n<2>(op, *plan, dst, src, add, which, stream); break;
-    case 3: if (plan->pipe) launch_pipe<3>(op, *plan, dst, src, add, which, stream); else launch_n<3>(op, *plan, dst, src, add, which, stream); break;
-    case 4: launch_n<4>(op, *plan, dst, src, add, which, stream); break;
+    case 2: launch_n<2>(op, *plan, dst, src, add, which, stream, list, n_list); break;
+    case 3: if (plan->pipe) launch_pipe<3>(op, *plan, dst, src, add, which, stream, list, n_list); else launch_n<3>(op, *plan, dst, src, add, which, stream, list, n_list); break;
+    case 4: launch_n<4>(op, *plan, dst, src, add, which, stream, list, n_list); break;
     case 5: {
       // warp-specialised kernel for full launches of an unpartitioned mesh and for the interior launch of a partition (no ghost
       // reads by construction: the very kernel instantiation that is verified on one GPU); the batches that touch ghost cells
@@ -981,15 +1011,16 @@ void launch_vmult_cartesian_part(const DeviceOperator & op, double * dst, const 
       const bool with_ghosts = which == 2 || (which == 0 && op.n_ghost > 0);
       const bool ws_ok = plan->ws && variant >= 1 && (!with_ghosts || ws_ghost);
       if (ws_ok)
-        ws_launch(op, plan->ws, dst, src, add, which == 0 ? nullptr : (which == 1 ? plan->d_interior : plan->d_boundary),
-                  which == 0 ? plan->n_batches : (which == 1 ? plan->n_interior : plan->n_boundary), plan->n_sm, variant == 2 ? 12 : (variant == 3 ? 4 : 8), with_ghosts, stream);
-      else if (plan->pipe) launch_pipe<5>(op, *plan, dst, src, add, which, stream);
-      else launch_n<5>(op, *plan, dst, src, add, which, stream);
+        ws_launch(op, plan->ws, dst, src, add, list ? list : (which == 0 ? nullptr : (which == 1 ? plan->d_interior : plan->d_boundary)),
+                  list ? n_list : (which == 0 ? plan->n_batches : (which == 1 ? plan->n_interior : plan->n_boundary)), plan->n_sm,
+                  variant == 2 ? 12 : (variant == 3 ? 4 : 8), with_ghosts, stream);
+      else if (plan->pipe) launch_pipe<5>(op, *plan, dst, src, add, which, stream, list, n_list);
+      else launch_n<5>(op, *plan, dst, src, add, which, stream, list, n_list);
       break;
     }
-    case 6: launch_n<6>(op, *plan, dst, src, add, which, stream); break;
-    case 7: launch_n<7>(op, *plan, dst, src, add, which, stream); break;
-    case 8: launch_n<8>(op, *plan, dst, src, add, which, stream); break;
+    case 6: launch_n<6>(op, *plan, dst, src, add, which, stream, list, n_list); break;
+    case 7: launch_n<7>(op, *plan, dst, src, add, which, stream, list, n_list); break;
+    case 8: launch_n<8>(op, *plan, dst, src, add, which, stream, list, n_list); break;
     default: throw std::runtime_error("Cartesian fast path supports degrees 1..7");
   }
 }

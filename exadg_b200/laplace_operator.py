@@ -146,6 +146,14 @@ class LaplaceOperator:
                 raise ExaDGError("vmult_host expects contiguous host tensors of the local size")
         _check(_lib().exadg_b200_vmult_host(self._h, C.c_void_p(dst_host.data_ptr()), C.c_void_p(src_host.data_ptr())))
 
+    def vmult_host_pipelined(self, dst_host, src_host):
+        """Same result as vmult_host with upload, operator and download overlapped chunk by chunk inside the call (unpartitioned
+        operators only; pinned host tensors)."""
+        for t in (dst_host, src_host):
+            if t.is_cuda or t.numel() != self._n_local or not t.is_contiguous():
+                raise ExaDGError("vmult_host_pipelined expects contiguous host tensors of the local size")
+        _check(_lib().exadg_b200_vmult_host_pipelined(self._h, C.c_void_p(dst_host.data_ptr()), C.c_void_p(src_host.data_ptr())))
+
     def calculate_diagonal(self, diagonal):
         _check(_lib().exadg_b200_calculate_diagonal(self._h, _ptr(diagonal, self._n_local)))
         self.synchronize_with_torch()
@@ -346,6 +354,22 @@ def cartesian_kernel(variant=-1):
     producer depth 8 / 12; -1 only queries.
     Process-wide tuning switch (no reference counterpart); returns the previous value."""
     return _lib().exadg_b200_cartesian_kernel(int(variant))
+
+
+def host_pipeline_plan(n_subdivisions, n_refinements, cells_per_chunk=0, boundary=(0,) * 6, rank=0, world=1):
+    """Host-only view (no GPU needed) of the chunk plan of vmult_host_pipelined on a hypercube grid: dict with n_chunks, upload_order,
+    compute_order, ready_chunk (per chunk: the chunk whose upload makes it computable) and the modelled duration of one call in units
+    of a one-direction transfer (2 = no overlap)."""
+    L = _lib()
+    d = _desc(1, n_subdivisions, n_refinements, 1, 0.0, 2, boundary, 1.0, rank, world, False)
+    n, model = C.c_int32(), C.c_double()
+    _check(L.exadg_b200_host_pipeline_plan(C.byref(d), int(cells_per_chunk), C.byref(n), None, None, None, C.byref(model)))
+    out = {k: np.zeros(n.value, dtype=np.int32) for k in ("upload_order", "compute_order", "ready_chunk")}
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))  # noqa: E731
+    _check(L.exadg_b200_host_pipeline_plan(C.byref(d), int(cells_per_chunk), C.byref(n), p(out["upload_order"]), p(out["compute_order"]), p(out["ready_chunk"]),
+                                           C.byref(model)))
+    out["n_chunks"], out["model"] = n.value, model.value
+    return out
 
 
 class PartitionPlan:

@@ -99,6 +99,16 @@ int exadg_b200_vmult_add(exadg_b200_operator *op, double *dst, const double *src
 /* same through host buffers (H2D copy, vmult, D2H copy) */
 int exadg_b200_vmult_host(exadg_b200_operator *op, double *dst_host, const double *src_host);
 
+/* same result, but upload, operator and download overlap chunk by chunk inside the call (PCIe is full duplex): a chunk of cells
+ * is applied once the chunks holding its face neighbours have arrived.  Unpartitioned operators only (returns
+ * EXADG_B200_ERR_UNSUPPORTED otherwise); the host buffers should be pinned. */
+int exadg_b200_vmult_host_pipelined(exadg_b200_operator *op, double *dst_host, const double *src_host);
+/* host-only view of the chunk plan of exadg_b200_vmult_host_pipelined (no CUDA call; CPU tests): n_chunks with null arrays, then
+ * upload order, compute order and, per chunk, the chunk whose upload makes it computable; model = duration of one call in units
+ * of a one-direction transfer (2 = no overlap). cells_per_chunk <= 0 selects the library's default for 24-cell batches. */
+int exadg_b200_host_pipeline_plan(const exadg_b200_hypercube_desc *desc, int64_t cells_per_chunk, int32_t *n_chunks, int32_t *upload_order,
+                                  int32_t *compute_order, int32_t *ready_chunk, double *model);
+
 /* OperatorBase::calculate_diagonal / add_diagonal / calculate_inverse_diagonal
  * (operator_base.cpp:608-646, 249-262; invert_diagonal.h:35-46) */
 int exadg_b200_calculate_diagonal(exadg_b200_operator *op, double *diagonal);

@@ -1,0 +1,49 @@
+"""Host logic of the pipelined host-buffer vmult (exadg_b200_vmult_host_pipelined, csrc/host_pipeline.hpp) on the CPU: the chunk plan
+must never apply a chunk before every chunk holding a face neighbour of its cells has been uploaded, and on the benchmark mesh it
+must overlap most of the two PCIe directions (model: duration of one call in units of a one-direction transfer; 2 = no overlap)."""
+import numpy as np
+import pytest
+
+import exadg_b200
+from exadg_b200.laplace_operator import PartitionPlan
+
+
+def check_plan(n_sub, refine, cells_per_chunk, boundary=(0,) * 6):
+    P = exadg_b200.host_pipeline_plan(n_sub, refine, cells_per_chunk, boundary)
+    K = P["n_chunks"]
+    nb = PartitionPlan(n_sub, refine, 0, 1, boundary).neighbors  # [cells][6], -1 on the boundary
+    n_cells = nb.shape[0]
+    assert K == -(-n_cells // cells_per_chunk)
+    assert sorted(P["upload_order"]) == list(range(K)) and sorted(P["compute_order"]) == list(range(K))
+    pos = np.empty(K, dtype=np.int64)
+    pos[P["upload_order"]] = np.arange(K)
+    chunk = np.arange(n_cells) // cells_per_chunk
+    for c in range(K):
+        cells = np.nonzero(chunk == c)[0]
+        neigh = nb[cells].ravel()
+        deps = set(chunk[neigh[neigh >= 0]].tolist()) | {c}
+        ready = P["ready_chunk"][c]
+        assert ready in deps
+        assert max(pos[d] for d in deps) == pos[ready], "chunk %d would be applied before its neighbours have arrived" % c
+    ready_pos = pos[P["ready_chunk"][P["compute_order"]]]
+    assert np.all(np.diff(ready_pos) >= 0), "compute order follows the upload order"
+    return P
+
+
+@pytest.mark.parametrize("n_sub,refine,cpc", [(3, 2, 48), (1, 3, 24), (5, 1, 72), (3, 2, 1536)])
+def test_chunks_are_applied_only_after_their_neighbours_arrived(n_sub, refine, cpc):
+    check_plan(n_sub, refine, cpc)
+
+
+def test_plan_with_boundaries():
+    check_plan(3, 1, 24, (1, 2, 1, 1, 0, 0))
+
+
+def test_partitioned_operators_keep_the_sequential_path():
+    assert exadg_b200.host_pipeline_plan(3, 2, 48, rank=0, world=2)["n_chunks"] == 0
+
+
+def test_benchmark_mesh_overlaps_most_of_the_two_transfers():
+    P = exadg_b200.host_pipeline_plan(3, 5)  # 96^3 cells, library default: 64 batches of 24 cells per chunk
+    assert P["n_chunks"] == 576
+    assert P["model"] < 1.3
