@@ -67,7 +67,7 @@ def probe_pipelined_e2e(degree, n_sub, refine, deformation):
         "assert (h_dst.cuda() - dst).abs().max().item() == 0.0\n"
         "print('PIPELINED_OK')\n" % (ROOT, degree, n_sub, refine, deformation))
     try:
-        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=240)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=150)
     except Exception:
         return False
     return r.returncode == 0 and "PIPELINED_OK" in r.stdout

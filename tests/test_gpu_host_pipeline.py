@@ -35,5 +35,5 @@ print("PIPELINED_OK")
 
 @pytest.mark.xfail(strict=False, reason="stream choreography not yet seen on hardware (written after the round-1 GPU budget was spent)")
 def test_pipelined_host_vmult_is_bitwise_the_device_vmult():
-    r = subprocess.run([sys.executable, "-c", CHILD], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([sys.executable, "-c", CHILD], capture_output=True, text=True, timeout=150)
     assert r.returncode == 0 and "PIPELINED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
