@@ -47,6 +47,40 @@ def ncu_traffic(workload_key):
     return None
 
 
+def tune_k4_kernel(n_sub, refine):
+    """Times the k=4 kernels of the affine fast path side by side in a child process (build/ws_tournament, C ABI only) and returns
+    (chosen variant, {variant: ms}): the fastest variant whose vmult and vmult_add agree with the pipelined kernel (which the GPU
+    tests pin to the oracle) to 1e-14, the default unless another one is at least 2 % faster. None if the tool is not built or fails."""
+    exe = os.path.join(ROOT, "build", "ws_tournament")
+    if not os.path.exists(exe):
+        return None
+    try:
+        r = subprocess.run([exe, "-1", str(n_sub), str(refine), "30"], capture_output=True, text=True, timeout=90)
+    except Exception:
+        return None
+    if r.returncode != 0 or "TOURNAMENT DONE" not in r.stdout:
+        return None
+    ms, worst = {}, {}
+    for line in r.stdout.splitlines():
+        w = line.split()
+        try:
+            if line.startswith("variant ") and "ms/vmult" in line:
+                ms[int(w[1].rstrip(":"))] = float(w[2])
+            elif "rel l2 (variant" in line:
+                v = int(line.split("(variant")[1].split()[0].rstrip(",)"))
+                worst[v] = max(worst.get(v, 0.0), float(w[-1]))
+        except (ValueError, IndexError):
+            return None
+    default = 1
+    if default not in ms or worst.get(default, 1.0) > 1e-14:
+        return None
+    chosen = default
+    for v, t in ms.items():
+        if v != 0 and worst.get(v, 1.0) <= 1e-14 and t < 0.98 * ms[chosen]:
+            chosen = v
+    return chosen, ms
+
+
 def probe_pipelined_e2e(degree, n_sub, refine, deformation):
     """Child process: vmult_host_pipelined on the same workload must reproduce the device vmult bit for bit (twice: events are reused).
     A fault or a hang in the child cannot take the benchmark down; the parent keeps the sequential entry point unless this succeeds."""
@@ -242,6 +276,14 @@ def run_gpu(args):
     else:
         n_sub, refine = GRIDS.get(world, (3, 5))
     deformation = 0.1 if args.mesh == "curvilinear" else 0.0
+    kernel_selection = None
+    if world == 1 and degree == 4 and deformation == 0.0 and not args.no_tune and "EXADG_B200_CART_KERNEL" not in os.environ:
+        # the k=4 fast path has several validated kernels; pick the fastest on this box before anything is allocated here
+        tuned = tune_k4_kernel(n_sub, refine)
+        if tuned is not None:
+            exadg_b200.cartesian_kernel(tuned[0])
+            kernel_selection = {"chosen_variant": tuned[0], "ms_per_vmult_by_variant": tuned[1],
+                                "variants": "0 pipelined, 1 warp-specialised (default), 2 deeper producers, 3 four producer warps"}
     op = exadg_b200.LaplaceOperator.hypercube(degree, n_sub, refine, 1, deformation, 2, (0,) * 6, 1.0, rank=rank, world=world)
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -351,7 +393,9 @@ def run_gpu(args):
             kernel = "cartesian"
             if degree == 4:
                 variant = exadg_b200.cartesian_kernel()
-                kernel = ("warp-specialised vmult_cartesian_ws_kernel<5,%d>" % (12 if variant == 2 else 8)) if variant >= 1 else "pipelined vmult_cartesian_pipe_kernel<5>"
+                names = {1: "warp-specialised vmult_cartesian_ws_kernel<5,8,2 producer warps>", 2: "warp-specialised vmult_cartesian_ws_kernel<5,12,2 producer warps>",
+                         3: "warp-specialised vmult_cartesian_ws_kernel<5,4,4 producer warps, setmaxnreg>"}
+                kernel = names.get(variant, names[1]) if variant >= 1 else "pipelined vmult_cartesian_pipe_kernel<5>"
                 if variant >= 1:
                     key += "_ws"
                     if world > 1:
@@ -362,7 +406,7 @@ def run_gpu(args):
                "config": {"workload": "SIPG Laplace vmult, FE_DGQ(%d), Gauss(%d), periodic %s box, %d^3 cells, %d DoFs, src uniform(-1,1)"
                                       % (degree, degree + 1, "Cartesian" if deformation == 0.0 else "sine-deformed (trilinear)", n_sub << refine, n_global),
                           "l2_policy": "inputs larger than L2 (%.0f MB per vector per GPU)" % (n_local * 8 / 1e6),
-                          "kernel_path": "cartesian" if op.is_cartesian_path else "general", "kernel": kernel, "partition": "p4est-style contiguous Morton ranges, %d rank(s)" % world,
+                          "kernel_path": "cartesian" if op.is_cartesian_path else "general", "kernel": kernel, "kernel_selection": kernel_selection, "partition": "p4est-style contiguous Morton ranges, %d rank(s)" % world,
                           "halo": "none" if world == 1 else ("NVLink peer-memory stores (CUDA IPC), overlapped with interior cells" if args.halo == "p2p" else "NCCL send/recv, overlapped with interior cells")},
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(key),
                             "peak_source": peak_src, "algorithmic_bytes_per_dof": b_alg, "dofs_per_launch": n_global // world},
@@ -393,6 +437,7 @@ def main():
     ap.add_argument("--mode", default="vmult", choices=["vmult", "cg", "chebyshev"], help="vmult = the headline metric; cg / chebyshev = secondary lines for the callers")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="ghost import transport for N>1")
     ap.add_argument("--e2e-api", default="auto", choices=["auto", "plain"], help="auto: also try the pipelined host-buffer entry point for the e2e figure (validated in a child process first)")
+    ap.add_argument("--no-tune", action="store_true", help="k=4: keep the default kernel instead of timing the validated variants in a child process first")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--fp64-peak", action="store_true", help="also report measured DFMA / DMMA rates")
