@@ -45,6 +45,8 @@ def lib():
         L.orc_vmult.argtypes = [C.c_void_p, dp, dp]
         L.orc_vmult_add.argtypes = [C.c_void_p, dp, dp]
         L.orc_vmult_cellwise.argtypes = [C.c_void_p, dp, dp, C.c_int]
+        L.orc_vmult_fast.restype = C.c_int
+        L.orc_vmult_fast.argtypes = [C.c_void_p, dp, dp, C.c_int]
         L.orc_max_threads.restype = C.c_int
         L.orc_calculate_diagonal.argtypes = [C.c_void_p, dp]
         L.orc_calculate_inverse_diagonal.argtypes = [C.c_void_p, dp]
@@ -107,6 +109,13 @@ class OracleOperator:
     def vmult_cellwise(self, src, n_threads=0, dst=None):
         dst = self._vec() if dst is None else dst
         lib().orc_vmult_cellwise(self.h, _p(dst), _p(np.ascontiguousarray(src, dtype=np.float64)), n_threads)
+        return dst
+
+    def vmult_fast(self, src, n_threads=0, dst=None):
+        """Vectorised CPU baseline (8 cells per SIMD batch, compile-time degree; uniform boxes with interior faces only, otherwise it
+        falls back to vmult_cellwise).  self.fast_path_used tells which of the two ran."""
+        dst = self._vec() if dst is None else dst
+        self.fast_path_used = bool(lib().orc_vmult_fast(self.h, _p(dst), _p(np.ascontiguousarray(src, dtype=np.float64)), n_threads))
         return dst
 
     def diagonal(self):

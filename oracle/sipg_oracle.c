@@ -6,7 +6,8 @@
  * the callers around it (diagonal, dealii::SolverCG, dealii::PreconditionChebyshev,
  * rhs / L2 error of applications/poisson/sine).  Only tests/, __graft_entry__.smoke()
  * and bench.py's cpu_baseline / --impl reference legs may load this library; the
- * product (exadg_b200/) never links, imports or calls it.
+ * product (exadg_b200/) never links, imports or calls it.  The timed CPU baseline is the
+ * vectorised variant in sipg_fast.inc (orc_vmult_fast), checked against the functions here.
  *
  * Parity pin: vmult itself is pinned by no reference fixture ("parity unpinned" at the
  * operator level); the oracle as a whole (cell + interior-face + Dirichlet + Neumann
@@ -271,6 +272,8 @@ typedef struct {
   /* unique interior faces (face-centric loop like MatrixFree::loop) */
   long n_faces; long *face_m, *face_p; unsigned char *face_fm, *face_fp;
   long n_bfaces; long *bface_c; unsigned char *bface_f;
+  /* vectorised baseline (sipg_fast.inc): applicability and cell sizes of the uniform box */
+  int fast_checked, fast_ok; double fast_h[3];
 } Op;
 
 static double det3(const double J[9])
@@ -1011,3 +1014,6 @@ void orc_get_basis(int degree, double *xn, double *xq, double *w, double *S, dou
   memcpy(S, b.S, sizeof(double) * n * n); memcpy(D, b.D, sizeof(double) * n * n);
   for (int s = 0; s < 2; ++s) { memcpy(fv + s * n, b.fv[s], sizeof(double) * n); memcpy(fd + s * n, b.fd[s], sizeof(double) * n); }
 }
+
+/* vectorised CPU baseline for uniform boxes (bench.py's cpu_baseline / --impl reference legs) */
+#include "sipg_fast.inc"
