@@ -17,8 +17,8 @@ PERIODIC, DIRICHLET, NEUMANN = 0, 1, 2
 
 def build(force=False):
     """Compile liboracle.so with the committed Makefile (gcc only)."""
-    src = os.path.join(_HERE, "sipg_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("sipg_oracle.c", "sipg_fast.inc", "Makefile")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _LIB_PATH
 
