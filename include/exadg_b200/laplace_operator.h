@@ -74,6 +74,12 @@ public:
   void apply_add(VectorType & dst, VectorType const & src) const { vmult_add(dst, src); }
   void vmult_interface_down(VectorType & dst, VectorType const & src) const { vmult(dst, src); }
   void vmult_add_interface_up(VectorType & dst, VectorType const & src) const { vmult_add(dst, src); }
+  // host vectors (a binding that keeps LinearAlgebra::distributed::Vector on the host): upload, vmult, download inside the call;
+  // overlap = true: the three overlap chunk by chunk (unpartitioned operators, pinned host memory)
+  void vmult_host(double * dst, double const * src, bool overlap = false) const
+  {
+    check(overlap ? exadg_b200_vmult_host_pipelined(op, dst, src) : exadg_b200_vmult_host(op, dst, src));
+  }
 
   std::int64_t m() const { return n(); }
   std::int64_t n() const { return exadg_b200_n(op); }
