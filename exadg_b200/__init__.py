@@ -32,6 +32,8 @@ EXPORTED_SYMBOLS = [
     "exadg_b200_halo_send_list", "exadg_b200_ghost_global_ids", "exadg_b200_ghost_buffer", "exadg_b200_halo_pack",
     "exadg_b200_fp64_peak", "exadg_b200_cartesian_kernel", "exadg_b200_plan_create", "exadg_b200_plan_destroy", "exadg_b200_plan_sizes", "exadg_b200_plan_peer",
     "exadg_b200_plan_tables", "exadg_b200_p2p_export", "exadg_b200_p2p_connect",
+    "exadg_b200_wait_stream", "exadg_b200_stream_wait_operator", "exadg_b200_operator_is_singular", "exadg_b200_degree",
+    "exadg_b200_set_kernel_variant", "exadg_b200_get_kernel_variant",
 ]
 
 
@@ -45,7 +47,7 @@ class MeshDesc(C.Structure):
     _fields_ = [("degree", C.c_int), ("mapping_degree", C.c_int), ("n_cells_owned", C.c_int64), ("n_cells_ghost", C.c_int64),
                 ("mapping_points", C.POINTER(C.c_double)), ("neighbors", C.POINTER(C.c_int32)), ("neighbor_face", C.POINTER(C.c_uint8)),
                 ("boundary_type", C.POINTER(C.c_uint8)), ("ip_factor", C.c_double), ("n_global_cells", C.c_int64),
-                ("global_cell_offset", C.c_int64), ("force_general", C.c_int)]
+                ("global_cell_offset", C.c_int64), ("force_general", C.c_int), ("operator_is_singular", C.c_int)]
 
 
 _lib = None
@@ -67,6 +69,12 @@ def load_library():
     L.exadg_b200_destroy.argtypes = [vp]
     L.exadg_b200_set_stream.argtypes = [vp, vp]
     L.exadg_b200_synchronize.argtypes = [vp]
+    L.exadg_b200_wait_stream.argtypes = [vp, vp]
+    L.exadg_b200_stream_wait_operator.argtypes = [vp, vp]
+    L.exadg_b200_operator_is_singular.argtypes = [vp]
+    L.exadg_b200_degree.argtypes = [vp]
+    L.exadg_b200_set_kernel_variant.argtypes = [vp, C.c_int]
+    L.exadg_b200_get_kernel_variant.argtypes = [vp]
     for name in ("exadg_b200_n", "exadg_b200_local_size", "exadg_b200_n_cells_owned", "exadg_b200_n_cells_ghost"):
         getattr(L, name).restype = i64
         getattr(L, name).argtypes = [vp]

@@ -122,7 +122,7 @@ struct exadg_b200_operator
   HostMesh mesh; // connectivity kept for the halo plan (mapping points dropped after setup)
   cudaStream_t stream = nullptr, comm_stream = nullptr;
   bool own_stream = true;
-  cudaEvent_t ev_packed = nullptr, ev_halo = nullptr;
+  cudaEvent_t ev_packed = nullptr, ev_halo = nullptr, ev_order = nullptr;
   Reducer red;
   int64_t launches = 0;
   int64_t n_local = 0; // locally owned DoFs
@@ -169,10 +169,21 @@ int guarded(F && f)
   catch (const std::exception & e) { g_last_error = e.what(); return std::string(e.what()).find("CUDA") != std::string::npos ? EXADG_B200_ERR_CUDA : EXADG_B200_ERR_UNSUPPORTED; }
 }
 
+// exadg_b200_create with n_cells_ghost > 0: the partition (ghost import, global dot products) is owned by the caller; the solver
+// and smoother entry points of the library cannot provide either and refuse instead of returning rank-local results
+void require_self_contained(const exadg_b200_operator * op, const char * what);
+
 void check_ptr(const void * p, const char * name)
 {
   if (!p) throw std::invalid_argument(std::string(name) + " is null");
   if ((reinterpret_cast<uintptr_t>(p) & 15) != 0) throw std::invalid_argument(std::string(name) + " must be 16-byte aligned");
+}
+
+void require_self_contained(const exadg_b200_operator * op, const char * what)
+{
+  if (op->dev.n_ghost > 0 && op->mesh.peers.empty())
+    throw std::runtime_error(std::string(what) + ": this operator has ghost cells filled by the caller (exadg_b200_create with n_cells_ghost > 0); "
+                             "the library cannot refresh them or reduce over the caller's ranks - drive vmult from the caller's solver instead");
 }
 
 void allreduce(exadg_b200_operator * op, double * dev_scalars, int count)
@@ -210,6 +221,7 @@ void finish_setup(exadg_b200_operator * op, double ip_factor, bool force_general
   }
   CUDA_CHECK(cudaEventCreateWithFlags(&op->ev_packed, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventCreateWithFlags(&op->ev_halo, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventCreateWithFlags(&op->ev_order, cudaEventDisableTiming));
   reducer_init(op->red);
   setup_geometry(D, M, ip_factor, op->stream);
   // halo plan on the device + interior/boundary split for overlap
@@ -523,6 +535,7 @@ int exadg_b200_create(const exadg_b200_mesh_desc * desc, exadg_b200_operator ** 
     M.mapping_degree = desc->mapping_degree; M.n_owned = desc->n_cells_owned; M.n_ghost = desc->n_cells_ghost;
     M.n_global_cells = desc->n_global_cells > 0 ? desc->n_global_cells : desc->n_cells_owned;
     M.global_offset = desc->global_cell_offset;
+    M.singular = desc->operator_is_singular < 0 ? -1 : (desc->operator_is_singular ? 1 : 0);
     const int64_t nloc = M.n_owned + M.n_ghost;
     const int np3 = (M.mapping_degree + 1) * (M.mapping_degree + 1) * (M.mapping_degree + 1);
     M.xmap.assign(desc->mapping_points, desc->mapping_points + (size_t)nloc * np3 * 3);
@@ -568,6 +581,7 @@ int exadg_b200_destroy(exadg_b200_operator * op)
   if (op->own_comm && op->comm) nccl().CommDestroy(op->comm);
   if (op->ev_packed) cudaEventDestroy(op->ev_packed);
   if (op->ev_halo) cudaEventDestroy(op->ev_halo);
+  if (op->ev_order) cudaEventDestroy(op->ev_order);
   if (op->own_stream && op->stream) cudaStreamDestroy(op->stream);
   if (op->comm_stream) cudaStreamDestroy(op->comm_stream);
   delete op;
@@ -583,7 +597,38 @@ int exadg_b200_set_stream(exadg_b200_operator * op, void * cuda_stream)
     return EXADG_B200_OK;
   });
 }
-int exadg_b200_synchronize(exadg_b200_operator * op) { return guarded([&]() { CUDA_CHECK(cudaStreamSynchronize(op->stream)); return EXADG_B200_OK; }); }
+int exadg_b200_synchronize(exadg_b200_operator * op) { return guarded([&]() { if (!op) throw std::invalid_argument("null operator"); CUDA_CHECK(cudaStreamSynchronize(op->stream)); return EXADG_B200_OK; }); }
+int exadg_b200_wait_stream(exadg_b200_operator * op, void * cuda_stream)
+{
+  return guarded([&]() {
+    if (!op) throw std::invalid_argument("null operator");
+    cudaStream_t other = (cudaStream_t)cuda_stream;
+    if (other == op->stream) return EXADG_B200_OK;
+    CUDA_CHECK(cudaEventRecord(op->ev_order, other));
+    CUDA_CHECK(cudaStreamWaitEvent(op->stream, op->ev_order, 0));
+    return EXADG_B200_OK;
+  });
+}
+int exadg_b200_stream_wait_operator(exadg_b200_operator * op, void * cuda_stream)
+{
+  return guarded([&]() {
+    if (!op) throw std::invalid_argument("null operator");
+    cudaStream_t other = (cudaStream_t)cuda_stream;
+    if (other == op->stream) return EXADG_B200_OK;
+    CUDA_CHECK(cudaEventRecord(op->ev_order, op->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(other, op->ev_order, 0));
+    return EXADG_B200_OK;
+  });
+}
+int exadg_b200_operator_is_singular(const exadg_b200_operator * op) { return (op && op->mesh.pure_neumann_or_periodic()) ? 1 : 0; }
+int exadg_b200_degree(const exadg_b200_operator * op) { return op ? op->dev.degree : -1; }
+int exadg_b200_set_kernel_variant(exadg_b200_operator * op, int variant)
+{
+  if (!op || variant < -1 || variant > 15) return EXADG_B200_ERR_ARG;
+  op->dev.cart_variant = variant;
+  return EXADG_B200_OK;
+}
+int exadg_b200_get_kernel_variant(const exadg_b200_operator * op) { return op ? (op->dev.cart_variant >= 0 ? op->dev.cart_variant : cartesian_kernel_variant(-1)) : -1; }
 
 int64_t exadg_b200_n(const exadg_b200_operator * op) { return op ? op->dev.n_global_dofs : -1; }
 int64_t exadg_b200_local_size(const exadg_b200_operator * op) { return op ? op->n_local : -1; }
@@ -598,7 +643,7 @@ int exadg_b200_initialize_dof_vector(const exadg_b200_operator * op, double ** v
     if (!op || !vec) throw std::invalid_argument("null argument");
     const size_t bytes = (size_t)std::max<int64_t>(op->n_local, 1) * sizeof(double);
     CUDA_CHECK(cudaMalloc(vec, bytes));
-    CUDA_CHECK(cudaMemset(*vec, 0, bytes));
+    CUDA_CHECK(cudaMemsetAsync(*vec, 0, bytes, op->stream)); // ordered before the kernels of this operator that write the vector
     return EXADG_B200_OK;
   });
 }
@@ -742,6 +787,7 @@ int exadg_b200_cg_solve(exadg_b200_operator * op, double * x, const double * b, 
 {
   return guarded([&]() {
     if (!op) throw std::invalid_argument("null operator");
+    require_self_contained(op, "exadg_b200_cg_solve");
     check_ptr(x, "x"); check_ptr(b, "b");
     double * inv_diag = nullptr;
     if (preconditioner == EXADG_B200_PRECOND_POINT_JACOBI) {
@@ -759,6 +805,7 @@ int exadg_b200_chebyshev_create(exadg_b200_operator * op, int degree, double smo
 {
   return guarded([&]() {
     if (!op || !out) throw std::invalid_argument("null argument");
+    require_self_contained(op, "exadg_b200_chebyshev_create");
     std::unique_ptr<exadg_b200_chebyshev> ch(new exadg_b200_chebyshev);
     ch->op = op; ch->degree = degree; ch->smoothing_range = smoothing_range; ch->eig_cg_n_iterations = eig_cg_n_iterations;
     const int64_t n = op->n_local; const size_t bytes = (size_t)std::max<int64_t>(n, 1) * sizeof(double);

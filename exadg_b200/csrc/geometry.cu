@@ -8,6 +8,10 @@
 // so that  grad_xi-test . (G grad_xi u)  is the cell integrand (laplace_operator.cpp:129-137) and
 // dn u = a . grad_xi u is get_normal_derivative (laplace_operator.cpp:149-150).
 #include <cstdio>
+#include <mutex>
+#include <set>
+#include <stdexcept>
+#include <utility>
 
 #include "operator.cuh"
 
@@ -16,6 +20,16 @@ namespace exadg_b200
 void cuda_check(cudaError_t e, const char * what)
 {
   if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what);
+}
+
+bool first_use_on_device(const void * key)
+{
+  static std::mutex mutex;
+  static std::set<std::pair<const void *, int>> seen;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mutex);
+  return seen.insert(std::make_pair(key, dev)).second;
 }
 
 namespace

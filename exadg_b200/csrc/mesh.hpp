@@ -47,6 +47,7 @@ struct HostMesh
   int rank = 0, world = 1;
   std::vector<PeerPlan> peers;
   std::vector<int64_t> ghost_global; // global cell id of each ghost
+  int singular = -1; // 1: no Dirichlet face anywhere in the domain (OperatorBaseData::operator_is_singular, operator_base.h:59-103), 0: some, -1: derive from the local cells
 
   // unique faces touching owned cells
   int64_t n_faces = 0;
@@ -89,6 +90,14 @@ struct HostMesh
   {
     for (size_t i = 0; i < bt.size(); ++i) if (bt[i] != BT_INTERIOR) return false;
     for (int64_t i = 0; i < n_owned * 6; ++i) if (nb[i] < 0) return false;
+    return true;
+  }
+
+  // constants lie in the kernel of the operator: periodic / Neumann faces only (operator_is_singular of the reference's operator data)
+  bool pure_neumann_or_periodic() const
+  {
+    if (singular >= 0) return singular == 1;
+    for (size_t i = 0; i < bt.size(); ++i) if (bt[i] == BT_DIRICHLET) return false;
     return true;
   }
 
@@ -152,6 +161,8 @@ inline HostMesh make_hypercube(const HypercubeDesc & d)
   HostMesh M;
   M.mapping_degree = d.mapping_degree; M.rank = d.rank; M.world = d.world;
   M.n_global_cells = N;
+  M.singular = 1;
+  for (int f = 0; f < 6; ++f) if (d.bc[f] == BT_DIRICHLET) M.singular = 0;
   auto first_of = [&](int r) { return (int64_t)((__int128)N * r / d.world); };
   auto owner_of = [&](int64_t g) {
     int r = (int)(((__int128)g * d.world) / N);

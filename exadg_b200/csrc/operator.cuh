@@ -34,6 +34,7 @@ struct DeviceOperator
   double h[3] = {0, 0, 0};
   double tau_hat = 0;           // tau_K (k+1)^2 IP_factor of the uniform box (times h_d = tau_hat_d)
   void * cart_plan = nullptr;   // batch plan of the Cartesian kernel (vmult_cartesian.cu)
+  int cart_variant = -1;        // n = 5 kernel of this operator (-1: the process-wide default, cartesian_kernel_variant)
 };
 
 // ---- geometry.cu ----
@@ -68,6 +69,9 @@ void ws_launch(const DeviceOperator & op, const void * plan, double * dst, const
 void fp64_peak(double * dfma_tflops, double * dmma_tflops);
 
 void cuda_check(cudaError_t e, const char * what);
+// true the first time it is called for (key, current device): per-device one-time configuration (cudaFuncSetAttribute applies to
+// the current device only)
+bool first_use_on_device(const void * key);
 #define CUDA_CHECK(x) ::exadg_b200::cuda_check((x), #x)
 
 } // namespace exadg_b200

@@ -768,7 +768,7 @@ struct CartPlan
   size_t smem = 0;
   std::vector<char> tables; // CartTables<n> of this operator (depends on h and tau)
   // pipelined kernel (n = 5)
-  bool pipe = false; int HL = 0, HD = 0, n_sm = 148; int4 * d_cnt4 = nullptr;
+  bool pipe = false; int HL = 0, HD = 0, n_sm = 148; int4 * d_cnt4 = nullptr; int pipe_ctas_per_sm = 1;
   // warp-specialised kernel (n = 5, same 24-cell batches): vmult_cartesian_ws.cu
   void * ws = nullptr;
 };
@@ -821,8 +821,8 @@ void launch_n(const DeviceOperator & op, const CartPlan & plan, double * dst, co
 {
   constexpr int B = CartCfg<N>::B;
   const CartTables<N> & T = *reinterpret_cast<const CartTables<N> *>(plan.tables.data());
-  static bool configured = false;
-  if (!configured) { CUDA_CHECK(cudaFuncSetAttribute(vmult_cartesian_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)); configured = true; }
+  if (first_use_on_device((const void *)vmult_cartesian_kernel<N>))
+    CUDA_CHECK(cudaFuncSetAttribute(vmult_cartesian_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
   CartArgs A;
   A.nb = op.nb; A.halo = plan.d_halo; A.halo_cnt = plan.d_cnt; A.src = src; A.ghost = op.ghost; A.dst = dst;
   A.n_owned = op.n_owned; A.H = plan.H; A.add = add ? 1 : 0;
@@ -838,12 +838,9 @@ void launch_pipe(const DeviceOperator & op, const CartPlan & plan, double * dst,
                  int n_list = 0)
 {
   const CartTables<N> & T = *reinterpret_cast<const CartTables<N> *>(plan.tables.data());
-  static int ctas_per_sm = 0;
-  if (ctas_per_sm == 0) {
+  if (first_use_on_device((const void *)vmult_cartesian_pipe_kernel<N>))
     CUDA_CHECK(cudaFuncSetAttribute(vmult_cartesian_pipe_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, vmult_cartesian_pipe_kernel<N>, PipeCfg<N>::NT, plan.smem));
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-  }
+  const int ctas_per_sm = plan.pipe_ctas_per_sm; // occupancy of this plan's shared-memory size (plan_create)
   PipeArgs A;
   A.nb = op.nb; A.halo = plan.d_halo; A.halo_cnt = plan.d_cnt4; A.src = src; A.ghost = op.ghost; A.dst = dst;
   A.n_owned = op.n_owned; A.HL = plan.HL; A.HD = plan.HD; A.add = add ? 1 : 0;
@@ -922,6 +919,17 @@ static size_t plan_create(DeviceOperator & op, const HostMesh & mesh, bool allow
     P.smem = ((size_t)2 * P.B * N3p + (size_t)P.B * 2 * N2p + (size_t)2 * P.HD * N2p) * sizeof(double) + (size_t)2 * P.HL * sizeof(int2)
              + (size_t)P.B * 18 * sizeof(int) + 64 + 16;
     if (P.smem > 227 * 1024 - 1024 || P.HL > PipeCfg<5>::NT) { delete Pp; return plan_create(op, mesh, false); } // irregular batches: the 5-warp kernel has no such limits
+    {
+      int occ = 0;
+      if (N == 3) {
+        CUDA_CHECK(cudaFuncSetAttribute(vmult_cartesian_pipe_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vmult_cartesian_pipe_kernel<3>, PipeCfg<3>::NT, P.smem));
+      } else {
+        CUDA_CHECK(cudaFuncSetAttribute(vmult_cartesian_pipe_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vmult_cartesian_pipe_kernel<5>, PipeCfg<5>::NT, P.smem));
+      }
+      P.pipe_ctas_per_sm = std::max(occ, 1);
+    }
     CUDA_CHECK(cudaMalloc(&P.d_cnt4, cnt4.size() * sizeof(int4)));
     CUDA_CHECK(cudaMemcpy(P.d_cnt4, cnt4.data(), cnt4.size() * sizeof(int4), cudaMemcpyHostToDevice));
   }
@@ -1006,7 +1014,7 @@ static void launch_cart(const DeviceOperator & op, double * dst, const double * 
       // warp-specialised kernel for full launches of an unpartitioned mesh and for the interior launch of a partition (no ghost
       // reads by construction: the very kernel instantiation that is verified on one GPU); the batches that touch ghost cells
       // stay on the pipelined kernel until the ghost path of the warp-specialised kernel has run on >= 2 GPUs
-      const int variant = cartesian_kernel_variant(-1);
+      const int variant = op.cart_variant >= 0 ? op.cart_variant : cartesian_kernel_variant(-1);
       static const bool ws_ghost = getenv("EXADG_B200_WS_GHOST") != nullptr; // verification switch: ghost path of the warp-specialised kernel (tests/multi_gpu_check.py)
       const bool with_ghosts = which == 2 || (which == 0 && op.n_ghost > 0);
       const bool ws_ok = plan->ws && variant >= 1 && (!with_ghosts || ws_ghost);

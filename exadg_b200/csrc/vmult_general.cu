@@ -261,11 +261,8 @@ void launch_n(const DeviceOperator & op, double * dst, const double * src, bool 
   constexpr int NP = N | 1;
   static const GenTables<N> T = make_tables<N>();
   const size_t smem = (size_t)CPB * (4 * NP * N * N + 10 * N * N) * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
+  if (first_use_on_device((const void *)vmult_general_kernel<N, CPB, MODE>))
     CUDA_CHECK(cudaFuncSetAttribute(vmult_general_kernel<N, CPB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
   GenArgs A;
   A.nb = op.nb; A.face_id = op.face_id; A.face_info = op.face_info; A.cellG = op.cellG; A.faceG = op.faceG; A.tau_f = op.tau_f;
   A.src = src; A.ghost = op.ghost; A.dst = dst; A.cells = cells; A.n_items = n_items; A.n_owned = op.n_owned; A.add = add ? 1 : 0;

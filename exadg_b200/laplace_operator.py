@@ -90,6 +90,7 @@ class LaplaceOperator:
         d.neighbor_face = nf.ctypes.data_as(C.POINTER(C.c_uint8))
         d.boundary_type = bt.ctypes.data_as(C.POINTER(C.c_uint8))
         d.ip_factor, d.n_global_cells, d.global_cell_offset, d.force_general = ip_factor, nb.shape[0], 0, int(force_general)
+        d.operator_is_singular = -1  # derived from the boundary types (OperatorBaseData::operator_is_singular)
         h = C.c_void_p()
         _check(_lib().exadg_b200_create(C.byref(d), C.byref(h)))
         op = cls(h)
@@ -122,11 +123,19 @@ class LaplaceOperator:
         torch = _torch()
         return torch.zeros(self._n_local, dtype=torch.float64, device="cuda")
 
+    def _order_after_torch(self):
+        """The operator launches on its own non-blocking stream: order it behind the work torch has queued on its current stream
+        (the producers of src, the zero fill of dst) without a host synchronisation."""
+        torch = _torch()
+        _check(_lib().exadg_b200_wait_stream(self._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
     def vmult(self, dst, src):
+        self._order_after_torch()
         _check(_lib().exadg_b200_vmult(self._h, _ptr(dst, self._n_local), _ptr(src, self._n_local)))
         self.synchronize_with_torch()
 
     def vmult_add(self, dst, src):
+        self._order_after_torch()
         _check(_lib().exadg_b200_vmult_add(self._h, _ptr(dst, self._n_local), _ptr(src, self._n_local)))
         self.synchronize_with_torch()
 
@@ -137,6 +146,7 @@ class LaplaceOperator:
 
     def vmult_async(self, dst, src):
         """vmult without the trailing stream synchronisation (benchmark loop)."""
+        self._order_after_torch()
         _check(_lib().exadg_b200_vmult(self._h, _ptr(dst, self._n_local), _ptr(src, self._n_local)))
 
     def vmult_host(self, dst_host, src_host):
@@ -155,19 +165,46 @@ class LaplaceOperator:
         _check(_lib().exadg_b200_vmult_host_pipelined(self._h, C.c_void_p(dst_host.data_ptr()), C.c_void_p(src_host.data_ptr())))
 
     def calculate_diagonal(self, diagonal):
+        self._order_after_torch()
         _check(_lib().exadg_b200_calculate_diagonal(self._h, _ptr(diagonal, self._n_local)))
         self.synchronize_with_torch()
 
     def add_diagonal(self, diagonal):
+        self._order_after_torch()
         _check(_lib().exadg_b200_add_diagonal(self._h, _ptr(diagonal, self._n_local)))
         self.synchronize_with_torch()
 
     def calculate_inverse_diagonal(self, diagonal):
+        self._order_after_torch()
         _check(_lib().exadg_b200_calculate_inverse_diagonal(self._h, _ptr(diagonal, self._n_local)))
         self.synchronize_with_torch()
 
     def operator_is_singular(self):
-        return False
+        """operator_base.h:196: constants lie in the kernel (no Dirichlet face, e.g. the all-periodic throughput box)."""
+        return bool(_lib().exadg_b200_operator_is_singular(self._h))
+
+    # getters of operator_base.h:144-197 that have a meaning without deal.II objects
+    def get_level(self):
+        return 0xFFFFFFFF  # dealii::numbers::invalid_unsigned_int = the active level (operator_base.cpp:224-230)
+
+    def get_dof_index(self):
+        return 0
+
+    def get_quad_index(self):
+        return 0
+
+    def set_time(self, time):
+        self._time = float(time)  # the Laplace operator has no time-dependent coefficient; kept for the interface
+
+    def get_time(self):
+        return getattr(self, "_time", 0.0)
+
+    def set_kernel_variant(self, variant):
+        """Kernel of the affine fast path of THIS operator (see cartesian_kernel); -1 follows the process-wide default."""
+        _check(_lib().exadg_b200_set_kernel_variant(self._h, int(variant)))
+
+    def get_kernel_variant(self):
+        return _lib().exadg_b200_get_kernel_variant(self._h)
 
     def is_empty_locally(self):
         return self.n_cells_owned == 0
@@ -256,6 +293,7 @@ class JacobiPreconditioner:
         self.op.calculate_inverse_diagonal(self.inverse_diagonal)
 
     def vmult(self, dst, src):
+        self.op._order_after_torch()
         _check(_lib().exadg_b200_jacobi_vmult(self.op._h, _ptr(dst), _ptr(src), _ptr(self.inverse_diagonal)))
         self.op.synchronize()
 
@@ -266,6 +304,7 @@ class ChebyshevSmoother:
     def __init__(self, op, iterations=5, smoothing_range=20.0, iterations_eigenvalue_estimation=20):
         self.op = op
         h = C.c_void_p()
+        op._order_after_torch()
         _check(_lib().exadg_b200_chebyshev_create(op._h, iterations, smoothing_range, iterations_eigenvalue_estimation, C.byref(h)))
         self._h = h
         v = [C.c_double() for _ in range(4)]
@@ -285,10 +324,12 @@ class ChebyshevSmoother:
         self.theta, self.delta = theta, delta
 
     def vmult(self, dst, src):
+        self.op._order_after_torch()
         _check(_lib().exadg_b200_chebyshev_vmult(self._h, _ptr(dst), _ptr(src)))
         self.op.synchronize()
 
     def step(self, dst, src):
+        self.op._order_after_torch()
         _check(_lib().exadg_b200_chebyshev_step(self._h, _ptr(dst), _ptr(src)))
         self.op.synchronize()
 
@@ -324,6 +365,7 @@ class KrylovSolverCG:
             raise ExaDGError("unsupported preconditioner")
         hist = np.zeros(sd.max_iter + 1)
         it = C.c_int(0)
+        self.op._order_after_torch()
         status = _lib().exadg_b200_cg_solve(self.op._h, _ptr(dst), _ptr(rhs), kind, cheb, sd.abs_tol, sd.rel_tol, sd.max_iter,
                                            C.byref(it), hist.ctypes.data_as(C.POINTER(C.c_double)))
         self.n = it.value

@@ -66,6 +66,8 @@ typedef struct {
   double ip_factor;
   int64_t n_global_cells, global_cell_offset;
   int force_general;
+  int operator_is_singular;       /* OperatorBaseData::operator_is_singular (I/operators/operator_base.h:59-103): 1 / 0, or -1 to derive it
+                                     from the local boundary types (no Dirichlet face => singular) */
 } exadg_b200_mesh_desc;
 
 const char *exadg_b200_last_error(void);
@@ -79,6 +81,11 @@ int exadg_b200_destroy(exadg_b200_operator *op);
 /* bind to a CUDA stream (cudaStream_t passed as void*); default: a stream owned by the operator */
 int exadg_b200_set_stream(exadg_b200_operator *op, void *cuda_stream);
 int exadg_b200_synchronize(exadg_b200_operator *op);
+/* stream ordering against the caller's stream without a host synchronisation: the operator's stream waits for the work queued
+ * on cuda_stream so far (call before vmult & co. when src/dst were produced on another stream) / cuda_stream waits for the
+ * operator's work queued so far (call before consuming results there) */
+int exadg_b200_wait_stream(exadg_b200_operator *op, void *cuda_stream);
+int exadg_b200_stream_wait_operator(exadg_b200_operator *op, void *cuda_stream);
 
 /* OperatorBase::m()/n() (I/operators/operator_base.cpp:199-214): global number of DoFs */
 int64_t exadg_b200_n(const exadg_b200_operator *op);
@@ -86,6 +93,10 @@ int64_t exadg_b200_local_size(const exadg_b200_operator *op);   /* locally owned
 int64_t exadg_b200_n_cells_owned(const exadg_b200_operator *op);
 int64_t exadg_b200_n_cells_ghost(const exadg_b200_operator *op);
 int exadg_b200_is_cartesian_path(const exadg_b200_operator *op);  /* 1 if the Cartesian fast kernel is used */
+/* OperatorBase::operator_is_singular (I/operators/operator_base.h:196; OperatorBaseData::operator_is_singular): 1 if constants
+ * lie in the kernel (no Dirichlet face: all-periodic or pure Neumann box) */
+int exadg_b200_operator_is_singular(const exadg_b200_operator *op);
+int exadg_b200_degree(const exadg_b200_operator *op);              /* k of FE_DGQ(k) */
 int exadg_b200_kernel_launches(const exadg_b200_operator *op, int64_t *count); /* kernels launched so far by this operator */
 
 /* OperatorBase::initialize_dof_vector (operator_base.cpp:232-237): allocate a zeroed device vector */
@@ -175,6 +186,9 @@ int exadg_b200_plan_tables(const exadg_b200_plan *plan, int32_t *neighbors, int6
  * Process-wide; returns the previous value. All kernels compute the same operator (OperatorBase::apply,
  * operator_base.cpp:264-310); the environment variable EXADG_B200_CART_KERNEL=pipe / ws / ws12 / ws4p selects 0 / 1 / 2 / 3 at start-up. */
 int exadg_b200_cartesian_kernel(int variant);
+/* the same switch per operator (-1: follow the process-wide default); two operators of one process can differ */
+int exadg_b200_set_kernel_variant(exadg_b200_operator *op, int variant);
+int exadg_b200_get_kernel_variant(const exadg_b200_operator *op);
 
 /* FP64 pipe microbenchmarks used for the roofline denominators (DFMA and DMMA rates) */
 int exadg_b200_fp64_peak(double *dfma_tflops, double *dmma_tflops);

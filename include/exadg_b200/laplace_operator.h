@@ -85,7 +85,19 @@ public:
   std::int64_t n() const { return exadg_b200_n(op); }
   double el(unsigned int, unsigned int) const { throw std::runtime_error("Matrix-free does not allow for entry access"); }
   bool is_empty_locally() const { return exadg_b200_n_cells_owned(op) == 0; }
-  bool operator_is_singular() const { return false; }
+  bool operator_is_singular() const { return exadg_b200_operator_is_singular(op) != 0; } // operator_base.h:196
+  // getters of operator_base.h:144-197 that have a meaning without deal.II objects; get_matrix_free and
+  // get_affine_constraints have no counterpart: the mesh lives inside the operator and FE_DGQ has no constraints
+  // (I/solvers_and_preconditioners/multigrid/constraints.h:120-125)
+  unsigned int get_level() const { return static_cast<unsigned int>(-1); } // dealii::numbers::invalid_unsigned_int = active level
+  unsigned int get_dof_index() const { return 0; }
+  unsigned int get_quad_index() const { return 0; }
+  unsigned int get_degree() const { return (unsigned int)exadg_b200_degree(op); }
+  void set_time(double const t) const { time = t; } // no time-dependent coefficient in the Laplace operator; kept for the interface
+  double get_time() const { return time; }
+  // order the operator's stream behind / ahead of a caller stream (cudaStream_t as void*)
+  void wait_stream(void * cuda_stream) const { check(exadg_b200_wait_stream(op, cuda_stream)); }
+  void stream_wait_operator(void * cuda_stream) const { check(exadg_b200_stream_wait_operator(op, cuda_stream)); }
 
   void initialize_dof_vector(VectorType & v) const
   {
@@ -121,6 +133,7 @@ public:
 
 private:
   exadg_b200_operator * op = nullptr;
+  mutable double time = 0.0; // operator_base.h:473
 };
 
 } // namespace B200

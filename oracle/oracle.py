@@ -34,6 +34,8 @@ def lib():
         dp = C.POINTER(C.c_double)
         L.orc_create_hypercube.restype = C.c_void_p
         L.orc_create_hypercube.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), C.c_double]
+        L.orc_create_periodic_box_lean.restype = C.c_void_p
+        L.orc_create_periodic_box_lean.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double]
         L.orc_create.restype = C.c_void_p
         L.orc_create.argtypes = [C.c_int, C.c_int, C.c_long, dp, C.POINTER(C.c_long), C.POINTER(C.c_ubyte), C.POINTER(C.c_ubyte), C.c_double]
         L.orc_destroy.argtypes = [C.c_void_p]
@@ -78,10 +80,14 @@ class OracleOperator:
     """SIPG Laplace operator on the reference's hypercube grids (CPU, FP64)."""
 
     def __init__(self, degree, n_sub=1, refine=0, mapping_degree=1, deformation=0.0, frequency=2,
-                 bc=(PERIODIC,) * 6, ip_factor=1.0):
+                 bc=(PERIODIC,) * 6, ip_factor=1.0, lean=False):
         L = lib()
         bc_arr = (C.c_int * 6)(*bc)
-        self.h = L.orc_create_hypercube(degree, n_sub, refine, mapping_degree, float(deformation), frequency, bc_arr, float(ip_factor))
+        if lean:  # periodic Cartesian box without stored geometry: vmult_fast only (the CPU baseline at benchmark size)
+            assert deformation == 0.0 and tuple(bc) == (PERIODIC,) * 6 and mapping_degree == 1
+            self.h = L.orc_create_periodic_box_lean(degree, n_sub, refine, float(ip_factor))
+        else:
+            self.h = L.orc_create_hypercube(degree, n_sub, refine, mapping_degree, float(deformation), frequency, bc_arr, float(ip_factor))
         if not self.h:
             raise ValueError("oracle: unsupported parameters")
         self.degree = degree

@@ -274,6 +274,7 @@ typedef struct {
   long n_bfaces; long *bface_c; unsigned char *bface_f;
   /* vectorised baseline (sipg_fast.inc): applicability and cell sizes of the uniform box */
   int fast_checked, fast_ok; double fast_h[3];
+  int lean; /* orc_create_periodic_box_lean: no stored geometry */
 } Op;
 
 static double det3(const double J[9])
@@ -607,6 +608,29 @@ static Op *op_from_mesh(Mesh *M, int degree, double ip_factor)
   return op;
 }
 
+/* Lean operator for the vectorised CPU baseline at benchmark size (bench.py, 96^3 cells): periodic Cartesian box only.  Holds the
+ * mesh connectivity and tau_K = sum_d 1/h_d (interior_penalty_parameter.h:68-98 on a uniform box with weights 1/2 on all six
+ * faces) - none of the per-quadrature-point geometry, which would take 36 KB per cell.  Only orc_vmult_fast, orc_n_dofs and
+ * orc_n_cells may be called on it (everything else needs the stored geometry and is refused by op->lean). */
+void *orc_create_periodic_box_lean(int degree, int n_sub, int refine, double ip_factor)
+{
+  if (degree < 1 || degree + 1 > MAXN - 3) return NULL;
+  const int bc[6] = {0, 0, 0, 0, 0, 0};
+  Mesh *M = mesh_hypercube(n_sub, refine, 1, 0.0, 2, bc);
+  Op *op = (Op *)calloc(1, sizeof(Op));
+  op->k = degree; op->mesh = M; op->ip_factor = ip_factor; op->lean = 1;
+  basis_init(&op->b, degree, degree + 1);
+  op->n_cells = M->n_cells; op->n_dofs = M->n_cells * op->b.n * op->b.n * op->b.n;
+  /* cell 0: vertices 0 and 7 of the trilinear mapping span the box */
+  const double *X = M->xmap;
+  double tk = 0.0;
+  for (int e = 0; e < 3; ++e) { op->fast_h[e] = X[7 * 3 + e] - X[e]; tk += 1.0 / op->fast_h[e]; }
+  op->tauK = (double *)malloc(sizeof(double) * op->n_cells);
+  for (long c = 0; c < op->n_cells; ++c) op->tauK[c] = tk;
+  op->fast_checked = 1; op->fast_ok = 1;
+  return op;
+}
+
 void *orc_create_hypercube(int degree, int n_sub, int refine, int mapping_degree, double deformation, int frequency, const int *bc, double ip_factor)
 {
   if (degree < 1 || degree + 1 > MAXN - 3 || mapping_degree < 1 || mapping_degree + 1 > MAXN) return NULL;
@@ -654,6 +678,7 @@ void orc_get_mesh(void *h, double *xmap, long *nb, unsigned char *nbface, unsign
 void orc_vmult_add(void *h, double *dst, const double *src)
 {
   Op *op = (Op *)h; int n3 = op->b.n * op->b.n * op->b.n;
+  if (op->lean) { fprintf(stderr, "oracle: operation needs the stored geometry (lean operator)\n"); abort(); }
   for (long c = 0; c < op->n_cells; ++c) cell_integral(op, c, src + c * n3, dst + c * n3);
   for (long f = 0; f < op->n_faces; ++f) interior_face_integral(op, f, src, dst);
   for (long f = 0; f < op->n_bfaces; ++f) {
@@ -675,6 +700,7 @@ void orc_vmult(void *h, double *dst, const double *src)
 void orc_vmult_cellwise(void *h, double *dst, const double *src, int n_threads)
 {
   Op *op = (Op *)h; int n3 = op->b.n * op->b.n * op->b.n;
+  if (op->lean) { fprintf(stderr, "oracle: operation needs the stored geometry (lean operator)\n"); abort(); }
 #ifdef _OPENMP
   if (n_threads > 0) omp_set_num_threads(n_threads);
 #endif
@@ -706,6 +732,7 @@ int orc_max_threads(void)
 void orc_calculate_diagonal(void *h, double *diag)
 {
   Op *op = (Op *)h; int n3 = op->b.n * op->b.n * op->b.n;
+  if (op->lean) { fprintf(stderr, "oracle: operation needs the stored geometry (lean operator)\n"); abort(); }
 #pragma omp parallel for schedule(static)
   for (long c = 0; c < op->n_cells; ++c) {
     double e[MAXP], y[MAXP];

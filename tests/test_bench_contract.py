@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def run(env_extra=None):
     env = dict(os.environ, **(env_extra or {}))
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"], capture_output=True, text=True,
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1", "--cells", "32"], capture_output=True, text=True,
                        env=env, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     return r.stdout.strip()
@@ -20,7 +20,7 @@ def test_reference_arm_prints_the_contract_line():
     out = run()
     line = json.loads(out.splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "DoFs/s" and line["higher_is_better"] is True
-    assert line["steps"] == 2 and line["warmup"] == 1 and line["value"] > 0 and line["ms_per_step"] > 0
+    assert line["steps"] == 2 and line["warmup"] == 3 and line["value"] > 0 and line["ms_per_step"] > 0
     assert line["dtype"] == "f64" and line["data"] == "synthetic" and line["vs_baseline"] is None and "workload" in line["config"]
     cb = line["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "vectorised" in cb["sample"]

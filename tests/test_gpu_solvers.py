@@ -45,10 +45,9 @@ def check_counts(its, hist, it_ref, hist_ref, rel_tol):
     tol = rel_tol * hist_ref[0]
     below = 1.0 - hist_ref[it_ref] / tol                # distance below the threshold at the stop
     above = hist_ref[it_ref - 1] / tol - 1.0 if it_ref > 0 else np.inf
-    if dev[max(0, m - 3):].max() < min(below, above):
-        assert its == it_ref, (its, it_ref)
-    else:
-        assert abs(its - it_ref) <= 1, (its, it_ref)
+    # north_star: identical iteration counts.  No +-1 allowance: the cases are fixed and deterministic (fixed summation orders on
+    # both sides), so a count that differs is a finding, reported with how close the reference was to its threshold.
+    assert its == it_ref, (its, it_ref, "reference cleared the threshold by", below, above, "history deviation", dev[max(0, m - 3):].max())
 
 
 import json

@@ -10,12 +10,13 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-12
 
 
-@pytest.fixture
-def ws_kernel():
-    import exadg_b200
-    previous = exadg_b200.cartesian_kernel(1)
-    yield
-    exadg_b200.cartesian_kernel(previous)
+# every kernel variant of the k=4 affine fast path that bench.py may time (include/exadg_b200.h: exadg_b200_set_kernel_variant)
+VARIANTS = [1, 2, 3]
+
+
+@pytest.fixture(params=VARIANTS, ids=["ws_depth8", "ws_depth12", "ws_4producers"])
+def ws_kernel(request):
+    return request.param
 
 
 def rel(a, b):
@@ -28,7 +29,8 @@ def rel(a, b):
 def test_ws_kernel_matches_oracle(ws_kernel, grid):
     import exadg_b200
     op = exadg_b200.LaplaceOperator.hypercube(4, grid[0], grid[1])
-    assert op.is_cartesian_path == 1 and exadg_b200.cartesian_kernel() == 1
+    op.set_kernel_variant(ws_kernel)  # per operator, not process-wide
+    assert op.is_cartesian_path == 1 and op.get_kernel_variant() == ws_kernel
     ref = OracleOperator(4, grid[0], grid[1])
     x = synthetic_vector(ref.n_dofs, seed=11)
     src = torch.from_numpy(x).cuda()
@@ -40,18 +42,24 @@ def test_ws_kernel_matches_oracle(ws_kernel, grid):
     assert rel(dst.cpu().numpy(), 2 * y_ref) < TOL
 
 
-def test_ws_kernel_persistent_ctas_equal_pipelined_kernel():
-    """48^3 cells = 4608 batches on 296 CTAs: every CTA runs ~16 batches through the double-buffered trace area"""
+def test_ws_kernel_persistent_ctas_equal_pipelined_kernel(ws_kernel):
+    """48^3 cells = 4608 batches on 296 CTAs: every CTA runs ~16 batches through the trace area; two operators of one process with
+    different kernels (the variant is a property of the operator)"""
     import exadg_b200
-    op = exadg_b200.LaplaceOperator.hypercube(4, 3, 4)
-    src = torch.rand(op.local_size(), dtype=torch.float64, device="cuda") * 2 - 1
-    y = [op.initialize_dof_vector(), op.initialize_dof_vector()]
-    previous = exadg_b200.cartesian_kernel(-1)
-    try:
-        for v in (0, 1):
-            exadg_b200.cartesian_kernel(v)
-            for _ in range(3):  # repeated launches: no state may leak between them
-                op.vmult(y[v], src)
-    finally:
-        exadg_b200.cartesian_kernel(previous)
+    ops = [exadg_b200.LaplaceOperator.hypercube(4, 3, 4), exadg_b200.LaplaceOperator.hypercube(4, 3, 4)]
+    ops[0].set_kernel_variant(0)
+    ops[1].set_kernel_variant(ws_kernel)
+    src = torch.rand(ops[0].local_size(), dtype=torch.float64, device="cuda") * 2 - 1
+    y = [op.initialize_dof_vector() for op in ops]
+    for v in (0, 1):
+        for _ in range(3):  # repeated launches: no state may leak between them
+            ops[v].vmult(y[v], src)
     assert ((y[1] - y[0]).norm() / y[0].norm()).item() < TOL
+    # size-independent properties at this size: A 1 = 0 on the periodic box, symmetry
+    one = torch.ones_like(src)
+    ops[1].vmult(y[1], one)
+    assert y[1].abs().max().item() < 1e-9 * y[0].abs().max().item()
+    v2 = torch.rand_like(src)
+    av = ops[1].initialize_dof_vector()
+    ops[1].vmult(av, v2)
+    assert abs((torch.dot(y[0], v2) - torch.dot(src, av)).item()) < 1e-11 * abs(torch.dot(y[0], v2).item()) + 1e-6
