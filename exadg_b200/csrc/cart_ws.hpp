@@ -67,6 +67,7 @@ struct WsArgs
   const i2 * halo;          // [n_batches][HL]: (local cell << 3 | face, neighbour cell), out-of-batch faces of the batch, x faces first, then y, z
   const int32_t * cnt;      // [n_batches] numbers of x, y, z entries packed as x | y << 10 | z << 20
   const int32_t * nloc;     // [n_batches][B * 6]: >= 0 in-batch neighbour (local index), < 0: -1 - (entry of the halo list)
+  const int64_t * nloc8;    // [n_batches][B]: the six values of a cell packed as signed bytes (face f in bits 8 f .. 8 f + 7)
   const int32_t * batches;  // optional list of batch ids
   const double * src; const double * ghost; double * dst;
   int64_t n_owned; int n_items; int HL; int add;
@@ -126,6 +127,7 @@ struct WsHostPlan
   int B = 0, HL = 0, n_batches = 0;
   std::vector<i2> halo;            // [n_batches][HL]
   std::vector<int32_t> cnt, nloc;  // [n_batches], [n_batches][B * 6]
+  std::vector<int64_t> nloc8;      // [n_batches][B], empty if a value does not fit a signed byte
 };
 
 // nb: [n_owned][6] local neighbour indices (ghost cells >= n_owned); every face has a neighbour on this path
@@ -152,6 +154,14 @@ inline WsHostPlan ws_build_plan(const int32_t * nb, int64_t n_owned, int B)
     P.HL = std::max(P.HL, (int)lists[b].size());
   }
   P.HL = std::max(P.HL, 1);
+  if (B <= 127 && P.HL <= 128) {
+    P.nloc8.assign((size_t)P.n_batches * B, 0);
+    for (size_t i = 0; i < P.nloc8.size(); ++i) {
+      uint64_t v = 0;
+      for (int f = 0; f < 6; ++f) v |= (uint64_t)(uint8_t)(int8_t)P.nloc[i * 6 + f] << (8 * f);
+      P.nloc8[i] = (int64_t)v;
+    }
+  }
   P.halo.assign((size_t)P.n_batches * P.HL, i2{0, 0});
   for (int b = 0; b < P.n_batches; ++b) std::copy(lists[b].begin(), lists[b].end(), P.halo.begin() + (size_t)b * P.HL);
   return P;

@@ -858,7 +858,7 @@ bool cartesian_supported(int n) { return n >= 2 && n <= 8; }
 
 int cartesian_kernel_variant(int set)
 {
-  if (g_cart_kernel < 0) { const char * e = getenv("EXADG_B200_CART_KERNEL"); g_cart_kernel = (e && std::strcmp(e, "pipe") == 0) ? 0 : ((e && std::strcmp(e, "ws12") == 0) ? 2 : ((e && std::strcmp(e, "ws4p") == 0) ? 3 : 1)); }
+  if (g_cart_kernel < 0) { const char * e = getenv("EXADG_B200_CART_KERNEL"); g_cart_kernel = (e && std::strcmp(e, "pipe") == 0) ? 0 : ((e && std::strcmp(e, "ws12") == 0) ? 2 : ((e && std::strcmp(e, "ws4p") == 0) ? 3 : ((e && std::strcmp(e, "wp") == 0) ? 4 : 1))); }
   const int previous = g_cart_kernel;
   if (set >= 0) g_cart_kernel = set;
   return previous;
@@ -1021,7 +1021,7 @@ static void launch_cart(const DeviceOperator & op, double * dst, const double * 
       if (ws_ok)
         ws_launch(op, plan->ws, dst, src, add, list ? list : (which == 0 ? nullptr : (which == 1 ? plan->d_interior : plan->d_boundary)),
                   list ? n_list : (which == 0 ? plan->n_batches : (which == 1 ? plan->n_interior : plan->n_boundary)), plan->n_sm,
-                  variant == 2 ? 12 : (variant == 3 ? 4 : 8), with_ghosts, stream);
+                  variant == 2 ? 12 : (variant == 3 ? 4 : (variant == 4 ? 100 : 8)), with_ghosts, stream);
       else if (plan->pipe) launch_pipe<5>(op, *plan, dst, src, add, which, stream, list, n_list);
       else launch_n<5>(op, *plan, dst, src, add, which, stream, list, n_list);
       break;

@@ -5,6 +5,7 @@
 #include <stdexcept>
 
 #include "cart_ws.hpp"
+#include "cart_wp.hpp"
 #include "operator.cuh"
 
 namespace exadg_b200
@@ -72,13 +73,65 @@ __global__ void __launch_bounds__(WsCfg<N, NP>::NT, 2) vmult_cartesian_ws_kernel
   ws_cta<N, R, GH, NP>(rt, T, A);
 }
 
+// run-time interface of the warp-private kernel (cart_wp.hpp): mbarriers with one arrival per warp, per-warp bulk stores
+template<int NT>
+struct DeviceRTwp
+{
+  double * base;
+  __device__ __forceinline__ double * smem() const { return base; }
+  __device__ __forceinline__ int tid() const { return (int)threadIdx.x; }
+  __device__ __forceinline__ int cta() const { return (int)blockIdx.x; }
+  __device__ __forceinline__ int ncta() const { return (int)gridDim.x; }
+  __device__ __forceinline__ void sync_all() { asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory"); }
+  __device__ __forceinline__ void sync_warp() { __syncwarp(); }
+  __device__ __forceinline__ void role_compute() {}
+  __device__ __forceinline__ void role_producer() {}
+  __device__ __forceinline__ void mbar_init(void * bar, int count)
+  {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __device__ __forceinline__ void mbar_arrive(void * bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(bar)) : "memory"); }
+  __device__ __forceinline__ void mbar_wait(void * bar, uint32_t parity)
+  {
+    uint32_t done;
+    do {
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(s32(bar)), "r"(parity) : "memory");
+    } while (!done);
+  }
+  __device__ __forceinline__ void load_issue(void * bar, double * dst, const double * src, uint32_t bytes)
+  {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)), "l"(src), "r"(bytes), "r"(s32(bar)) : "memory");
+  }
+  __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+  __device__ __forceinline__ void store_issue(double * g, const double * s, uint32_t bytes, bool add)
+  {
+    if (add) asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(g), "r"(s32(s)), "r"(bytes) : "memory");
+    else asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(s32(s)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  __device__ __forceinline__ void store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+  __device__ __forceinline__ void store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+};
+
+// warp-private kernel (cart_wp.hpp): four compute warps that own six cells each + NP producer warps
+template<int N, int R, bool GH, int NP>
+__global__ void __launch_bounds__(wp::WpCfg<N, NP>::NT, 2) vmult_cartesian_wp_kernel(const __grid_constant__ WsTables<N> T, const WsArgs A)
+{
+  extern __shared__ __align__(128) double wp_shared[];
+  DeviceRTwp<wp::WpCfg<N, NP>::NT> rt{wp_shared};
+  wp::wp_cta<N, R, GH, NP>(rt, T, A);
+}
+
 constexpr size_t WS_MAX_SMEM = 228 * 1024 / 2 - 1024; // half of an SM's shared memory minus the per-CTA reservation
 
 struct WsDevPlan
 {
-  i2 * d_halo = nullptr; int32_t * d_cnt = nullptr, * d_nloc = nullptr;
+  i2 * d_halo = nullptr; int32_t * d_cnt = nullptr, * d_nloc = nullptr; int64_t * d_nloc8 = nullptr;
   int HL = 0, n_batches = 0, ctas_per_sm = 0;
   size_t smem = 0, smem4 = 0; // smem4: with 4 producer warps (0 if it does not fit)
+  size_t smem_wp = 0;         // warp-private kernel (0: not applicable to this mesh)
   WsTables<5> T;
 };
 } // namespace
@@ -102,6 +155,10 @@ void * ws_plan_create(const DeviceOperator & op, const HostMesh & mesh)
   CUDA_CHECK(cudaMemcpy(P->d_cnt, H.cnt.data(), H.cnt.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   CUDA_CHECK(cudaMalloc(&P->d_nloc, H.nloc.size() * sizeof(int32_t)));
   CUDA_CHECK(cudaMemcpy(P->d_nloc, H.nloc.data(), H.nloc.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  if (!H.nloc8.empty()) {
+    CUDA_CHECK(cudaMalloc(&P->d_nloc8, H.nloc8.size() * sizeof(int64_t)));
+    CUDA_CHECK(cudaMemcpy(P->d_nloc8, H.nloc8.data(), H.nloc8.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+  }
   P->ctas_per_sm = 2;
   auto configure = [&](auto kernel, int threads, size_t bytes) {
     int occ = 0;
@@ -121,6 +178,14 @@ void * ws_plan_create(const DeviceOperator & op, const HostMesh & mesh)
         || configure(vmult_cartesian_ws_kernel<5, 4, true, 4>, WsCfg<5, 4>::NT, P->smem4) < 2)
       P->smem4 = 0;
   } catch (const std::exception &) { P->smem4 = 0; cudaGetLastError(); }
+  // warp-private kernel: same batch plan; needs an even number of owned cells (every bulk copy a multiple of 16 bytes)
+  try {
+    P->smem_wp = wp::wp_smem_bytes<5, 2>();
+    if (mesh.n_owned % 2 != 0 || !P->d_nloc8 || H.HL > wp::WpCfg<5>::HLMAX || P->smem_wp > WS_MAX_SMEM
+        || configure(vmult_cartesian_wp_kernel<5, 8, false, 2>, wp::WpCfg<5, 2>::NT, P->smem_wp) < 2
+        || configure(vmult_cartesian_wp_kernel<5, 8, true, 2>, wp::WpCfg<5, 2>::NT, P->smem_wp) < 2)
+      P->smem_wp = 0;
+  } catch (const std::exception &) { P->smem_wp = 0; cudaGetLastError(); }
   } catch (...) { ws_plan_destroy(P); throw; }
   if (P->ctas_per_sm < 1) { ws_plan_destroy(P); return nullptr; }
   return P;
@@ -130,7 +195,7 @@ void ws_plan_destroy(void * p)
 {
   WsDevPlan * P = static_cast<WsDevPlan *>(p);
   if (!P) return;
-  cudaFree(P->d_halo); cudaFree(P->d_cnt); cudaFree(P->d_nloc);
+  cudaFree(P->d_halo); cudaFree(P->d_cnt); cudaFree(P->d_nloc); cudaFree(P->d_nloc8);
   delete P;
 }
 
@@ -143,10 +208,13 @@ void ws_launch(const DeviceOperator & op, const void * p, double * dst, const do
   const WsDevPlan * P = static_cast<const WsDevPlan *>(p);
   if (n_items == 0) return;
   WsArgs A;
-  A.halo = P->d_halo; A.cnt = P->d_cnt; A.nloc = P->d_nloc; A.batches = batches;
+  A.halo = P->d_halo; A.cnt = P->d_cnt; A.nloc = P->d_nloc; A.nloc8 = P->d_nloc8; A.batches = batches;
   A.src = src; A.ghost = op.ghost; A.dst = dst; A.n_owned = op.n_owned; A.n_items = n_items; A.HL = P->HL; A.add = add ? 1 : 0;
   const int grid = std::min(n_items, n_sm * P->ctas_per_sm);
-  if (depth == 4 && P->smem4 > 0) {
+  if (depth == 100 && P->smem_wp > 0) { // warp-private kernel
+    if (gh) vmult_cartesian_wp_kernel<5, 8, true, 2><<<grid, wp::WpCfg<5, 2>::NT, P->smem_wp, stream>>>(P->T, A);
+    else vmult_cartesian_wp_kernel<5, 8, false, 2><<<grid, wp::WpCfg<5, 2>::NT, P->smem_wp, stream>>>(P->T, A);
+  } else if (depth == 4 && P->smem4 > 0) {
     if (gh) vmult_cartesian_ws_kernel<5, 4, true, 4><<<grid, WsCfg<5, 4>::NT, P->smem4, stream>>>(P->T, A);
     else vmult_cartesian_ws_kernel<5, 4, false, 4><<<grid, WsCfg<5, 4>::NT, P->smem4, stream>>>(P->T, A);
   } else if (depth == 12) {

@@ -132,7 +132,7 @@ int wse_vmult(void * h, const double * src, const double * ghost, double * dst, 
 {
   Emu * E = static_cast<Emu *>(h);
   WsArgs A;
-  A.halo = E->plan.halo.data(); A.cnt = E->plan.cnt.data(); A.nloc = E->plan.nloc.data();
+  A.halo = E->plan.halo.data(); A.cnt = E->plan.cnt.data(); A.nloc = E->plan.nloc.data(); A.nloc8 = E->plan.nloc8.data();
   A.batches = which == 0 ? nullptr : (which == 1 ? E->interior.data() : E->boundary.data());
   A.n_items = wse_n_batches(h, which);
   A.src = src; A.ghost = ghost; A.dst = dst; A.n_owned = E->mesh.n_owned; A.HL = E->plan.HL; A.add = add;
