@@ -63,7 +63,8 @@ struct WpSmem
 template<int N, int NP = 2>
 inline size_t wp_smem_bytes()
 {
-  return (size_t)WpSmem<N>::END * sizeof(double) + (size_t)NP * WpCfg<N>::HLMAX * sizeof(i2) + 4 * 8 /* mbarriers */ + 16;
+  return (size_t)WpSmem<N>::END * sizeof(double) + (size_t)NP * WpCfg<N>::HLMAX * sizeof(i2) + (size_t)WpCfg<N>::B * sizeof(int64_t) /* neighbour table */
+         + 4 * 8 /* mbarriers */ + 16;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -148,7 +149,8 @@ WS_FN void wp_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
   double * const TRV = smem + S::TRV;
   double * const TRG = smem + S::TRG;
   i2 * const hlS = reinterpret_cast<i2 *>(smem + S::END);                               // [NP][HLMAX]
-  void * const barU = reinterpret_cast<char *>(hlS + NP * Cfg::HLMAX);                  // batch landed (bulk copy, tx count)
+  int64_t * const NL = reinterpret_cast<int64_t *>(hlS + NP * Cfg::HLMAX);              // [B] packed neighbour indices of the batch (handed over by barrier A)
+  void * const barU = reinterpret_cast<char *>(NL + B);                                 // batch landed (bulk copy, tx count)
   void * const barA = reinterpret_cast<char *>(barU) + 8;                               // GN / VNz / TR of the batch complete
   void * const barB = reinterpret_cast<char *>(barU) + 16;                              // GN / VNz / TR of the batch consumed
   void * const barC = reinterpret_cast<char *>(barU) + 24;                              // U of the batch consumed
@@ -175,8 +177,10 @@ WS_FN void wp_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
     ws::ws_prefetch(A, batch_of(first), lane, pre);
     if (pw == 0 && lane == 0) rt.load_issue(barU, U, A.src + (int64_t)batch_of(first) * B * N3, batch_bytes(batch_of(first)));
     uint32_t n = 0; // batches handled so far
+    bool ghosts_acquired = false;
     for (int it = first; it < A.n_items; it += step, ++n) {
       const int itn = it + step;
+      if (GH && A.flags && !ghosts_acquired && it >= A.first_ghost_item) { ws::ws_acquire_ghosts(rt, A); ghosts_acquired = true; }
       // traces of batch `it`; the trace area was last read for the batch before (barrier B of iteration n - 1)
       const int cx = pre.c & 1023, cy = (pre.c >> 10) & 1023, cz = (pre.c >> 20) & 1023;
       hl[lane] = pre.h[0]; hl[lane + 32] = pre.h[1];
@@ -189,6 +193,7 @@ WS_FN void wp_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
       wp_produce_dir<N, R, 1, GH, NP>(T, A, hl, cx, cx + cy, round, pw, ab, act, TRV, TRG, gate);
       wp_produce_dir<N, R, 2, GH, NP>(T, A, hl, cx + cy, cx + cy + cz, round, pw, ab, act, TRV, TRG, gate);
       gate(); // a warp without any round still orders itself behind the consumers (its arrival below completes barrier A)
+      if (pw == 0 && lane < B) NL[lane] = A.nloc8[(size_t)batch_of(it) * B + lane]; // read by the compute warps between barriers A and B
       rt.sync_warp(); // all lanes' trace stores (and reads of hl) precede the elected arrival
       if (lane == 0) rt.mbar_arrive(barA);
       // the next batch may land as soon as the compute warps are done with U (barrier C of this iteration)
@@ -212,23 +217,11 @@ WS_FN void wp_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
   double * const Tw = smem + S::T + warp * WT;    // the warp's transposition area
   const int sk = s + N * c;                       // lane-dependent part of the skewed address in the z layout (j = s)
   uint32_t n = 0;
-  int64_t nl8 = 0; // the six neighbour indices of the lane's cell, one signed byte each
-  auto load_nl = [&](int bt, bool ok) { nl8 = ok ? A.nloc8[(size_t)bt * B + lc] : 0; };
-  {
-    const int bt = batch_of(first);
-    load_nl(bt, lane_ok && lc < (int)ws::ws_min(B, A.n_owned - (int64_t)bt * B));
-  }
   for (int it = first; it < A.n_items; it += step, ++n) {
-    const int itn = it + step;
     const int batch = batch_of(it);
     const int64_t b0 = (int64_t)batch * B;
     const int nvalid = (int)ws::ws_min(B, A.n_owned - b0);
     const bool valid = lane_ok && lc < nvalid;
-    const int64_t nlc8 = nl8;
-    if (itn < A.n_items) { // index table of the next batch: in flight during this one
-      const int bn = batch_of(itn);
-      load_nl(bn, lane_ok && lc < (int)ws::ws_min(B, A.n_owned - (int64_t)bn * B));
-    }
     rt.mbar_wait(barU, n & 1);                       // the batch has landed
     if (n > 0) rt.mbar_wait(barB, (n - 1) & 1);      // GN / VNz of the previous batch are consumed
 
@@ -294,6 +287,7 @@ WS_FN void wp_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
     rt.sync_warp();
     if (lane == 0) rt.mbar_arrive(barA);
     rt.mbar_wait(barA, n & 1); // traces of every cell of the batch and of the out-of-batch neighbours are complete
+    const int64_t nlc8 = NL[lc]; // the six neighbour indices of the lane's cell, one signed byte each
 
     // ---- P1: face terms in x and y on the register plane ----
     if (valid) {

@@ -71,7 +71,18 @@ struct WsArgs
   const int32_t * batches;  // optional list of batch ids
   const double * src; const double * ghost; double * dst;
   int64_t n_owned; int n_items; int HL; int add;
+  // single-launch partitioned vmult (NVLink peer-memory halo, csrc/c_api.cu): items [first_ghost_item, n_items) read ghost cells that
+  // the peers store into this rank's ghost buffer during the launch; a producer warp acquires the peers' flags (>= epoch) before
+  // its first such item.  flags == nullptr: the ghost buffer is complete before the launch.
+  const long long * flags; long long epoch; int first_ghost_item; int n_peers; int peer_rank[16];
 };
+
+// all peers have stored this vmult's ghost cells (every lane acquires every flag: its later loads are ordered behind them)
+template<class RT>
+WS_FN void ws_acquire_ghosts(RT & rt, const WsArgs & A)
+{
+  for (int p = 0; p < A.n_peers; ++p) rt.flag_wait(A.flags + A.peer_rank[p], A.epoch);
+}
 
 // shared memory of one CTA in bytes (doubles first, then the int tables, then the mbarrier)
 template<int N, int NP = 2>
@@ -290,10 +301,12 @@ WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
   const int pw = producer ? (t - NC) / 32 : 0, lane = t % 32;
   WsPrefetch pre;
   pre.c = 0; pre.h[0] = i2{0, 0}; pre.h[1] = i2{0, 0};
+  bool ghosts_acquired = false;
   {
     const int bt = A.batches ? A.batches[first] : first;
     if (producer) {
       const int it1 = first + step;
+      if (GH && A.flags && first >= A.first_ghost_item) { ws_acquire_ghosts(rt, A); ghosts_acquired = true; }
       ws_prefetch(A, bt, lane, pre);
       ws_produce<N, R, GH, NP>(rt, T, A, bt, it1 < A.n_items ? (A.batches ? A.batches[it1] : it1) : -1, pw, lane, pre, smem + OFF_TR, smem + OFF_TR + trs, nl2,
                            hlS + pw * WsCfg<N>::HLMAX);
@@ -313,6 +326,7 @@ WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
       const int itn = it + step, itnn = itn + step;
       if (itn < A.n_items) {
         const int bn = A.batches ? A.batches[itn] : itn;
+        if (GH && A.flags && !ghosts_acquired && itn >= A.first_ghost_item) { ws_acquire_ghosts(rt, A); ghosts_acquired = true; }
         ws_produce<N, R, GH, NP>(rt, T, A, bn, itnn < A.n_items ? (A.batches ? A.batches[itnn] : itnn) : -1, pw, lane, pre, smem + OFF_TR + (buf ^ 1) * 2 * trs,
                              smem + OFF_TR + (buf ^ 1) * 2 * trs + trs, nl2 + (buf ^ 1) * B * 6, hlS + pw * WsCfg<N>::HLMAX);
       }

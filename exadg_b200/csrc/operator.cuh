@@ -58,12 +58,22 @@ void launch_vmult_cartesian_list(const DeviceOperator & op, double * dst, const 
 int cartesian_batch_size(const DeviceOperator & op);
 int cartesian_n_batches(const DeviceOperator & op);
 
+// in-kernel ghost hand-over of the single-launch partitioned vmult (NVLink peer-memory halo): this rank's flag slots, indexed by
+// peer rank, reach `epoch` once that peer has stored its cells into this rank's ghost buffer
+struct GhostSync
+{
+  const long long * flags = nullptr; long long epoch = 0; int n_peers = 0; int peer_rank[16] = {0};
+};
+// one launch over all batches of a partition, batches without ghost neighbours first; the producers of the remaining batches acquire
+// the peers' flags inside the kernel.  Returns false (nothing launched) if the operator has no kernel with that capability.
+bool launch_vmult_cartesian_fused(const DeviceOperator & op, double * dst, const double * src, bool add, const GhostSync & gs, cudaStream_t stream);
+
 // ---- vmult_cartesian_ws.cu (warp-specialised kernel, n = 5) ----
 bool ws_supported(int n);
 void * ws_plan_create(const DeviceOperator & op, const HostMesh & mesh);
 void ws_plan_destroy(void * plan);
 void ws_launch(const DeviceOperator & op, const void * plan, double * dst, const double * src, bool add, const int32_t * batches, int n_items, int n_sm, int depth, bool gh,
-               cudaStream_t stream);
+               cudaStream_t stream, const GhostSync * gs = nullptr, int first_ghost_item = 0);
 
 // ---- microbench.cu ----
 void fp64_peak(double * dfma_tflops, double * dmma_tflops);

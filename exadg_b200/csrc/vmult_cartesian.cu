@@ -765,6 +765,7 @@ struct CartPlan
   int n = 0, B = 0, H = 0, n_batches = 0;
   int2 * d_halo = nullptr; int32_t * d_cnt = nullptr;
   int32_t * d_interior = nullptr, * d_boundary = nullptr; int n_interior = 0, n_boundary = 0;
+  int32_t * d_ordered = nullptr; // interior batches, then the batches with ghost neighbours (single-launch partitioned vmult)
   size_t smem = 0;
   std::vector<char> tables; // CartTables<n> of this operator (depends on h and tau)
   // pipelined kernel (n = 5)
@@ -947,6 +948,9 @@ static size_t plan_create(DeviceOperator & op, const HostMesh & mesh, bool allow
   if (mesh.world > 1) {
     if (P.n_interior) { CUDA_CHECK(cudaMalloc(&P.d_interior, interior.size() * 4)); CUDA_CHECK(cudaMemcpy(P.d_interior, interior.data(), interior.size() * 4, cudaMemcpyHostToDevice)); }
     if (P.n_boundary) { CUDA_CHECK(cudaMalloc(&P.d_boundary, boundary.size() * 4)); CUDA_CHECK(cudaMemcpy(P.d_boundary, boundary.data(), boundary.size() * 4, cudaMemcpyHostToDevice)); }
+    std::vector<int32_t> ordered(interior);
+    ordered.insert(ordered.end(), boundary.begin(), boundary.end());
+    if (!ordered.empty()) { CUDA_CHECK(cudaMalloc(&P.d_ordered, ordered.size() * 4)); CUDA_CHECK(cudaMemcpy(P.d_ordered, ordered.data(), ordered.size() * 4, cudaMemcpyHostToDevice)); }
   }
   switch (N) {
     case 2: store_tables<2>(P, op); break;
@@ -970,7 +974,7 @@ void cartesian_plan_destroy(DeviceOperator & op)
 {
   CartPlan * P = static_cast<CartPlan *>(op.cart_plan);
   if (!P) return;
-  cudaFree(P->d_halo); cudaFree(P->d_cnt); cudaFree(P->d_cnt4); cudaFree(P->d_interior); cudaFree(P->d_boundary);
+  cudaFree(P->d_halo); cudaFree(P->d_cnt); cudaFree(P->d_cnt4); cudaFree(P->d_interior); cudaFree(P->d_boundary); cudaFree(P->d_ordered);
   ws_plan_destroy(P->ws);
   delete P;
   op.cart_plan = nullptr;
@@ -988,6 +992,18 @@ int cartesian_n_batches(const DeviceOperator & op)
 }
 
 static void launch_cart(const DeviceOperator & op, double * dst, const double * src, bool add, int which, const int32_t * list, int n_list, cudaStream_t stream);
+
+static int ws_depth_of(int variant) { return variant == 2 ? 12 : (variant == 3 ? 4 : (variant == 4 ? 100 : (variant == 5 ? 101 : 8))); }
+
+bool launch_vmult_cartesian_fused(const DeviceOperator & op, double * dst, const double * src, bool add, const GhostSync & gs, cudaStream_t stream)
+{
+  const CartPlan * plan = static_cast<const CartPlan *>(op.cart_plan);
+  const int variant = op.cart_variant >= 0 ? op.cart_variant : cartesian_kernel_variant(-1);
+  static const bool off = getenv("EXADG_B200_NO_FUSED_HALO") != nullptr; // measurement switch: the multi-launch path
+  if (off || !plan || op.n != 5 || !plan->ws || variant < 1 || !plan->d_ordered || gs.n_peers > 16) return false;
+  ws_launch(op, plan->ws, dst, src, add, plan->d_ordered, plan->n_interior + plan->n_boundary, plan->n_sm, ws_depth_of(variant), true, stream, &gs, plan->n_interior);
+  return true;
+}
 
 // which: 0 all batches, 1 batches that touch no ghost cell, 2 batches that do
 void launch_vmult_cartesian_part(const DeviceOperator & op, double * dst, const double * src, bool add, int which, cudaStream_t stream)
@@ -1015,13 +1031,13 @@ static void launch_cart(const DeviceOperator & op, double * dst, const double * 
       // reads by construction: the very kernel instantiation that is verified on one GPU); the batches that touch ghost cells
       // stay on the pipelined kernel until the ghost path of the warp-specialised kernel has run on >= 2 GPUs
       const int variant = op.cart_variant >= 0 ? op.cart_variant : cartesian_kernel_variant(-1);
-      static const bool ws_ghost = getenv("EXADG_B200_WS_GHOST") != nullptr; // verification switch: ghost path of the warp-specialised kernel (tests/multi_gpu_check.py)
+      static const bool pipe_ghost = getenv("EXADG_B200_PIPE_GHOST") != nullptr; // measurement switch: batches with ghost neighbours on the pipelined kernel (round-1 behaviour)
       const bool with_ghosts = which == 2 || (which == 0 && op.n_ghost > 0);
-      const bool ws_ok = plan->ws && variant >= 1 && (!with_ghosts || ws_ghost);
+      const bool ws_ok = plan->ws && variant >= 1 && (!with_ghosts || !pipe_ghost);
       if (ws_ok)
         ws_launch(op, plan->ws, dst, src, add, list ? list : (which == 0 ? nullptr : (which == 1 ? plan->d_interior : plan->d_boundary)),
                   list ? n_list : (which == 0 ? plan->n_batches : (which == 1 ? plan->n_interior : plan->n_boundary)), plan->n_sm,
-                  variant == 2 ? 12 : (variant == 3 ? 4 : (variant == 4 ? 100 : 8)), with_ghosts, stream);
+                  ws_depth_of(variant), with_ghosts, stream);
       else if (plan->pipe) launch_pipe<5>(op, *plan, dst, src, add, which, stream, list, n_list);
       else launch_n<5>(op, *plan, dst, src, add, which, stream, list, n_list);
       break;

@@ -51,6 +51,11 @@ struct DeviceRT
     } while (!done);
     parity ^= 1;
   }
+  __device__ __forceinline__ void flag_wait(const long long * p, long long epoch)
+  {
+    long long v;
+    do { asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); } while (v < epoch);
+  }
   __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
   // shared -> global bulk copy (plain store, or FP64 add-reduction for vmult_add)
   __device__ __forceinline__ void store_issue(double * g, const double * s, uint32_t bytes, bool add)
@@ -103,6 +108,11 @@ struct DeviceRTwp
   {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)), "l"(src), "r"(bytes), "r"(s32(bar)) : "memory");
+  }
+  __device__ __forceinline__ void flag_wait(const long long * p, long long epoch)
+  {
+    long long v;
+    do { asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); } while (v < epoch);
   }
   __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
   __device__ __forceinline__ void store_issue(double * g, const double * s, uint32_t bytes, bool add)
@@ -183,7 +193,9 @@ void * ws_plan_create(const DeviceOperator & op, const HostMesh & mesh)
     P->smem_wp = wp::wp_smem_bytes<5, 2>();
     if (mesh.n_owned % 2 != 0 || !P->d_nloc8 || H.HL > wp::WpCfg<5>::HLMAX || P->smem_wp > WS_MAX_SMEM
         || configure(vmult_cartesian_wp_kernel<5, 8, false, 2>, wp::WpCfg<5, 2>::NT, P->smem_wp) < 2
-        || configure(vmult_cartesian_wp_kernel<5, 8, true, 2>, wp::WpCfg<5, 2>::NT, P->smem_wp) < 2)
+        || configure(vmult_cartesian_wp_kernel<5, 8, true, 2>, wp::WpCfg<5, 2>::NT, P->smem_wp) < 2
+        || configure(vmult_cartesian_wp_kernel<5, 12, false, 2>, wp::WpCfg<5, 2>::NT, P->smem_wp) < 2
+        || configure(vmult_cartesian_wp_kernel<5, 12, true, 2>, wp::WpCfg<5, 2>::NT, P->smem_wp) < 2)
       P->smem_wp = 0;
   } catch (const std::exception &) { P->smem_wp = 0; cudaGetLastError(); }
   } catch (...) { ws_plan_destroy(P); throw; }
@@ -203,17 +215,26 @@ void ws_plan_destroy(void * p)
 // depth: neighbour cells per producer round (8 or 12; 4 selects the variant with 4 producer warps); gh: the selected batches may
 // have neighbours in the ghost buffer
 void ws_launch(const DeviceOperator & op, const void * p, double * dst, const double * src, bool add, const int32_t * batches, int n_items, int n_sm, int depth, bool gh,
-               cudaStream_t stream)
+               cudaStream_t stream, const GhostSync * gs, int first_ghost_item)
 {
   const WsDevPlan * P = static_cast<const WsDevPlan *>(p);
   if (n_items == 0) return;
   WsArgs A;
   A.halo = P->d_halo; A.cnt = P->d_cnt; A.nloc = P->d_nloc; A.nloc8 = P->d_nloc8; A.batches = batches;
   A.src = src; A.ghost = op.ghost; A.dst = dst; A.n_owned = op.n_owned; A.n_items = n_items; A.HL = P->HL; A.add = add ? 1 : 0;
+  A.flags = nullptr; A.epoch = 0; A.first_ghost_item = 0; A.n_peers = 0;
+  for (int i = 0; i < 16; ++i) A.peer_rank[i] = 0;
+  if (gs && gs->flags) {
+    A.flags = gs->flags; A.epoch = gs->epoch; A.first_ghost_item = first_ghost_item; A.n_peers = gs->n_peers;
+    for (int i = 0; i < gs->n_peers && i < 16; ++i) A.peer_rank[i] = gs->peer_rank[i];
+  }
   const int grid = std::min(n_items, n_sm * P->ctas_per_sm);
   if (depth == 100 && P->smem_wp > 0) { // warp-private kernel
     if (gh) vmult_cartesian_wp_kernel<5, 8, true, 2><<<grid, wp::WpCfg<5, 2>::NT, P->smem_wp, stream>>>(P->T, A);
     else vmult_cartesian_wp_kernel<5, 8, false, 2><<<grid, wp::WpCfg<5, 2>::NT, P->smem_wp, stream>>>(P->T, A);
+  } else if (depth == 101 && P->smem_wp > 0) { // warp-private kernel, 12 neighbour cells per producer round
+    if (gh) vmult_cartesian_wp_kernel<5, 12, true, 2><<<grid, wp::WpCfg<5, 2>::NT, P->smem_wp, stream>>>(P->T, A);
+    else vmult_cartesian_wp_kernel<5, 12, false, 2><<<grid, wp::WpCfg<5, 2>::NT, P->smem_wp, stream>>>(P->T, A);
   } else if (depth == 4 && P->smem4 > 0) {
     if (gh) vmult_cartesian_ws_kernel<5, 4, true, 4><<<grid, WsCfg<5, 4>::NT, P->smem4, stream>>>(P->T, A);
     else vmult_cartesian_ws_kernel<5, 4, false, 4><<<grid, WsCfg<5, 4>::NT, P->smem4, stream>>>(P->T, A);

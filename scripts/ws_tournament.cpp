@@ -35,8 +35,8 @@ static int run_mesh(int n_sub, int refine, int steps, int only)
   CK(exadg_b200_set_stream(op, stream));
   const int64_t n = exadg_b200_local_size(op);
   std::printf("cells %d^3 dofs %lld cartesian_path %d\n", n_sub << refine, (long long)n, exadg_b200_is_cartesian_path(op));
-  constexpr int NV = 5; // 0 pipelined, 1 WS depth 8, 2 WS depth 12, 3 WS with 4 producer warps (setmaxnreg), 4 warp-private kernel
-  double * src = nullptr, * dst[NV] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  constexpr int NV = 6; // 0 pipelined, 1 WS depth 8, 2 WS depth 12, 3 WS with 4 producer warps (setmaxnreg), 4 warp-private kernel
+  double * src = nullptr, * dst[NV] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   CK(exadg_b200_initialize_dof_vector(op, &src));
   for (int v = 0; v < NV; ++v) CK(exadg_b200_initialize_dof_vector(op, &dst[v]));
   {

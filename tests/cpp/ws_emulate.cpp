@@ -67,6 +67,10 @@ struct HostRT
     ++waits;
     while (c->loads.load(std::memory_order_acquire) < waits) sched_yield();
   }
+  void flag_wait(const long long * p, long long epoch)
+  {
+    while (__atomic_load_n(p, __ATOMIC_ACQUIRE) < epoch) sched_yield();
+  }
   void fence_async() {}
   void check_store()
   {
@@ -136,6 +140,7 @@ int wse_vmult(void * h, const double * src, const double * ghost, double * dst, 
   A.batches = which == 0 ? nullptr : (which == 1 ? E->interior.data() : E->boundary.data());
   A.n_items = wse_n_batches(h, which);
   A.src = src; A.ghost = ghost; A.dst = dst; A.n_owned = E->mesh.n_owned; A.HL = E->plan.HL; A.add = add;
+  A.flags = nullptr; A.epoch = 0; A.first_ghost_item = 0; A.n_peers = 0;
   if (A.n_items == 0) return 0;
   if (E->plan.HL > WsCfg<N>::HLMAX) return -1; // the library falls back to the pipelined kernel
   n_ctas = std::min(n_ctas, A.n_items);
