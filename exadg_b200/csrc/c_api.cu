@@ -87,36 +87,6 @@ __global__ void put_cells_kernel(const PutArgs a, const double * __restrict__ sr
     dst[i] = src[(int64_t)cells[c] * n3 + k];
   }
 }
-// put + signal in one kernel: the last CTA of a peer's column (ticket counter) publishes the epoch in the peer's flag slot.
-// done[p] counts the CTAs that have finished storing for peer p over all vmults (never reset): the column of vmult number
-// `epoch` is complete when the count reaches epoch * gridDim.x.
-__global__ void put_signal_kernel(const PutArgs a, const double * __restrict__ src, int n3, unsigned long long * done, long long epoch)
-{
-  const int p = blockIdx.y;
-  const int32_t * __restrict__ cells = a.cells[p];
-  double * __restrict__ dst = a.dst[p]; // peer memory
-  const int64_t total = a.n_cells[p] * n3;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
-    double v[4]; // four independent loads in flight per thread
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int64_t i = i0 + q * stride;
-      if (i < total) { const int64_t c = i / n3; const int k = (int)(i - c * n3); v[q] = src[(int64_t)cells[c] * n3 + k]; }
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { const int64_t i = i0 + q * stride; if (i < total) dst[i] = v[q]; }
-  }
-  __threadfence_system(); // this thread's peer stores are performed before the ticket below
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned long long ticket = atomicAdd(done + p, 1ull) + 1ull;
-    if (ticket == (unsigned long long)epoch * gridDim.x) {
-      __threadfence_system(); // the other CTAs' stores (ordered before their tickets) are performed before the flag
-      asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(a.peer_flag[p]), "l"(epoch) : "memory");
-    }
-  }
-}
 __global__ void signal_peers_kernel(const PutArgs a, long long epoch)
 {
   const int p = threadIdx.x;
@@ -162,7 +132,7 @@ struct exadg_b200_operator
   int32_t * d_interior = nullptr, * d_boundary = nullptr; int64_t n_interior = 0, n_boundary = 0;
   // peer-memory halo (NVLink): one region [ghost A | ghost B | flags[world]] mapped by all peers
   bool p2p = false; char * p2p_region = nullptr; size_t p2p_ghost_bytes = 0; long long p2p_epoch = 0;
-  unsigned long long * d_put_done = nullptr; unsigned put_grid_x = 0; // ticket counters of put_signal_kernel (fixed grid: the counters never reset)
+  unsigned long long * d_put_done = nullptr; long long put_seq = 0; int put_grid = 0; // ticket counters of the in-launch export (GhostSync)
   std::vector<void *> p2p_peer_regions; // opened IPC mappings, indexed like mesh.peers
   std::vector<int64_t> p2p_peer_recv_begin, p2p_peer_ghost_bytes;
   double * ghost_alloc = nullptr; // the ghost buffer of the NCCL path (dev.ghost points into p2p_region once p2p is on)
@@ -320,30 +290,21 @@ void apply(exadg_b200_operator * op, double * dst, const double * src, bool add)
     // src must be complete (work queued on the compute stream) before it is read on the communication stream
     CUDA_CHECK(cudaEventRecord(op->ev_packed, op->stream));
     CUDA_CHECK(cudaStreamWaitEvent(op->comm_stream, op->ev_packed, 0));
-    if (op->dev.cartesian && op->put_grid_x > 0) {
-      // single launch: put + signal fused on the communication stream, ONE operator launch on the compute stream whose producers
-      // acquire the peers' flags before the first batch that reads ghost cells
+    if (op->dev.cartesian && op->d_put_done) {
+      // single launch: the operator kernel exports this rank's cells before its first batch (every CTA a slice, the last one per
+      // peer publishes the epoch), runs the batches without ghost neighbours, and its producers acquire the peers' flags before
+      // the first batch that reads ghost cells.  No communication stream, no events.
       GhostSync gs;
       gs.flags = reinterpret_cast<const long long *>(op->p2p_region + 2 * op->p2p_ghost_bytes); gs.epoch = epoch; gs.n_peers = a.n_peers;
-      for (int i = 0; i < a.n_peers; ++i) gs.peer_rank[i] = a.peer_rank[i];
-      const dim3 grid(op->put_grid_x, (unsigned)a.n_peers);
-      put_signal_kernel<<<grid, 256, 0, op->comm_stream>>>(a, src, n3, op->d_put_done, epoch);
-      CUDA_CHECK(cudaEventRecord(op->ev_halo, op->comm_stream));
+      gs.done = op->d_put_done; gs.put_seq = &op->put_seq; gs.put_grid = &op->put_grid;
+      for (int i = 0; i < a.n_peers; ++i) {
+        gs.peer_rank[i] = a.peer_rank[i]; gs.send_cells[i] = a.cells[i]; gs.n_send[i] = a.n_cells[i]; gs.peer_ghost[i] = a.dst[i]; gs.peer_flag[i] = a.peer_flag[i];
+      }
       if (launch_vmult_cartesian_fused(op->dev, dst, src, add, gs, op->stream)) {
-        op->launches += 2;
-        CUDA_CHECK(cudaStreamWaitEvent(op->stream, op->ev_halo, 0)); // src is read by the put kernel until then
+        op->launches += 1;
         CUDA_CHECK(cudaGetLastError());
         return;
       }
-      // no kernel with in-kernel hand-over for this operator: the flags are awaited by a kernel in front of the boundary launch
-      wait_peers_kernel<<<1, 32, 0, op->comm_stream>>>(a, reinterpret_cast<const long long *>(op->p2p_region + 2 * op->p2p_ghost_bytes), epoch);
-      op->launches += 2;
-      launch_vmult(op, dst, src, add, 2, op->comm_stream);
-      CUDA_CHECK(cudaEventRecord(op->ev_halo, op->comm_stream));
-      launch_vmult(op, dst, src, add, 1);
-      CUDA_CHECK(cudaStreamWaitEvent(op->stream, op->ev_halo, 0));
-      CUDA_CHECK(cudaGetLastError());
-      return;
     }
     const dim3 grid((unsigned)std::min<int64_t>((max_total + 255) / 256, 64), (unsigned)a.n_peers);
     put_cells_kernel<<<grid, 256, 0, op->comm_stream>>>(a, src, n3);
@@ -1036,9 +997,6 @@ int exadg_b200_p2p_connect(exadg_b200_operator * op, const char * handles /*[wor
     if (!op->d_put_done) {
       CUDA_CHECK(cudaMalloc(&op->d_put_done, MAX_PEERS * sizeof(unsigned long long)));
       CUDA_CHECK(cudaMemset(op->d_put_done, 0, MAX_PEERS * sizeof(unsigned long long)));
-      int64_t max_total = 1;
-      for (auto & p : M.peers) max_total = std::max<int64_t>(max_total, (int64_t)p.send_cells.size() * (int64_t)(op->dev.n * op->dev.n * op->dev.n));
-      op->put_grid_x = (unsigned)std::min<int64_t>((max_total + 1023) / 1024, 48);
       CUDA_CHECK(cudaDeviceSynchronize());
     }
     op->p2p = true;

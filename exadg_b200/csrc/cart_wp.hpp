@@ -189,9 +189,15 @@ WS_FN void wp_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
       bool gated = false;
       auto gate = [&]() { if (!gated) { if (n > 0) rt.mbar_wait(barB, (n - 1) & 1); gated = true; } };
       int round = 0;
-      wp_produce_dir<N, (R > 8 ? 8 : R), 0, GH, NP>(T, A, hl, 0, cx, round, pw, ab, act, TRV, TRG, gate);
-      wp_produce_dir<N, R, 1, GH, NP>(T, A, hl, cx, cx + cy, round, pw, ab, act, TRV, TRG, gate);
-      wp_produce_dir<N, R, 2, GH, NP>(T, A, hl, cx + cy, cx + cy + cz, round, pw, ab, act, TRV, TRG, gate);
+      if (GH && (!A.flags || it >= A.first_ghost_item)) { // only these items can have neighbours in the ghost buffer
+        wp_produce_dir<N, (R > 8 ? 8 : R), 0, GH, NP>(T, A, hl, 0, cx, round, pw, ab, act, TRV, TRG, gate);
+        wp_produce_dir<N, R, 1, GH, NP>(T, A, hl, cx, cx + cy, round, pw, ab, act, TRV, TRG, gate);
+        wp_produce_dir<N, R, 2, GH, NP>(T, A, hl, cx + cy, cx + cy + cz, round, pw, ab, act, TRV, TRG, gate);
+      } else {
+        wp_produce_dir<N, (R > 8 ? 8 : R), 0, false, NP>(T, A, hl, 0, cx, round, pw, ab, act, TRV, TRG, gate);
+        wp_produce_dir<N, R, 1, false, NP>(T, A, hl, cx, cx + cy, round, pw, ab, act, TRV, TRG, gate);
+        wp_produce_dir<N, R, 2, false, NP>(T, A, hl, cx + cy, cx + cy + cz, round, pw, ab, act, TRV, TRG, gate);
+      }
       gate(); // a warp without any round still orders itself behind the consumers (its arrival below completes barrier A)
       if (pw == 0 && lane < B) NL[lane] = A.nloc8[(size_t)batch_of(it) * B + lane]; // read by the compute warps between barriers A and B
       rt.sync_warp(); // all lanes' trace stores (and reads of hl) precede the elected arrival

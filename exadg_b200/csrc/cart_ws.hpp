@@ -308,8 +308,14 @@ WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
       const int it1 = first + step;
       if (GH && A.flags && first >= A.first_ghost_item) { ws_acquire_ghosts(rt, A); ghosts_acquired = true; }
       ws_prefetch(A, bt, lane, pre);
-      ws_produce<N, R, GH, NP>(rt, T, A, bt, it1 < A.n_items ? (A.batches ? A.batches[it1] : it1) : -1, pw, lane, pre, smem + OFF_TR, smem + OFF_TR + trs, nl2,
-                           hlS + pw * WsCfg<N>::HLMAX);
+      // with the in-kernel hand-over only the items from first_ghost_item on can have neighbours in the ghost buffer: the others run
+      // the very producer code of an unpartitioned mesh (no pointer select per load)
+      if (GH && (!A.flags || first >= A.first_ghost_item))
+        ws_produce<N, R, GH, NP>(rt, T, A, bt, it1 < A.n_items ? (A.batches ? A.batches[it1] : it1) : -1, pw, lane, pre, smem + OFF_TR, smem + OFF_TR + trs, nl2,
+                                 hlS + pw * WsCfg<N>::HLMAX);
+      else
+        ws_produce<N, R, false, NP>(rt, T, A, bt, it1 < A.n_items ? (A.batches ? A.batches[it1] : it1) : -1, pw, lane, pre, smem + OFF_TR, smem + OFF_TR + trs, nl2,
+                                    hlS + pw * WsCfg<N>::HLMAX);
     } else if (t == 0) {
       const int64_t c0 = (int64_t)bt * B;
       const uint32_t by = (uint32_t)((int)ws_min(B, A.n_owned - c0) * N3 * sizeof(double));
@@ -327,7 +333,11 @@ WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
       if (itn < A.n_items) {
         const int bn = A.batches ? A.batches[itn] : itn;
         if (GH && A.flags && !ghosts_acquired && itn >= A.first_ghost_item) { ws_acquire_ghosts(rt, A); ghosts_acquired = true; }
-        ws_produce<N, R, GH, NP>(rt, T, A, bn, itnn < A.n_items ? (A.batches ? A.batches[itnn] : itnn) : -1, pw, lane, pre, smem + OFF_TR + (buf ^ 1) * 2 * trs,
+        if (GH && (!A.flags || itn >= A.first_ghost_item))
+          ws_produce<N, R, GH, NP>(rt, T, A, bn, itnn < A.n_items ? (A.batches ? A.batches[itnn] : itnn) : -1, pw, lane, pre, smem + OFF_TR + (buf ^ 1) * 2 * trs,
+                             smem + OFF_TR + (buf ^ 1) * 2 * trs + trs, nl2 + (buf ^ 1) * B * 6, hlS + pw * WsCfg<N>::HLMAX);
+        else
+          ws_produce<N, R, false, NP>(rt, T, A, bn, itnn < A.n_items ? (A.batches ? A.batches[itnn] : itnn) : -1, pw, lane, pre, smem + OFF_TR + (buf ^ 1) * 2 * trs,
                              smem + OFF_TR + (buf ^ 1) * 2 * trs + trs, nl2 + (buf ^ 1) * B * 6, hlS + pw * WsCfg<N>::HLMAX);
       }
       rt.sync_all(); // hand-over: traces / index table of the next batch are complete, those of this batch are free

@@ -63,6 +63,12 @@ int cartesian_n_batches(const DeviceOperator & op);
 struct GhostSync
 {
   const long long * flags = nullptr; long long epoch = 0; int n_peers = 0; int peer_rank[16] = {0};
+  // the export of this rank's cells, done by the same launch before its first batch (every CTA copies a slice of every send list
+  // straight into the peer's ghost buffer over NVLink; the CTA that completes a peer's list publishes the epoch in the peer's flag
+  // slot).  done[p] counts finished CTAs over all launches and is never reset: the launch grid must not change between vmults.
+  const int32_t * send_cells[16] = {nullptr}; int64_t n_send[16] = {0}; double * peer_ghost[16] = {nullptr}; long long * peer_flag[16] = {nullptr};
+  unsigned long long * done = nullptr;
+  long long * put_seq = nullptr; int * put_grid = nullptr; // host-side state of the operator: launches counted by `done`, their grid
 };
 // one launch over all batches of a partition, batches without ghost neighbours first; the producers of the remaining batches acquire
 // the peers' flags inside the kernel.  Returns false (nothing launched) if the operator has no kernel with that capability.

@@ -859,7 +859,7 @@ bool cartesian_supported(int n) { return n >= 2 && n <= 8; }
 
 int cartesian_kernel_variant(int set)
 {
-  if (g_cart_kernel < 0) { const char * e = getenv("EXADG_B200_CART_KERNEL"); g_cart_kernel = (e && std::strcmp(e, "pipe") == 0) ? 0 : ((e && std::strcmp(e, "ws12") == 0) ? 2 : ((e && std::strcmp(e, "ws4p") == 0) ? 3 : ((e && std::strcmp(e, "wp") == 0) ? 4 : 1))); }
+  if (g_cart_kernel < 0) { const char * e = getenv("EXADG_B200_CART_KERNEL"); g_cart_kernel = (e && std::strcmp(e, "pipe") == 0) ? 0 : ((e && std::strcmp(e, "ws12") == 0) ? 2 : ((e && std::strcmp(e, "ws4p") == 0) ? 3 : ((e && std::strcmp(e, "wp") == 0) ? 4 : ((e && std::strcmp(e, "ws") == 0) ? 1 : 3)))); }
   const int previous = g_cart_kernel;
   if (set >= 0) g_cart_kernel = set;
   return previous;

@@ -16,6 +16,43 @@ using namespace ws;
 
 __device__ __forceinline__ uint32_t s32(const void * p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// export of this rank's boundary cells by the operator launch itself (single-launch partitioned vmult): see GhostSync
+struct PutDesc
+{
+  const int32_t * cells[16]; long long n_cells[16]; double * dst[16]; long long * flag[16];
+  unsigned long long * done; long long epoch; long long seq; int n_peers;
+};
+
+__device__ __forceinline__ void put_slice(const PutDesc & P, const double * __restrict__ src, int n3)
+{
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (int p = 0; p < P.n_peers; ++p) {
+    const int32_t * __restrict__ cells = P.cells[p];
+    double * __restrict__ dst = P.dst[p]; // peer memory
+    const long long total = P.n_cells[p] * n3;
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+      double v[4]; // four independent loads in flight per thread
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const long long i = i0 + q * stride;
+        if (i < total) { const long long c = i / n3; const int k = (int)(i - c * n3); v[q] = src[(long long)cells[c] * n3 + k]; }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const long long i = i0 + q * stride; if (i < total) dst[i] = v[q]; }
+    }
+  }
+  __threadfence_system(); // this thread's peer stores are performed before the ticket below
+  __syncthreads();
+  if (threadIdx.x < P.n_peers) {
+    const int p = threadIdx.x;
+    const unsigned long long ticket = atomicAdd(P.done + p, 1ull) + 1ull;
+    if (ticket == (unsigned long long)P.seq * gridDim.x) {
+      __threadfence_system(); // the other CTAs' stores (ordered before their tickets) are performed before the flag
+      asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(P.flag[p]), "l"(P.epoch) : "memory");
+    }
+  }
+}
+
 // NT: threads per CTA (CTA-wide barrier); REG: re-allocate registers between the roles (4 compute + 4 producer warps launched
 // with 128 registers per thread: the compute warpgroup grows to 160, the producer warpgroup shrinks to 96)
 template<int NT, bool REG>
@@ -71,9 +108,10 @@ struct DeviceRT
 // R: neighbour cells per producer round; GH: the partition has ghost cells (src of the neighbours may live in the ghost buffer);
 // NP: producer warps (2, or 4 with register re-allocation between the roles - not measured yet)
 template<int N, int R, bool GH, int NP>
-__global__ void __launch_bounds__(WsCfg<N, NP>::NT, 2) vmult_cartesian_ws_kernel(const __grid_constant__ WsTables<N> T, const WsArgs A)
+__global__ void __launch_bounds__(WsCfg<N, NP>::NT, 2) vmult_cartesian_ws_kernel(const __grid_constant__ WsTables<N> T, const WsArgs A, const __grid_constant__ PutDesc put)
 {
   extern __shared__ __align__(128) double ws_shared[];
+  if (GH && put.n_peers > 0) put_slice(put, A.src, N * N * N);
   DeviceRT<WsCfg<N, NP>::NT, (NP == 4)> rt{ws_shared, 0u};
   ws_cta<N, R, GH, NP>(rt, T, A);
 }
@@ -127,9 +165,10 @@ struct DeviceRTwp
 
 // warp-private kernel (cart_wp.hpp): four compute warps that own six cells each + NP producer warps
 template<int N, int R, bool GH, int NP>
-__global__ void __launch_bounds__(wp::WpCfg<N, NP>::NT, 2) vmult_cartesian_wp_kernel(const __grid_constant__ WsTables<N> T, const WsArgs A)
+__global__ void __launch_bounds__(wp::WpCfg<N, NP>::NT, 2) vmult_cartesian_wp_kernel(const __grid_constant__ WsTables<N> T, const WsArgs A, const __grid_constant__ PutDesc put)
 {
   extern __shared__ __align__(128) double wp_shared[];
+  if (GH && put.n_peers > 0) put_slice(put, A.src, N * N * N);
   DeviceRTwp<wp::WpCfg<N, NP>::NT> rt{wp_shared};
   wp::wp_cta<N, R, GH, NP>(rt, T, A);
 }
@@ -224,26 +263,42 @@ void ws_launch(const DeviceOperator & op, const void * p, double * dst, const do
   A.src = src; A.ghost = op.ghost; A.dst = dst; A.n_owned = op.n_owned; A.n_items = n_items; A.HL = P->HL; A.add = add ? 1 : 0;
   A.flags = nullptr; A.epoch = 0; A.first_ghost_item = 0; A.n_peers = 0;
   for (int i = 0; i < 16; ++i) A.peer_rank[i] = 0;
+  PutDesc put;
+  std::memset(&put, 0, sizeof(put));
   if (gs && gs->flags) {
     A.flags = gs->flags; A.epoch = gs->epoch; A.first_ghost_item = first_ghost_item; A.n_peers = gs->n_peers;
     for (int i = 0; i < gs->n_peers && i < 16; ++i) A.peer_rank[i] = gs->peer_rank[i];
+    if (gs->done) {
+      put.done = gs->done; put.epoch = gs->epoch; put.n_peers = gs->n_peers;
+      for (int i = 0; i < gs->n_peers && i < 16; ++i) { put.cells[i] = gs->send_cells[i]; put.n_cells[i] = gs->n_send[i]; put.dst[i] = gs->peer_ghost[i]; put.flag[i] = gs->peer_flag[i]; }
+    }
   }
-  const int grid = std::min(n_items, n_sm * P->ctas_per_sm);
+  int grid = std::min(n_items, n_sm * P->ctas_per_sm);
+  // in-kernel ghost hand-over: CTAs spin until the PEERS' put kernels have run, and those wait for this rank's previous launch -
+  // this rank's own put kernel must therefore always find room next to the persistent CTAs (otherwise two ranks whose operator
+  // kernels got all SMs before their put kernels became runnable wait for each other forever): leave four SMs' worth of CTAs out
+  if (A.flags && !put.done) grid = std::max(1, std::min(grid, n_sm * P->ctas_per_sm - 4 * P->ctas_per_sm));
+  // with the export inside the launch every CTA must be resident at once (a CTA that has not started yet holds back the peers'
+  // flags while the resident ones spin on theirs): the grid never exceeds the occupancy computed for this kernel
+  if (put.done) { // tickets are counted per launch of a fixed grid
+    if (*gs->put_grid != grid) { CUDA_CHECK(cudaMemsetAsync(put.done, 0, 16 * sizeof(unsigned long long), stream)); *gs->put_seq = 0; *gs->put_grid = grid; }
+    put.seq = ++*gs->put_seq;
+  }
   if (depth == 100 && P->smem_wp > 0) { // warp-private kernel
-    if (gh) vmult_cartesian_wp_kernel<5, 8, true, 2><<<grid, wp::WpCfg<5, 2>::NT, P->smem_wp, stream>>>(P->T, A);
-    else vmult_cartesian_wp_kernel<5, 8, false, 2><<<grid, wp::WpCfg<5, 2>::NT, P->smem_wp, stream>>>(P->T, A);
+    if (gh) vmult_cartesian_wp_kernel<5, 8, true, 2><<<grid, wp::WpCfg<5, 2>::NT, P->smem_wp, stream>>>(P->T, A, put);
+    else vmult_cartesian_wp_kernel<5, 8, false, 2><<<grid, wp::WpCfg<5, 2>::NT, P->smem_wp, stream>>>(P->T, A, put);
   } else if (depth == 101 && P->smem_wp > 0) { // warp-private kernel, 12 neighbour cells per producer round
-    if (gh) vmult_cartesian_wp_kernel<5, 12, true, 2><<<grid, wp::WpCfg<5, 2>::NT, P->smem_wp, stream>>>(P->T, A);
-    else vmult_cartesian_wp_kernel<5, 12, false, 2><<<grid, wp::WpCfg<5, 2>::NT, P->smem_wp, stream>>>(P->T, A);
+    if (gh) vmult_cartesian_wp_kernel<5, 12, true, 2><<<grid, wp::WpCfg<5, 2>::NT, P->smem_wp, stream>>>(P->T, A, put);
+    else vmult_cartesian_wp_kernel<5, 12, false, 2><<<grid, wp::WpCfg<5, 2>::NT, P->smem_wp, stream>>>(P->T, A, put);
   } else if (depth == 4 && P->smem4 > 0) {
-    if (gh) vmult_cartesian_ws_kernel<5, 4, true, 4><<<grid, WsCfg<5, 4>::NT, P->smem4, stream>>>(P->T, A);
-    else vmult_cartesian_ws_kernel<5, 4, false, 4><<<grid, WsCfg<5, 4>::NT, P->smem4, stream>>>(P->T, A);
+    if (gh) vmult_cartesian_ws_kernel<5, 4, true, 4><<<grid, WsCfg<5, 4>::NT, P->smem4, stream>>>(P->T, A, put);
+    else vmult_cartesian_ws_kernel<5, 4, false, 4><<<grid, WsCfg<5, 4>::NT, P->smem4, stream>>>(P->T, A, put);
   } else if (depth == 12) {
-    if (gh) vmult_cartesian_ws_kernel<5, 12, true, 2><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A);
-    else vmult_cartesian_ws_kernel<5, 12, false, 2><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A);
+    if (gh) vmult_cartesian_ws_kernel<5, 12, true, 2><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A, put);
+    else vmult_cartesian_ws_kernel<5, 12, false, 2><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A, put);
   } else {
-    if (gh) vmult_cartesian_ws_kernel<5, 8, true, 2><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A);
-    else vmult_cartesian_ws_kernel<5, 8, false, 2><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A);
+    if (gh) vmult_cartesian_ws_kernel<5, 8, true, 2><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A, put);
+    else vmult_cartesian_ws_kernel<5, 8, false, 2><<<grid, WsCfg<5>::NT, P->smem, stream>>>(P->T, A, put);
   }
   CUDA_CHECK(cudaGetLastError());
 }
