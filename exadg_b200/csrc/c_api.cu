@@ -132,7 +132,7 @@ struct exadg_b200_operator
   int32_t * d_interior = nullptr, * d_boundary = nullptr; int64_t n_interior = 0, n_boundary = 0;
   // peer-memory halo (NVLink): one region [ghost A | ghost B | flags[world]] mapped by all peers
   bool p2p = false; char * p2p_region = nullptr; size_t p2p_ghost_bytes = 0; long long p2p_epoch = 0;
-  unsigned long long * d_put_done = nullptr; long long put_seq = 0; int put_grid = 0; // ticket counters of the in-launch export (GhostSync)
+  unsigned long long * d_put_done = nullptr; long long put_seq = 0; int put_grid = 0; int * d_work_counter = nullptr; // ticket counters of the in-launch export (GhostSync)
   std::vector<void *> p2p_peer_regions; // opened IPC mappings, indexed like mesh.peers
   std::vector<int64_t> p2p_peer_recv_begin, p2p_peer_ghost_bytes;
   double * ghost_alloc = nullptr; // the ghost buffer of the NCCL path (dev.ghost points into p2p_region once p2p is on)
@@ -297,6 +297,8 @@ void apply(exadg_b200_operator * op, double * dst, const double * src, bool add)
       GhostSync gs;
       gs.flags = reinterpret_cast<const long long *>(op->p2p_region + 2 * op->p2p_ghost_bytes); gs.epoch = epoch; gs.n_peers = a.n_peers;
       gs.done = op->d_put_done; gs.put_seq = &op->put_seq; gs.put_grid = &op->put_grid;
+      static const bool static_items = getenv("EXADG_B200_STATIC_ITEMS") != nullptr; // measurement switch: every CTA exports, static striding
+      gs.counter = static_items ? nullptr : op->d_work_counter;
       for (int i = 0; i < a.n_peers; ++i) {
         gs.peer_rank[i] = a.peer_rank[i]; gs.send_cells[i] = a.cells[i]; gs.n_send[i] = a.n_cells[i]; gs.peer_ghost[i] = a.dst[i]; gs.peer_flag[i] = a.peer_flag[i];
       }
@@ -583,7 +585,7 @@ int exadg_b200_destroy(exadg_b200_operator * op)
   cudaFree(D.nb); cudaFree(D.face_id); cudaFree(D.face_info); cudaFree(D.cellG); cudaFree(D.faceG); cudaFree(D.tau_f); cudaFree(D.tau_cell); cudaFree(D.ghost);
   for (auto p : op->p2p_peer_regions) if (p) cudaIpcCloseMemHandle(p);
   if (op->p2p_region) cudaFree(op->p2p_region);
-  cudaFree(op->d_put_done);
+  cudaFree(op->d_put_done); cudaFree(op->d_work_counter);
   for (auto p : op->d_send_lists) cudaFree(p);
   for (auto p : op->d_send_bufs) cudaFree(p);
   cudaFree(op->d_interior); cudaFree(op->d_boundary); cudaFree(op->d_cell_diag);
@@ -995,6 +997,7 @@ int exadg_b200_p2p_connect(exadg_b200_operator * op, const char * handles /*[wor
     op->ghost_alloc = op->dev.ghost;
     // ticket counters of the fused put + signal kernel; the grid is fixed from here on (the counters accumulate over the vmults)
     if (!op->d_put_done) {
+      CUDA_CHECK(cudaMalloc(&op->d_work_counter, sizeof(int)));
       CUDA_CHECK(cudaMalloc(&op->d_put_done, MAX_PEERS * sizeof(unsigned long long)));
       CUDA_CHECK(cudaMemset(op->d_put_done, 0, MAX_PEERS * sizeof(unsigned long long)));
       CUDA_CHECK(cudaDeviceSynchronize());

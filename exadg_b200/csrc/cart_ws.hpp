@@ -75,6 +75,9 @@ struct WsArgs
   // the peers store into this rank's ghost buffer during the launch; a producer warp acquires the peers' flags (>= epoch) before
   // its first such item.  flags == nullptr: the ghost buffer is complete before the launch.
   const long long * flags; long long epoch; int first_ghost_item; int n_peers; int peer_rank[16];
+  // optional work counter (zeroed before the launch): the CTAs claim their items dynamically instead of striding through them -
+  // CTAs that start late (those that export this rank's cells first) then simply process fewer items
+  int * counter;
 };
 
 // all peers have stored this vmult's ghost cells (every lane acquires every flag: its later loads are ordered behind them)
@@ -90,7 +93,7 @@ inline size_t ws_smem_bytes(int HL)
 {
   constexpr int B = WsCfg<N>::B, N2 = N * N, N3 = N2 * N;
   return ((size_t)2 * B * N3 + (size_t)2 * B * N2 + (size_t)4 * HL * N2) * sizeof(double) + (size_t)2 * B * 6 * sizeof(int)
-         + (size_t)NP * WsCfg<N>::HLMAX * sizeof(i2) + 16;
+         + (size_t)NP * WsCfg<N>::HLMAX * sizeof(i2) + 16 + 16 /* item ring */;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -292,7 +295,18 @@ WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
   const bool producer = t >= NC;
   if (t == 0) rt.bar_init(bar);
   rt.sync_all();
-  const int first = rt.cta(), step = rt.ncta();
+  // item sequence of this CTA: item q(n) of its n-th iteration is cta + n * ncta, or - with a work counter - claimed one by one.
+  // Claimed items travel through a ring of four in shared memory: thread 0 claims q(n + 3) during iteration n; the CTA-wide barrier
+  // at the end of every iteration orders the write before the reads (iteration n + 1 needs q(n + 1), q(n + 2), q(n + 3)).
+  int * const ring = reinterpret_cast<int *>(reinterpret_cast<char *>(bar) + 16);
+  const bool dynamic = A.counter != nullptr;
+  if (dynamic) {
+    if (t == 0) { ring[0] = rt.claim(A.counter); ring[1] = rt.claim(A.counter); ring[2] = rt.claim(A.counter); }
+    rt.sync_all();
+  }
+  const int cta0 = rt.cta(), step = rt.ncta();
+  auto q = [&](int n) { return dynamic ? ring[n & 3] : cta0 + n * step; };
+  const int first = q(0);
   if (first >= A.n_items) return;
   const int lc = t / N, s = t % N;    // plane layout
   const int lz = t % B, sz = t / B;   // z-line layout: consecutive lanes = consecutive cells (stride n^3, odd -> conflict-free)
@@ -305,7 +319,7 @@ WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
   {
     const int bt = A.batches ? A.batches[first] : first;
     if (producer) {
-      const int it1 = first + step;
+      const int it1 = q(1);
       if (GH && A.flags && first >= A.first_ghost_item) { ws_acquire_ghosts(rt, A); ghosts_acquired = true; }
       ws_prefetch(A, bt, lane, pre);
       // with the in-kernel hand-over only the items from first_ghost_item on can have neighbours in the ghost buffer: the others run
@@ -328,8 +342,8 @@ WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
   if (producer) {
     rt.role_producer(); // register re-allocation between the roles where the run-time interface implements it
     int buf = 0;
-    for (int it = first; it < A.n_items; it += step, buf ^= 1) {
-      const int itn = it + step, itnn = itn + step;
+    for (int n = 0; q(n) < A.n_items; ++n, buf ^= 1) {
+      const int itn = q(n + 1), itnn = q(n + 2);
       if (itn < A.n_items) {
         const int bn = A.batches ? A.batches[itn] : itn;
         if (GH && A.flags && !ghosts_acquired && itn >= A.first_ghost_item) { ws_acquire_ghosts(rt, A); ghosts_acquired = true; }
@@ -346,9 +360,10 @@ WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
   }
   rt.role_compute();
   int buf = 0;
-  for (int it = first; it < A.n_items; it += step, buf ^= 1) {
-    const int itn = it + step;
+  for (int n = 0; q(n) < A.n_items; ++n, buf ^= 1) {
+    const int it = q(n), itn = q(n + 1);
     const bool has_next = itn < A.n_items;
+    if (dynamic && t == 0) ring[(n + 3) & 3] = rt.claim(A.counter); // slot of q(n - 1): read for the last time before the previous barrier
     {
       const int batch = A.batches ? A.batches[it] : it;
       const int64_t b0 = (int64_t)batch * B;

@@ -69,6 +69,7 @@ struct GhostSync
   const int32_t * send_cells[16] = {nullptr}; int64_t n_send[16] = {0}; double * peer_ghost[16] = {nullptr}; long long * peer_flag[16] = {nullptr};
   unsigned long long * done = nullptr;
   long long * put_seq = nullptr; int * put_grid = nullptr; // host-side state of the operator: launches counted by `done`, their grid
+  int * counter = nullptr; // device work counter (zeroed per launch) for dynamic item claiming; nullptr: static striding, every CTA exports
 };
 // one launch over all batches of a partition, batches without ghost neighbours first; the producers of the remaining batches acquire
 // the peers' flags inside the kernel.  Returns false (nothing launched) if the operator has no kernel with that capability.

@@ -20,12 +20,12 @@ __device__ __forceinline__ uint32_t s32(const void * p) { return (uint32_t)__cvt
 struct PutDesc
 {
   const int32_t * cells[16]; long long n_cells[16]; double * dst[16]; long long * flag[16];
-  unsigned long long * done; long long epoch; long long seq; int n_peers;
+  unsigned long long * done; long long epoch; long long seq; int n_peers; int n_export; // CTAs 0 .. n_export - 1 share the export
 };
 
 __device__ __forceinline__ void put_slice(const PutDesc & P, const double * __restrict__ src, int n3)
 {
-  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long stride = (long long)P.n_export * blockDim.x;
   for (int p = 0; p < P.n_peers; ++p) {
     const int32_t * __restrict__ cells = P.cells[p];
     double * __restrict__ dst = P.dst[p]; // peer memory
@@ -46,7 +46,7 @@ __device__ __forceinline__ void put_slice(const PutDesc & P, const double * __re
   if (threadIdx.x < P.n_peers) {
     const int p = threadIdx.x;
     const unsigned long long ticket = atomicAdd(P.done + p, 1ull) + 1ull;
-    if (ticket == (unsigned long long)P.seq * gridDim.x) {
+    if (ticket == (unsigned long long)P.seq * P.n_export) {
       __threadfence_system(); // the other CTAs' stores (ordered before their tickets) are performed before the flag
       asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(P.flag[p]), "l"(P.epoch) : "memory");
     }
@@ -88,6 +88,7 @@ struct DeviceRT
     } while (!done);
     parity ^= 1;
   }
+  __device__ __forceinline__ int claim(int * counter) { return atomicAdd(counter, 1); }
   __device__ __forceinline__ void flag_wait(const long long * p, long long epoch)
   {
     long long v;
@@ -111,7 +112,7 @@ template<int N, int R, bool GH, int NP>
 __global__ void __launch_bounds__(WsCfg<N, NP>::NT, 2) vmult_cartesian_ws_kernel(const __grid_constant__ WsTables<N> T, const WsArgs A, const __grid_constant__ PutDesc put)
 {
   extern __shared__ __align__(128) double ws_shared[];
-  if (GH && put.n_peers > 0) put_slice(put, A.src, N * N * N);
+  if (GH && put.n_peers > 0 && (int)blockIdx.x < put.n_export) put_slice(put, A.src, N * N * N);
   DeviceRT<WsCfg<N, NP>::NT, (NP == 4)> rt{ws_shared, 0u};
   ws_cta<N, R, GH, NP>(rt, T, A);
 }
@@ -147,6 +148,7 @@ struct DeviceRTwp
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)), "l"(src), "r"(bytes), "r"(s32(bar)) : "memory");
   }
+  __device__ __forceinline__ int claim(int * counter) { return atomicAdd(counter, 1); }
   __device__ __forceinline__ void flag_wait(const long long * p, long long epoch)
   {
     long long v;
@@ -168,7 +170,7 @@ template<int N, int R, bool GH, int NP>
 __global__ void __launch_bounds__(wp::WpCfg<N, NP>::NT, 2) vmult_cartesian_wp_kernel(const __grid_constant__ WsTables<N> T, const WsArgs A, const __grid_constant__ PutDesc put)
 {
   extern __shared__ __align__(128) double wp_shared[];
-  if (GH && put.n_peers > 0) put_slice(put, A.src, N * N * N);
+  if (GH && put.n_peers > 0 && (int)blockIdx.x < put.n_export) put_slice(put, A.src, N * N * N);
   DeviceRTwp<wp::WpCfg<N, NP>::NT> rt{wp_shared};
   wp::wp_cta<N, R, GH, NP>(rt, T, A);
 }
@@ -261,7 +263,7 @@ void ws_launch(const DeviceOperator & op, const void * p, double * dst, const do
   WsArgs A;
   A.halo = P->d_halo; A.cnt = P->d_cnt; A.nloc = P->d_nloc; A.nloc8 = P->d_nloc8; A.batches = batches;
   A.src = src; A.ghost = op.ghost; A.dst = dst; A.n_owned = op.n_owned; A.n_items = n_items; A.HL = P->HL; A.add = add ? 1 : 0;
-  A.flags = nullptr; A.epoch = 0; A.first_ghost_item = 0; A.n_peers = 0;
+  A.flags = nullptr; A.epoch = 0; A.first_ghost_item = 0; A.n_peers = 0; A.counter = nullptr;
   for (int i = 0; i < 16; ++i) A.peer_rank[i] = 0;
   PutDesc put;
   std::memset(&put, 0, sizeof(put));
@@ -281,6 +283,11 @@ void ws_launch(const DeviceOperator & op, const void * p, double * dst, const do
   // with the export inside the launch every CTA must be resident at once (a CTA that has not started yet holds back the peers'
   // flags while the resident ones spin on theirs): the grid never exceeds the occupancy computed for this kernel
   if (put.done) { // tickets are counted per launch of a fixed grid
+    // with a work counter the first 64 CTAs export and join the batches late (they claim fewer items); otherwise every CTA does
+    int * const counter = depth < 100 ? gs->counter : nullptr; // the warp-private kernel strides statically
+    put.n_export = counter ? std::min(grid, 64) : grid;
+    A.counter = counter;
+    if (counter) CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), stream));
     if (*gs->put_grid != grid) { CUDA_CHECK(cudaMemsetAsync(put.done, 0, 16 * sizeof(unsigned long long), stream)); *gs->put_seq = 0; *gs->put_grid = grid; }
     put.seq = ++*gs->put_seq;
   }

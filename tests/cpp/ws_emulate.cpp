@@ -71,6 +71,7 @@ struct HostRT
   {
     while (__atomic_load_n(p, __ATOMIC_ACQUIRE) < epoch) sched_yield();
   }
+  int claim(int * counter) { return __atomic_fetch_add(counter, 1, __ATOMIC_RELAXED); }
   void fence_async() {}
   void check_store()
   {
@@ -130,6 +131,10 @@ int wse_halo_max(void * h) { return static_cast<Emu *>(h)->plan.HL; }
 int64_t wse_smem_bytes(void * h) { return (int64_t)ws_smem_bytes<N, NP>(static_cast<Emu *>(h)->plan.HL); }
 int wse_n_batches(void * h, int which) { Emu * E = static_cast<Emu *>(h); return which == 0 ? E->plan.n_batches : (which == 1 ? (int)E->interior.size() : (int)E->boundary.size()); }
 
+static int g_dynamic = 0, g_counter = 0;
+// 1: the CTAs claim their items from a work counter (the scheduling of the single-launch partitioned vmult)
+void wse_set_dynamic(int on) { g_dynamic = on; }
+
 // dst (+)= A src on the batches selected by `which` (0 all, 1 batches without ghost neighbours, 2 batches with), n_ctas persistent CTAs;
 // returns the number of protocol errors
 int wse_vmult(void * h, const double * src, const double * ghost, double * dst, int add, int n_ctas, int which)
@@ -140,7 +145,8 @@ int wse_vmult(void * h, const double * src, const double * ghost, double * dst, 
   A.batches = which == 0 ? nullptr : (which == 1 ? E->interior.data() : E->boundary.data());
   A.n_items = wse_n_batches(h, which);
   A.src = src; A.ghost = ghost; A.dst = dst; A.n_owned = E->mesh.n_owned; A.HL = E->plan.HL; A.add = add;
-  A.flags = nullptr; A.epoch = 0; A.first_ghost_item = 0; A.n_peers = 0;
+  A.flags = nullptr; A.epoch = 0; A.first_ghost_item = 0; A.n_peers = 0; A.counter = nullptr;
+  if (g_dynamic) { g_counter = 0; A.counter = &g_counter; }
   if (A.n_items == 0) return 0;
   if (E->plan.HL > WsCfg<N>::HLMAX) return -1; // the library falls back to the pipelined kernel
   n_ctas = std::min(n_ctas, A.n_items);

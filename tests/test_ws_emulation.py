@@ -97,6 +97,19 @@ def test_plan_of_octet_aligned_meshes_fits_two_ctas_per_sm(emu, n_sub, refine, w
             emu.wse_destroy(h)
 
 
+def test_emulated_kernel_dynamic_item_claiming(emu):
+    """items claimed from a work counter through the ring in shared memory (single-launch partitioned vmult): same result"""
+    n = 6 ** 3 * N3
+    x = np.random.default_rng(10).uniform(-1, 1, n)
+    emu.wse_set_dynamic(1)
+    try:
+        y, _, _ = _run(emu, 3, 1, 0, 1, x, 3)
+    finally:
+        emu.wse_set_dynamic(0)
+    ref = _oracle(3, 1, x)
+    assert np.linalg.norm(y - ref) / np.linalg.norm(ref) < 1e-13
+
+
 def test_emulated_kernel_add(emu):
     n = 4 ** 3 * N3
     x = np.random.default_rng(8).uniform(-1, 1, n)
