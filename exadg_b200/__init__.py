@@ -34,6 +34,8 @@ EXPORTED_SYMBOLS = [
     "exadg_b200_plan_tables", "exadg_b200_p2p_export", "exadg_b200_p2p_connect",
     "exadg_b200_wait_stream", "exadg_b200_stream_wait_operator", "exadg_b200_operator_is_singular", "exadg_b200_degree",
     "exadg_b200_set_kernel_variant", "exadg_b200_get_kernel_variant",
+    "exadg_b200_n_boundary_faces", "exadg_b200_boundary_quadrature_points", "exadg_b200_set_boundary_values", "exadg_b200_rhs", "exadg_b200_rhs_add",
+    "exadg_b200_evaluate", "exadg_b200_evaluate_add", "exadg_b200_cell_quadrature_points", "exadg_b200_integrate_source_add", "exadg_b200_l2_error",
 ]
 
 
@@ -79,6 +81,16 @@ def load_library():
         getattr(L, name).restype = i64
         getattr(L, name).argtypes = [vp]
     L.exadg_b200_is_cartesian_path.argtypes = [vp]
+    L.exadg_b200_n_boundary_faces.argtypes = [vp, C.POINTER(i64)]
+    L.exadg_b200_boundary_quadrature_points.argtypes = [vp, vp, vp]
+    L.exadg_b200_set_boundary_values.argtypes = [vp, vp]
+    L.exadg_b200_rhs.argtypes = [vp, dp]
+    L.exadg_b200_rhs_add.argtypes = [vp, dp]
+    L.exadg_b200_evaluate.argtypes = [vp, dp, dp]
+    L.exadg_b200_evaluate_add.argtypes = [vp, dp, dp]
+    L.exadg_b200_cell_quadrature_points.argtypes = [vp, C.c_int, vp]
+    L.exadg_b200_integrate_source_add.argtypes = [vp, dp, vp]
+    L.exadg_b200_l2_error.argtypes = [vp, dp, vp, C.c_int, C.POINTER(C.c_double)]
     L.exadg_b200_kernel_launches.argtypes = [vp, C.POINTER(i64)]
     L.exadg_b200_initialize_dof_vector.argtypes = [vp, C.POINTER(vp)]
     L.exadg_b200_free_dof_vector.argtypes = [vp]

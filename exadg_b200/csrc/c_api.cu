@@ -139,6 +139,7 @@ struct exadg_b200_operator
   // work vectors
   double * w[4] = {nullptr, nullptr, nullptr, nullptr};
   double * d_cell_diag = nullptr;
+  void * post = nullptr; // boundary data / right-hand side / error norms (rhs_error.cu), built on first use
   double * d_stage_src = nullptr, * d_stage_dst = nullptr;
   // pipelined host-buffer vmult (exadg_b200_vmult_host_pipelined)
   HostPipelinePlan hp; bool hp_built = false;
@@ -244,8 +245,7 @@ void finish_setup(exadg_b200_operator * op, double ip_factor, bool force_general
     if (!interior.empty()) { CUDA_CHECK(cudaMalloc(&op->d_interior, interior.size() * 4)); CUDA_CHECK(cudaMemcpy(op->d_interior, interior.data(), interior.size() * 4, cudaMemcpyHostToDevice)); }
     if (!boundary.empty()) { CUDA_CHECK(cudaMalloc(&op->d_boundary, boundary.size() * 4)); CUDA_CHECK(cudaMemcpy(op->d_boundary, boundary.data(), boundary.size() * 4, cudaMemcpyHostToDevice)); }
   }
-  // free the big host arrays that are no longer needed
-  std::vector<double>().swap(M.xmap);
+  // the mapping support points stay on the host: rhs / evaluate / error norms rebuild their geometry from them on first use
 }
 
 // which: 0 all owned cells, 1 cells (batches) that touch no ghost, 2 those that do
@@ -589,6 +589,7 @@ int exadg_b200_destroy(exadg_b200_operator * op)
   for (auto p : op->d_send_lists) cudaFree(p);
   for (auto p : op->d_send_bufs) cudaFree(p);
   cudaFree(op->d_interior); cudaFree(op->d_boundary); cudaFree(op->d_cell_diag);
+  post_destroy(op->post);
   for (int i = 0; i < 4; ++i) cudaFree(op->w[i]);
   cudaFree(op->d_stage_src); cudaFree(op->d_stage_dst);
   cudaFree(op->d_iota);
@@ -788,6 +789,96 @@ int exadg_b200_calculate_inverse_diagonal(exadg_b200_operator * op, double * d)
     if (!op) throw std::invalid_argument("null operator");
     diagonal(op, d, false);
     invert_diagonal(d, op->n_local, op->stream); op->launches++;
+    return EXADG_B200_OK;
+  });
+}
+
+
+/* ---- inhomogeneous boundary data, right-hand side, error norms ---- */
+static void * post_of(exadg_b200_operator * op) { return post_get(op->post, op->dev, op->mesh, 0.0, op->stream); }
+
+int exadg_b200_n_boundary_faces(exadg_b200_operator * op, int64_t * n_faces)
+{
+  return guarded([&]() { if (!op || !n_faces) throw std::invalid_argument("null argument"); *n_faces = post_n_boundary_faces(post_of(op)); return EXADG_B200_OK; });
+}
+int exadg_b200_boundary_quadrature_points(exadg_b200_operator * op, double * xyz_host, uint8_t * type_host)
+{
+  return guarded([&]() { if (!op) throw std::invalid_argument("null operator"); post_boundary_points(post_of(op), op->dev, xyz_host, type_host, op->stream); return EXADG_B200_OK; });
+}
+int exadg_b200_set_boundary_values(exadg_b200_operator * op, const double * values_host)
+{
+  return guarded([&]() { if (!op || !values_host) throw std::invalid_argument("null argument"); post_set_boundary_values(post_of(op), op->dev, values_host, op->stream); return EXADG_B200_OK; });
+}
+int exadg_b200_rhs_add(exadg_b200_operator * op, double * dst)
+{
+  return guarded([&]() { if (!op) throw std::invalid_argument("null operator"); check_ptr(dst, "dst"); post_boundary_inhom_add(post_of(op), op->dev, op->mesh, -1.0, dst, op->stream); op->launches++; return EXADG_B200_OK; });
+}
+int exadg_b200_rhs(exadg_b200_operator * op, double * dst)
+{
+  return guarded([&]() {
+    if (!op) throw std::invalid_argument("null operator");
+    check_ptr(dst, "dst");
+    CUDA_CHECK(cudaMemsetAsync(dst, 0, (size_t)op->n_local * sizeof(double), op->stream));
+    post_boundary_inhom_add(post_of(op), op->dev, op->mesh, -1.0, dst, op->stream); op->launches++;
+    return EXADG_B200_OK;
+  });
+}
+int exadg_b200_evaluate_add(exadg_b200_operator * op, double * dst, const double * src)
+{
+  return guarded([&]() {
+    if (!op) throw std::invalid_argument("null operator");
+    apply(op, dst, src, true);
+    post_boundary_inhom_add(post_of(op), op->dev, op->mesh, +1.0, dst, op->stream); op->launches++;
+    return EXADG_B200_OK;
+  });
+}
+int exadg_b200_evaluate(exadg_b200_operator * op, double * dst, const double * src)
+{
+  return guarded([&]() {
+    if (!op) throw std::invalid_argument("null operator");
+    apply(op, dst, src, false);
+    post_boundary_inhom_add(post_of(op), op->dev, op->mesh, +1.0, dst, op->stream); op->launches++;
+    return EXADG_B200_OK;
+  });
+}
+int exadg_b200_cell_quadrature_points(exadg_b200_operator * op, int n_q_points_1d, double * xyz_host)
+{
+  return guarded([&]() {
+    if (!op || !xyz_host) throw std::invalid_argument("null argument");
+    if (n_q_points_1d < 1 || n_q_points_1d > 10) throw std::invalid_argument("n_q_points_1d must be in 1..10");
+    post_cell_points(post_of(op), op->dev, op->mesh, n_q_points_1d, xyz_host, op->stream);
+    return EXADG_B200_OK;
+  });
+}
+int exadg_b200_integrate_source_add(exadg_b200_operator * op, double * dst, const double * f_host)
+{
+  return guarded([&]() {
+    if (!op || !f_host) throw std::invalid_argument("null argument");
+    check_ptr(dst, "dst");
+    post_source_add(post_of(op), op->dev, op->mesh, f_host, dst, op->stream); op->launches += 2;
+    return EXADG_B200_OK;
+  });
+}
+int exadg_b200_l2_error(exadg_b200_operator * op, const double * u, const double * exact_host, int relative, double * error)
+{
+  return guarded([&]() {
+    if (!op || !exact_host || !error) throw std::invalid_argument("null argument");
+    check_ptr(u, "u");
+    const int nq = op->dev.degree + 3; // additional_quadrature_points = 3 (error_calculation.cpp:46)
+    const int64_t nc = op->dev.n_owned;
+    double * d_out = nullptr;
+    CUDA_CHECK(cudaMalloc(&d_out, (size_t)std::max<int64_t>(2 * nc, 1) * sizeof(double)));
+    CUDA_CHECK(cudaMemsetAsync(d_out, 0, (size_t)std::max<int64_t>(2 * nc, 1) * sizeof(double), op->stream));
+    post_l2_cells(post_of(op), op->dev, op->mesh, nq, u, exact_host, d_out, op->stream); op->launches += 2;
+    sum(op->red, 5, d_out, nc, op->stream); sum(op->red, 6, d_out + nc, nc, op->stream); op->launches += 2;
+    allreduce(op, op->red.result + 5, 2);
+    read_all_scalars(op);
+    cudaFree(d_out);
+    const double e2 = op->red.host[5], n2 = op->red.host[6];
+    if (relative) {
+      if (!(std::sqrt(n2) > 1e-15)) throw std::runtime_error("Cannot compute relative error since norm of solution tends to zero.");
+      *error = std::sqrt(e2) / std::sqrt(n2);
+    } else *error = std::sqrt(e2);
     return EXADG_B200_OK;
   });
 }

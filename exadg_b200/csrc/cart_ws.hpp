@@ -299,7 +299,7 @@ WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
   // Claimed items travel through a ring of four in shared memory: thread 0 claims q(n + 3) during iteration n; the CTA-wide barrier
   // at the end of every iteration orders the write before the reads (iteration n + 1 needs q(n + 1), q(n + 2), q(n + 3)).
   int * const ring = reinterpret_cast<int *>(reinterpret_cast<char *>(bar) + 16);
-  const bool dynamic = A.counter != nullptr;
+  const bool dynamic = GH && A.counter != nullptr; // unpartitioned launches (GH = false) keep the static sequence at compile time
   if (dynamic) {
     if (t == 0) { ring[0] = rt.claim(A.counter); ring[1] = rt.claim(A.counter); ring[2] = rt.claim(A.counter); }
     rt.sync_all();

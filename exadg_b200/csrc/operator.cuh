@@ -82,6 +82,17 @@ void ws_plan_destroy(void * plan);
 void ws_launch(const DeviceOperator & op, const void * plan, double * dst, const double * src, bool add, const int32_t * batches, int n_items, int n_sm, int depth, bool gh,
                cudaStream_t stream, const GhostSync * gs = nullptr, int first_ghost_item = 0);
 
+// ---- rhs_error.cu (inhomogeneous boundary data, right-hand side, error norms) ----
+void * post_get(void *& slot, const DeviceOperator & op, const HostMesh & mesh, double penalty_factor, cudaStream_t stream);
+void post_destroy(void * p);
+int64_t post_n_boundary_faces(void * p);
+void post_boundary_points(void * p, const DeviceOperator & op, double * xyz_host, uint8_t * type_host, cudaStream_t stream);
+void post_set_boundary_values(void * p, const DeviceOperator & op, const double * values_host, cudaStream_t stream);
+void post_boundary_inhom_add(void * p, const DeviceOperator & op, const HostMesh & mesh, double sign, double * dst, cudaStream_t stream);
+void post_cell_points(void * p, const DeviceOperator & op, const HostMesh & mesh, int nq, double * xyz_host, cudaStream_t stream);
+void post_source_add(void * p, const DeviceOperator & op, const HostMesh & mesh, const double * f_host, double * dst, cudaStream_t stream);
+void post_l2_cells(void * p, const DeviceOperator & op, const HostMesh & mesh, int nq, const double * u, const double * exact_host, double * d_out, cudaStream_t stream);
+
 // ---- microbench.cu ----
 void fp64_peak(double * dfma_tflops, double * dmma_tflops);
 

@@ -1,6 +1,7 @@
 // Warp-specialised Cartesian vmult for n = 5 (k = 4): device side of cart_ws.hpp - the PTX run-time interface (named
 // barriers, mbarrier + 1-D bulk copies), the kernel wrapper, the device copy of the batch plan and the launch.
 // The CTA body itself lives in cart_ws.hpp and is also compiled for the CPU emulation (tests/cpp/ws_emulate.cpp).
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 

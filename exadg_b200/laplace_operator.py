@@ -209,6 +209,62 @@ class LaplaceOperator:
     def is_empty_locally(self):
         return self.n_cells_owned == 0
 
+    # -- inhomogeneous boundary data, right-hand side, error (operator_base.h:314-344; error_calculation.cpp) ------
+    def boundary_quadrature_points(self):
+        """(xyz [n_faces, (k+1)^2, 3], type [n_faces]) of the boundary faces of the owned cells."""
+        n = C.c_int64()
+        _check(_lib().exadg_b200_n_boundary_faces(self._h, C.byref(n)))
+        nq2 = (self.degree + 1) ** 2
+        xyz = np.zeros((n.value, nq2, 3))
+        bt = np.zeros(n.value, dtype=np.uint8)
+        _check(_lib().exadg_b200_boundary_quadrature_points(self._h, xyz.ctypes.data_as(C.c_void_p), bt.ctypes.data_as(C.c_void_p)))
+        return xyz, bt
+
+    def set_boundary_values(self, values):
+        """g at the quadrature points of Dirichlet faces, h at those of Neumann faces ([n_faces, (k+1)^2])."""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        _check(_lib().exadg_b200_set_boundary_values(self._h, v.ctypes.data_as(C.c_void_p)))
+
+    def rhs(self, dst):
+        self._order_after_torch()
+        _check(_lib().exadg_b200_rhs(self._h, _ptr(dst, self._n_local)))
+        self.synchronize()
+
+    def rhs_add(self, dst):
+        self._order_after_torch()
+        _check(_lib().exadg_b200_rhs_add(self._h, _ptr(dst, self._n_local)))
+        self.synchronize()
+
+    def evaluate(self, dst, src):
+        self._order_after_torch()
+        _check(_lib().exadg_b200_evaluate(self._h, _ptr(dst, self._n_local), _ptr(src, self._n_local)))
+        self.synchronize()
+
+    def evaluate_add(self, dst, src):
+        self._order_after_torch()
+        _check(_lib().exadg_b200_evaluate_add(self._h, _ptr(dst, self._n_local), _ptr(src, self._n_local)))
+        self.synchronize()
+
+    def cell_quadrature_points(self, n_q_points_1d):
+        xyz = np.zeros((self.n_cells_owned, n_q_points_1d ** 3, 3))
+        _check(_lib().exadg_b200_cell_quadrature_points(self._h, n_q_points_1d, xyz.ctypes.data_as(C.c_void_p)))
+        return xyz
+
+    def integrate_source_add(self, dst, f_at_quadrature_points):
+        """RHSOperator: dst += (f, phi_i), f at cell_quadrature_points(k + 1)."""
+        f = np.ascontiguousarray(f_at_quadrature_points, dtype=np.float64)
+        self._order_after_torch()
+        _check(_lib().exadg_b200_integrate_source_add(self._h, _ptr(dst, self._n_local), f.ctypes.data_as(C.c_void_p)))
+        self.synchronize()
+
+    def l2_error(self, u, exact_at_quadrature_points, relative=True):
+        """calculate_error with the L2 norm: exact solution at cell_quadrature_points(k + 3)."""
+        ex = np.ascontiguousarray(exact_at_quadrature_points, dtype=np.float64)
+        err = C.c_double()
+        self._order_after_torch()
+        _check(_lib().exadg_b200_l2_error(self._h, _ptr(u, self._n_local), ex.ctypes.data_as(C.c_void_p), int(relative), C.byref(err)))
+        return err.value
+
     # -- stream handling ---------------------------------------------------------------------------
     def synchronize(self):
         _check(_lib().exadg_b200_synchronize(self._h))

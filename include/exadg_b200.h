@@ -126,6 +126,30 @@ int exadg_b200_calculate_diagonal(exadg_b200_operator *op, double *diagonal);
 int exadg_b200_add_diagonal(exadg_b200_operator *op, double *diagonal);
 int exadg_b200_calculate_inverse_diagonal(exadg_b200_operator *op, double *diagonal);
 
+/* Inhomogeneous boundary data, right-hand side and error norms on the GPU.  The reference evaluates
+ * dealii::Function objects at quadrature points; the C ABI hands out the physical coordinates of its quadrature points and takes
+ * the function values back as HOST arrays (the binding evaluates BoundaryDescriptor / FieldFunctions there).
+ *   boundary faces of the owned cells, cell-major then face number; (k+1)^2 Gauss points per face, x fastest within the face:
+ *   xyz_host [n_faces][(k+1)^2][3], type_host [n_faces] (EXADG_B200_DIRICHLET / NEUMANN); values: g on Dirichlet faces, h on
+ *   Neumann faces (I/poisson/user_interface/boundary_descriptor.h) */
+int exadg_b200_n_boundary_faces(exadg_b200_operator *op, int64_t *n_faces);
+int exadg_b200_boundary_quadrature_points(exadg_b200_operator *op, double *xyz_host, uint8_t *type_host);
+int exadg_b200_set_boundary_values(exadg_b200_operator *op, const double *values_host);
+/* OperatorBase::rhs / rhs_add (operator_base.cpp:509-546): dst (+)= -(inhomogeneous boundary face integrals), exterior values per
+ * weak_boundary_conditions.h:72-134, 188-234 with OperatorType::inhomogeneous */
+int exadg_b200_rhs(exadg_b200_operator *op, double *dst);
+int exadg_b200_rhs_add(exadg_b200_operator *op, double *dst);
+/* OperatorBase::evaluate / evaluate_add (operator_base.cpp:548-606): homogeneous operator + inhomogeneous boundary integrals */
+int exadg_b200_evaluate(exadg_b200_operator *op, double *dst, const double *src);
+int exadg_b200_evaluate_add(exadg_b200_operator *op, double *dst, const double *src);
+/* Gauss(n_q_points_1d) points of the owned cells, xyz_host [owned][n_q^3][3], x fastest */
+int exadg_b200_cell_quadrature_points(exadg_b200_operator *op, int n_q_points_1d, double *xyz_host);
+/* RHSOperator (I/poisson/spatial_discretization/operator.cpp:414-423): dst += (f, phi_i), f_host = f at the Gauss(k+1) points */
+int exadg_b200_integrate_source_add(exadg_b200_operator *op, double *dst, const double *f_host);
+/* calculate_error (I/postprocessor/error_calculation.cpp:36-115): L2 norm of u - u_exact with Gauss(k+3), relative to the L2 norm
+ * of u_exact if `relative`; exact_host = u_exact at exadg_b200_cell_quadrature_points(op, k + 3, .); reduced over all ranks */
+int exadg_b200_l2_error(exadg_b200_operator *op, const double *u, const double *exact_host, int relative, double *error);
+
 /* JacobiPreconditioner::vmult (I/solvers_and_preconditioners/preconditioners/jacobi_preconditioner.h:50-62) */
 int exadg_b200_jacobi_vmult(exadg_b200_operator *op, double *dst, const double *src, const double *inverse_diagonal);
 

@@ -81,6 +81,16 @@ public:
     check(overlap ? exadg_b200_vmult_host_pipelined(op, dst, src) : exadg_b200_vmult_host(op, dst, src));
   }
 
+  // inhomogeneous boundary data (OperatorBase::rhs / rhs_add / evaluate / evaluate_add, operator_base.h:314-344): the binding
+  // evaluates its BoundaryDescriptor functions at boundary_quadrature_points() and hands the values to set_boundary_values()
+  std::int64_t n_boundary_faces() const { std::int64_t n = 0; check(exadg_b200_n_boundary_faces(op, &n)); return n; }
+  void boundary_quadrature_points(double * xyz, std::uint8_t * type) const { check(exadg_b200_boundary_quadrature_points(op, xyz, type)); }
+  void set_boundary_values(double const * values) const { check(exadg_b200_set_boundary_values(op, values)); }
+  void rhs(VectorType & dst) const { check(exadg_b200_rhs(op, dst.data())); }
+  void rhs_add(VectorType & dst) const { check(exadg_b200_rhs_add(op, dst.data())); }
+  void evaluate(VectorType & dst, VectorType const & src) const { check(exadg_b200_evaluate(op, dst.data(), src.data())); }
+  void evaluate_add(VectorType & dst, VectorType const & src) const { check(exadg_b200_evaluate_add(op, dst.data(), src.data())); }
+
   std::int64_t m() const { return n(); }
   std::int64_t n() const { return exadg_b200_n(op); }
   double el(unsigned int, unsigned int) const { throw std::runtime_error("Matrix-free does not allow for entry access"); }

@@ -91,6 +91,8 @@ struct HostRT
   void store_wait_all() { check_store(); }
 };
 
+static int g_dynamic = 0, g_counter = 0;
+
 struct Emu
 {
   HostMesh mesh;
@@ -131,7 +133,6 @@ int wse_halo_max(void * h) { return static_cast<Emu *>(h)->plan.HL; }
 int64_t wse_smem_bytes(void * h) { return (int64_t)ws_smem_bytes<N, NP>(static_cast<Emu *>(h)->plan.HL); }
 int wse_n_batches(void * h, int which) { Emu * E = static_cast<Emu *>(h); return which == 0 ? E->plan.n_batches : (which == 1 ? (int)E->interior.size() : (int)E->boundary.size()); }
 
-static int g_dynamic = 0, g_counter = 0;
 // 1: the CTAs claim their items from a work counter (the scheduling of the single-launch partitioned vmult)
 void wse_set_dynamic(int on) { g_dynamic = on; }
 
@@ -162,7 +163,7 @@ int wse_vmult(void * h, const double * src, const double * ghost, double * dst, 
     for (int t = 0; t < WsCfg<N, NP>::NT; ++t)
       threads.emplace_back([&, t]() {
         HostRT rt{&C, t};
-        if (E->mesh.n_ghost > 0) ws_cta<N, WSE_R, true, NP>(rt, E->T, A); else ws_cta<N, WSE_R, false, NP>(rt, E->T, A);
+        if (E->mesh.n_ghost > 0 || g_dynamic) ws_cta<N, WSE_R, true, NP>(rt, E->T, A); else ws_cta<N, WSE_R, false, NP>(rt, E->T, A);
       });
     for (auto & th : threads) th.join();
     pthread_barrier_destroy(&C.ba); pthread_barrier_destroy(&C.bc); for (int p = 0; p < NP; ++p) pthread_barrier_destroy(&C.bp[p]);
