@@ -276,6 +276,75 @@ def run_callers(args, op, src, dst, world, rank, barrier, dist):
                                        "peak_source": peak_src}}), flush=True)
 
 
+def callers_block(op, src, n_global, degree):
+    """Secondary figures inside the one JSON line (N=1): the callers of vmult on the same workload, device-timed with CUDA events on
+    the operator's stream (= torch's current stream), and a solve-level end-to-end figure (host rhs in, host solution out)."""
+    import torch
+    import exadg_b200
+    peak, _ = measured_peak()
+    out = {}
+
+    def timed(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3
+
+    b = op.initialize_dof_vector()
+    op.vmult(b, src)  # consistent right-hand side (the periodic operator is singular)
+    its = 20
+    solver = exadg_b200.KrylovSolverCG(op, None, exadg_b200.SolverData(its, 0.0, 0.0))
+
+    def cg_run(x):
+        try:
+            solver.solve(x, b)
+        except exadg_b200.ExaDGError:
+            pass  # max_iter reached on purpose: exactly `its` iterations
+
+    x = op.initialize_dof_vector()
+    cg_run(x)  # warm-up (work vectors)
+    x.zero_()
+    t = timed(lambda: cg_run(x))
+    b_alg = 16.0 + 16.0 + 48.0 + 24.0  # vmult + d.Ad + (x, g update with |g|^2) + d update
+    out["cg_iteration"] = {"ms": t / its * 1e3, "dofs_per_s": n_global * its / t, "iterations": its, "algorithmic_bytes_per_dof": b_alg,
+                           "hbm_frac": b_alg * n_global * its / t / 1e9 / peak,
+                           "what": "dealii::SolverCG restated (no preconditioner): vmult, d.Ad, fused x/g update with |g|^2, d update; one host read of the residual per iteration (ReductionControl::check)"}
+    ch = exadg_b200.ChebyshevSmoother(op, 5, 20.0, 20)
+    y = op.initialize_dof_vector()
+    ch.vmult(y, b)
+    reps = 5
+    t = timed(lambda: [ch.vmult(y, b) for _ in range(reps)])
+    b_alg = 4 * 16.0 + 3 * 8.0 + 4 * 7 * 8.0
+    out["chebyshev_application"] = {"ms": t / reps * 1e3, "dofs_per_s": n_global * reps / t, "algorithmic_bytes_per_dof": b_alg, "hbm_frac": b_alg * n_global * reps / t / 1e9 / peak,
+                                    "what": "ChebyshevSmoother(5 iterations, point Jacobi): 4 vmults + 5 fused update passes"}
+    # solve-level end to end: pinned host rhs -> H2D -> 20 CG iterations -> D2H of the solution
+    h_b = torch.empty(b.numel(), dtype=torch.float64).pin_memory()
+    h_b.copy_(b.cpu())
+    h_x = torch.empty(b.numel(), dtype=torch.float64).pin_memory()
+
+    def solve_e2e():
+        bb = h_b.cuda(non_blocking=True)
+        xx = torch.zeros_like(bb)
+        try:
+            exadg_b200.KrylovSolverCG(op, None, exadg_b200.SolverData(its, 0.0, 0.0)).solve(xx, bb)
+        except exadg_b200.ExaDGError:
+            pass
+        h_x.copy_(xx, non_blocking=True)
+        torch.cuda.synchronize()
+
+    solve_e2e()
+    t0 = time.perf_counter()
+    solve_e2e()
+    t = time.perf_counter() - t0
+    out["solve_e2e"] = {"ms": t * 1e3, "dofs_times_iterations_per_s": n_global * its / t, "iterations": its, "h2d_bytes": n_global * 8, "d2h_bytes": n_global * 8,
+                        "what": "host rhs (pinned) -> device, 20 CG iterations with all vectors resident, solution -> host: the transfers a Krylov solve actually pays, amortised over its iterations"}
+    del ch, solver, x, y, b
+    return out
+
+
 def run_gpu(args):
     import torch
     import exadg_b200
@@ -299,13 +368,13 @@ def run_gpu(args):
         n_sub, refine = GRIDS.get(world, (3, 5))
     deformation = 0.1 if args.mesh == "curvilinear" else 0.0
     kernel_selection = None
-    if world == 1 and degree == 4 and deformation == 0.0 and not args.no_tune and "EXADG_B200_CART_KERNEL" not in os.environ:
+    if world == 1 and degree == 4 and deformation == 0.0 and args.tune and "EXADG_B200_CART_KERNEL" not in os.environ:
         # the k=4 fast path has several validated kernels; pick the fastest on this box before anything is allocated here
         tuned = tune_k4_kernel(n_sub, refine)
         if tuned is not None:
             exadg_b200.cartesian_kernel(tuned[0])
             kernel_selection = {"chosen_variant": tuned[0], "ms_per_vmult_by_variant": tuned[1],
-                                "variants": "0 pipelined, 1 warp-specialised (default), 2 deeper producers, 3 four producer warps"}
+                                "variants": "0 pipelined, 1 warp-specialised 2 producer warps, 2 deeper producers, 3 four producer warps + setmaxnreg (library default), 4/5 warp-private"}
     op = exadg_b200.LaplaceOperator.hypercube(degree, n_sub, refine, 1, deformation, 2, (0,) * 6, 1.0, rank=rank, world=world)
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -441,14 +510,16 @@ def run_gpu(args):
         if op.is_cartesian_path:
             kernel = "cartesian"
             if degree == 4:
-                variant = exadg_b200.cartesian_kernel()
-                names = {1: "warp-specialised vmult_cartesian_ws_kernel<5,8,2 producer warps>", 2: "warp-specialised vmult_cartesian_ws_kernel<5,12,2 producer warps>",
-                         3: "warp-specialised vmult_cartesian_ws_kernel<5,4,4 producer warps, setmaxnreg>"}
-                kernel = names.get(variant, names[1]) if variant >= 1 else "pipelined vmult_cartesian_pipe_kernel<5>"
+                variant = op.get_kernel_variant()
+                names = {0: "pipelined vmult_cartesian_pipe_kernel<5>",
+                         1: "warp-specialised vmult_cartesian_ws_kernel<5,8,2 producer warps>", 2: "warp-specialised vmult_cartesian_ws_kernel<5,12,2 producer warps>",
+                         3: "warp-specialised vmult_cartesian_ws_kernel<5,4,4 producer warps, setmaxnreg> (library default)",
+                         4: "warp-private vmult_cartesian_wp_kernel<5,8,2 producer warps>", 5: "warp-private vmult_cartesian_wp_kernel<5,12,2 producer warps>"}
+                kernel = names.get(variant, str(variant))
                 if variant >= 1:
-                    key += "_ws"
-                    if world > 1:
-                        kernel += " for the interior batches, pipelined kernel for the batches with ghost neighbours"
+                    key += "_ws" if variant <= 3 else "_wp"
+                    if world > 1 and args.halo == "p2p":
+                        kernel += "; ONE launch per vmult: 64 CTAs export this rank's cells to the peers' ghost buffers over NVLink first, batches without ghost neighbours next (items claimed from a work counter), the producers acquire the peers' flags before the first batch that reads ghost cells"
         out = {"metric": METRIC if degree == 4 else METRIC.replace("k=4", "k=%d" % degree), "value": value, "unit": "DoFs/s", "n_gpus": world,
                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -463,6 +534,11 @@ def run_gpu(args):
                        "api": e2e_api, "sequential_dofs_per_s": n_global * e2e_steps / e2e_plain_s,
                        "pipelined_dofs_per_s": (n_global * e2e_steps / e2e_pipe_s) if e2e_pipe_s else None},
                "gpu_launches": launches, "clocks": clocks}
+        if world == 1 and not args.no_callers and deformation == 0.0:
+            try:
+                out["callers"] = callers_block(op, src, n_global, degree)
+            except Exception as e:  # secondary figures must not take the headline down
+                out["callers"] = {"error": str(e)[:200]}
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(degree, seconds=args.cpu_seconds, cells_1d=n_sub << refine)[0]
         if not args.no_fp64_peak:
@@ -492,7 +568,9 @@ def main():
     ap.add_argument("--mode", default="vmult", choices=["vmult", "cg", "chebyshev"], help="vmult = the headline metric; cg / chebyshev = secondary lines for the callers")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="ghost import transport for N>1")
     ap.add_argument("--e2e-api", default="auto", choices=["auto", "plain"], help="auto: also try the pipelined host-buffer entry point for the e2e figure (validated in a child process first)")
-    ap.add_argument("--no-tune", action="store_true", help="k=4: keep the default kernel instead of timing the validated variants in a child process first")
+    ap.add_argument("--tune", action="store_true", help="k=4: time the validated kernel variants in a child process first and use the fastest (default: the library's default kernel)")
+    ap.add_argument("--no-tune", action="store_true", help="(default behaviour, kept for older command lines)")
+    ap.add_argument("--no-callers", action="store_true", help="skip the secondary measurements of the callers (CG iteration, Chebyshev application, solve-level e2e)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-fp64-peak", action="store_true", help="skip the measured DFMA / DMMA rates")

@@ -46,11 +46,22 @@ __device__ __forceinline__ void finish_reduction(double v, double * partial, dou
   }
 }
 
+// All streaming kernels below move 16 bytes per access (double2; the vectors of the C ABI are 16-byte aligned, check_ptr in
+// c_api.cu) with two independent accesses per thread in flight; an odd tail element is handled by one thread.  The summation
+// order of the reductions is fixed by (grid, thread, element order) and therefore reproducible run to run.
+__device__ __forceinline__ double2 ld2(const double * p, int64_t i2) { return reinterpret_cast<const double2 *>(p)[i2]; }
+__device__ __forceinline__ void st2(double * p, int64_t i2, double2 v) { reinterpret_cast<double2 *>(p)[i2] = v; }
+
 __global__ void __launch_bounds__(RED_THREADS) dot_kernel(const double * __restrict__ a, const double * __restrict__ b, int64_t n, double * partial, double * result, int slot)
 {
-  double acc = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)RED_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * RED_THREADS) acc = fma(a[i], b[i], acc);
-  finish_reduction(acc, partial, result, slot);
+  double acc0 = 0.0, acc1 = 0.0;
+  const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * RED_THREADS;
+  for (int64_t i = blockIdx.x * (int64_t)RED_THREADS + threadIdx.x; i < n2; i += stride) {
+    const double2 x = ld2(a, i), y = ld2(b, i);
+    acc0 = fma(x.x, y.x, acc0); acc1 = fma(x.y, y.y, acc1);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) acc0 = fma(a[n - 1], b[n - 1], acc0);
+  finish_reduction(acc0 + acc1, partial, result, slot);
 }
 
 __global__ void __launch_bounds__(RED_THREADS) sum_kernel(const double * __restrict__ a, int64_t n, double * partial, double * result, int slot)
@@ -64,32 +75,50 @@ __global__ void __launch_bounds__(RED_THREADS) cg_update_x_g_kernel(double * __r
                                                                   int64_t n, double * partial, double * result, int slot, int num, int den)
 {
   const double alpha = result[num] / result[den];
-  double acc = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)RED_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * RED_THREADS) {
+  double acc0 = 0.0, acc1 = 0.0;
+  const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * RED_THREADS;
+  for (int64_t i = blockIdx.x * (int64_t)RED_THREADS + threadIdx.x; i < n2; i += stride) {
+    const double2 xi = ld2(x, i), di = ld2(d, i), gi = ld2(g, i), hi = ld2(h, i);
+    double2 xo, go;
+    xo.x = fma(alpha, di.x, xi.x); xo.y = fma(alpha, di.y, xi.y);
+    go.x = fma(alpha, hi.x, gi.x); go.y = fma(alpha, hi.y, gi.y);
+    st2(x, i, xo); st2(g, i, go);
+    acc0 = fma(go.x, go.x, acc0); acc1 = fma(go.y, go.y, acc1);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int64_t i = n - 1;
     x[i] = fma(alpha, d[i], x[i]);
     const double gi = fma(alpha, h[i], g[i]);
-    g[i] = gi;
-    acc = fma(gi, gi, acc);
+    g[i] = gi; acc0 = fma(gi, gi, acc0);
   }
-  finish_reduction(acc, partial, result, slot);
+  finish_reduction(acc0 + acc1, partial, result, slot);
 }
 
 __global__ void __launch_bounds__(RED_THREADS) jacobi_dot_kernel(double * __restrict__ z, const double * __restrict__ inv_diag, const double * __restrict__ g, int64_t n,
                                                                double * partial, double * result, int slot)
 {
-  double acc = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)RED_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * RED_THREADS) {
-    const double gi = g[i], zi = inv_diag[i] * gi;
-    z[i] = zi;
-    acc = fma(gi, zi, acc);
+  double acc0 = 0.0, acc1 = 0.0;
+  const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * RED_THREADS;
+  for (int64_t i = blockIdx.x * (int64_t)RED_THREADS + threadIdx.x; i < n2; i += stride) {
+    const double2 gi = ld2(g, i), pi = ld2(inv_diag, i);
+    double2 zi; zi.x = pi.x * gi.x; zi.y = pi.y * gi.y;
+    st2(z, i, zi);
+    acc0 = fma(gi.x, zi.x, acc0); acc1 = fma(gi.y, zi.y, acc1);
   }
-  finish_reduction(acc, partial, result, slot);
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) { const int64_t i = n - 1; const double gi = g[i], zi = inv_diag[i] * gi; z[i] = zi; acc0 = fma(gi, zi, acc0); }
+  finish_reduction(acc0 + acc1, partial, result, slot);
 }
 
 __global__ void cg_update_d_kernel(double * __restrict__ d, const double * __restrict__ z, int64_t n, const double * result, int num, int den)
 {
   const double beta = result[num] / result[den];
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = fma(beta, d[i], -z[i]);
+  const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += stride) {
+    const double2 di = ld2(d, i), zi = ld2(z, i);
+    double2 o; o.x = fma(beta, di.x, -zi.x); o.y = fma(beta, di.y, -zi.y);
+    st2(d, i, o);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) d[n - 1] = fma(beta, d[n - 1], -z[n - 1]);
 }
 
 __global__ void axpby_kernel(double a, const double * __restrict__ x, double b, double * __restrict__ y, int64_t n)
@@ -122,8 +151,16 @@ __global__ void cheb_first_kernel(double * __restrict__ x, double * __restrict__
 __global__ void cheb_step_kernel(double * __restrict__ x, double * __restrict__ xold, const double * __restrict__ inv_diag, const double * __restrict__ b, const double * __restrict__ r,
                                  double f1, double f2, int64_t n)
 {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const double xi = x[i];
+  const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += stride) {
+    const double2 xi = ld2(x, i), xo = ld2(xold, i), pi = ld2(inv_diag, i), bi = ld2(b, i), ri = ld2(r, i);
+    double2 o;
+    o.x = xi.x + f1 * (xi.x - xo.x) + f2 * pi.x * (bi.x - ri.x);
+    o.y = xi.y + f1 * (xi.y - xo.y) + f2 * pi.y * (bi.y - ri.y);
+    st2(x, i, o); st2(xold, i, xi);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int64_t i = n - 1; const double xi = x[i];
     x[i] = xi + f1 * (xi - xold[i]) + f2 * inv_diag[i] * (b[i] - r[i]);
     xold[i] = xi;
   }

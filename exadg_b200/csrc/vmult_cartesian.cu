@@ -354,6 +354,188 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
 
 
 // =====================================================================================================
+// Line variant (used for n = 6, 7, 8; k = 5, 6, 7).  A plane of a cell in registers costs 2 n^2 doubles: 192 / 242 / 255 registers
+// (+ 680 bytes of spills) for n = 6 / 7 / 8, which left 3 - 9 warps per SM to the plane kernel above (round 1: 14 / 13 / 8 % of
+// the HBM roofline).  Here a thread owns ONE line of a cell per sweep (2 n doubles in registers), a CTA of B n^2 threads a batch
+// of B cells, every sweep goes through shared memory:
+//     T = sum_d K_d u (line by line, face terms from the traces of the neighbour lines)  ->  T <- M_z M_y M_x T
+// 14 shared-memory accesses per DoF against 6 n + 18 FMAs per DoF - at n >= 6 a better ratio than the plane kernel has at n = 5 -
+// and 18 - 32 resident warps per SM.  Rows are padded to an odd stride so that consecutive lanes (consecutive lines) never share a
+// bank in any of the three sweep directions.
+// =====================================================================================================
+template<int N> struct LineCfg { static constexpr int B = 16; static constexpr int NT = B * N * N; static constexpr int RS = N | 1; static constexpr int CS = RS * N * N; };
+
+template<int N>
+__global__ void __launch_bounds__(LineCfg<N>::NT, 1) vmult_cartesian_line_kernel(const __grid_constant__ CartTables<N> T, const CartArgs A)
+{
+  constexpr int B = LineCfg<N>::B, NT = LineCfg<N>::NT, RS = LineCfg<N>::RS, CS = LineCfg<N>::CS;
+  constexpr int N2 = N * N, N3 = N2 * N;
+  extern __shared__ __align__(128) double smem[];
+  double * U = smem;                   // [B][N][N][RS] src values (x fastest, rows padded to RS)
+  double * Tt = U + B * CS;            // [B][N][N][RS] accumulated result
+  double * GN = Tt + B * CS;           // [2][B][N2] end derivatives of the batch's own lines of the current direction
+  double * HV = GN + 2 * B * N2;       // [H][N2] end values of out-of-batch neighbours
+  double * HG = HV + (size_t)A.H * N2; // [H][N2] end derivatives of out-of-batch neighbours
+  int2 * hlS = reinterpret_cast<int2 *>(HG + (size_t)A.H * N2); // [H]
+  int * nbS = reinterpret_cast<int *>(hlS + A.H);               // [B][6]
+  int * slotS = nbS + B * 6;                                     // [B][6]
+
+  const int t = threadIdx.x, c = t / N2, ab = t % N2, a = ab % N, b = ab / N;
+  const int batch = A.batches ? A.batches[blockIdx.x] : (int)blockIdx.x;
+  const int64_t b0 = (int64_t)batch * B;
+  const int nvalid = (int)min((int64_t)B, A.n_owned - b0);
+  const bool valid = c < nvalid;
+
+  // ---- stage the batch (coalesced loads, 8 in flight per thread), its neighbour table and the halo list ----
+  const int cnt = A.halo_cnt[batch];
+  for (int i = t; i < B * 6; i += NT) { nbS[i] = (i / 6 < nvalid) ? A.nb[b0 * 6 + i] : -1; slotS[i] = -1; }
+  for (int i = t; i < cnt; i += NT) hlS[i] = A.halo[(size_t)batch * A.H + i];
+  {
+    constexpr int UNR = 8;
+    for (int i0 = t; i0 < nvalid * N3; i0 += NT * UNR) {
+      double v[UNR];
+#pragma unroll
+      for (int q = 0; q < UNR; ++q) { const int i = i0 + q * NT; v[q] = (i < nvalid * N3) ? A.src[b0 * N3 + i] : 0.0; }
+#pragma unroll
+      for (int q = 0; q < UNR; ++q) {
+        const int i = i0 + q * NT;
+        if (i < nvalid * N3) { const int cc = i / N3, rem = i % N3; U[cc * CS + (rem / N) * RS + rem % N] = v[q]; }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- traces of the out-of-batch neighbours: one line per item, UNR items x n loads in flight per thread (register budget) ----
+  {
+    constexpr int UNR = (N >= 8) ? 2 : (N == 7 ? 3 : 4);
+    for (int it0 = t; it0 < cnt * N2; it0 += NT * UNR) {
+      double x[UNR][N]; int sp[UNR];
+#pragma unroll
+      for (int q = 0; q < UNR; ++q) {
+        const int item = it0 + q * NT;
+        sp[q] = 0;
+        if (item < cnt * N2) {
+          const int e = item / N2, lab = item % N2, la = lab % N, lb = lab / N;
+          const int2 h = hlS[e];
+          const int f = h.x & 7, d = f >> 1;
+          sp[q] = (f & 1) ^ 1; // the neighbour is entered through its face (d, sp)
+          const double * un = (h.y < A.n_owned) ? A.src + (size_t)h.y * N3 : A.ghost + (size_t)(h.y - A.n_owned) * N3;
+          const int sd = (d == 0) ? 1 : (d == 1 ? N : N2);
+          const int s1 = (d == 0) ? N : 1, s2 = (d == 2) ? N : N2;
+          const double * line = un + la * s1 + lb * s2;
+#pragma unroll
+          for (int i = 0; i < N; ++i) x[q][i] = line[i * sd];
+        } else {
+#pragma unroll
+          for (int i = 0; i < N; ++i) x[q][i] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < UNR; ++q) {
+        const int item = it0 + q * NT;
+        if (item < cnt * N2) {
+          const int e = item / N2, lab = item % N2;
+          double g = 0.0;
+#pragma unroll
+          for (int i = 0; i < N; ++i) g = fma(sp[q] ? T.fd[1][i] : T.fd[0][i], x[q][i], g);
+          HV[e * N2 + lab] = sp[q] ? x[q][N - 1] : x[q][0];
+          HG[e * N2 + lab] = g;
+          if (lab == 0) { const int2 h = hlS[e]; slotS[(h.x >> 3) * 6 + (h.x & 7)] = e; }
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- three sweeps: thread (c, ab) owns line ab of cell c in direction d ----
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    // offset of the line's first node and stride along it in the padded cell
+    const int base = c * CS + ((d == 0) ? (a + N * b) * RS : (d == 1 ? a + b * N * RS : a + b * RS));
+    const int sd = (d == 0) ? 1 : (d == 1 ? RS : N * RS);
+    double x[N], y[N];
+    if (valid) {
+      double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+      for (int m = 0; m < N; ++m) { x[m] = U[base + m * sd]; g0 = fma(T.fd[0][m], x[m], g0); g1 = fma(T.fd[1][m], x[m], g1); }
+      GN[(0 * B + c) * N2 + ab] = g0;
+      GN[(1 * B + c) * N2 + ab] = g1;
+#pragma unroll
+      for (int r = 0; r < N; ++r) {
+        double v = 0.0;
+#pragma unroll
+        for (int m = 0; m < N; ++m) v = fma(T.G[d][r * N + m], x[m], v);
+        y[r] = v;
+      }
+    }
+    __syncthreads(); // end derivatives of this direction visible
+    if (valid) {
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        const int f = 2 * d + side;
+        const int nbl = nbS[c * 6 + f] - (int)b0;
+        const bool inb = (nbl >= 0 && nbl < nvalid);
+        double vn, gn;
+        if (inb) {
+          const int endn = side ? 0 : N - 1; // the neighbour's end node facing us
+          vn = U[base - c * CS + nbl * CS + endn * sd];
+          gn = GN[((side ^ 1) * B + nbl) * N2 + ab];
+        } else {
+          const int slot = slotS[c * 6 + f];
+          vn = HV[slot * N2 + ab]; gn = HG[slot * N2 + ab];
+        }
+        const double tt = fma(side ? 0.5 : -0.5, gn, T.tau_hat[d] * vn);
+#pragma unroll
+        for (int m = 0; m < N; ++m) { y[m] = fma(T.P[d][side][m], vn, y[m]); y[m] = fma(T.Q[d][side][m], tt, y[m]); }
+      }
+      if (d == 0) {
+#pragma unroll
+        for (int m = 0; m < N; ++m) Tt[base + m * sd] = y[m];
+      } else if (d == 1) {
+#pragma unroll
+        for (int m = 0; m < N; ++m) Tt[base + m * sd] += y[m];
+      } else {
+        // last direction: complete the sum and apply the mass matrix along z in place (this thread owns the whole line)
+#pragma unroll
+        for (int m = 0; m < N; ++m) x[m] = Tt[base + m * sd] + y[m];
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+          double v = 0.0;
+#pragma unroll
+          for (int m = 0; m < N; ++m) v = fma(T.M[r * N + m], x[m], v);
+          Tt[base + r * sd] = v;
+        }
+      }
+    }
+    __syncthreads(); // GN is reused by the next direction; the lines of the next direction cross these
+  }
+  // ---- mass matrices along x, then y (in place, line by line) ----
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const int base = c * CS + ((d == 0) ? (a + N * b) * RS : a + b * N * RS);
+    const int sd = (d == 0) ? 1 : RS;
+    if (valid) {
+      double x[N];
+#pragma unroll
+      for (int m = 0; m < N; ++m) x[m] = Tt[base + m * sd];
+#pragma unroll
+      for (int r = 0; r < N; ++r) {
+        double v = 0.0;
+#pragma unroll
+        for (int m = 0; m < N; ++m) v = fma(T.M[r * N + m], x[m], v);
+        Tt[base + r * sd] = v;
+      }
+    }
+    __syncthreads();
+  }
+  // ---- coalesced store ----
+  for (int i = t; i < nvalid * N3; i += NT) {
+    const int cc = i / N3, rem = i % N3;
+    const double v = Tt[cc * CS + (rem / N) * RS + rem % N];
+    if (A.add) A.dst[b0 * N3 + i] += v; else A.dst[b0 * N3 + i] = v;
+  }
+}
+
+// =====================================================================================================
 // Pipelined variant (used for n = 5): persistent CTAs of 4 warps on 24-cell batches.
 //  * 24 cells x 5 planes = 120 plane threads = 4 warps: one warp per SM sub-partition, so the FP64 pipes of the
 //    four sub-partitions carry equal work (5-warp CTAs load them 2:1:1:1 and stall at every barrier);
@@ -766,7 +948,7 @@ struct CartPlan
   int2 * d_halo = nullptr; int32_t * d_cnt = nullptr;
   int32_t * d_interior = nullptr, * d_boundary = nullptr; int n_interior = 0, n_boundary = 0;
   int32_t * d_ordered = nullptr; // interior batches, then the batches with ghost neighbours (single-launch partitioned vmult)
-  size_t smem = 0;
+  size_t smem = 0, smem_line = 0; // smem_line: line kernel (n >= 6), 0 if it does not apply
   std::vector<char> tables; // CartTables<n> of this operator (depends on h and tau)
   // pipelined kernel (n = 5)
   bool pipe = false; int HL = 0, HD = 0, n_sm = 148; int4 * d_cnt4 = nullptr; int pipe_ctas_per_sm = 1;
@@ -832,6 +1014,23 @@ void launch_n(const DeviceOperator & op, const CartPlan & plan, double * dst, co
   if (list) { A.batches = list; A.n_items = n_list; }
   if (A.n_items == 0) return;
   vmult_cartesian_kernel<N><<<A.n_items, B * N, plan.smem, stream>>>(T, A);
+  CUDA_CHECK(cudaGetLastError());
+}
+template<int N>
+void launch_line(const DeviceOperator & op, const CartPlan & plan, double * dst, const double * src, bool add, int which, cudaStream_t stream, const int32_t * list = nullptr,
+                 int n_list = 0)
+{
+  const CartTables<N> & T = *reinterpret_cast<const CartTables<N> *>(plan.tables.data());
+  if (first_use_on_device((const void *)vmult_cartesian_line_kernel<N>))
+    CUDA_CHECK(cudaFuncSetAttribute(vmult_cartesian_line_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+  CartArgs A;
+  A.nb = op.nb; A.halo = plan.d_halo; A.halo_cnt = plan.d_cnt; A.src = src; A.ghost = op.ghost; A.dst = dst;
+  A.n_owned = op.n_owned; A.H = plan.H; A.add = add ? 1 : 0;
+  A.batches = which == 0 ? nullptr : (which == 1 ? plan.d_interior : plan.d_boundary);
+  A.n_items = which == 0 ? plan.n_batches : (which == 1 ? plan.n_interior : plan.n_boundary);
+  if (list) { A.batches = list; A.n_items = n_list; }
+  if (A.n_items == 0) return;
+  vmult_cartesian_line_kernel<N><<<A.n_items, LineCfg<N>::NT, plan.smem_line, stream>>>(T, A);
   CUDA_CHECK(cudaGetLastError());
 }
 template<int N>
@@ -936,6 +1135,11 @@ static size_t plan_create(DeviceOperator & op, const HostMesh & mesh, bool allow
   }
   const int N2 = N * N, PS = N2 | 1, CS = N * PS;
   if (!P.pipe) P.smem = ((size_t)2 * P.B * CS + (size_t)P.B * 2 * N2 + (size_t)2 * P.H * N2) * sizeof(double) + (size_t)P.H * sizeof(int2) + (size_t)P.B * 12 * sizeof(int) + 16;
+  if (N >= 6 && P.B == 16 && !getenv("EXADG_B200_NO_LINE")) {
+    const int RS = N | 1;
+    const size_t sl = ((size_t)2 * P.B * RS * N2 + (size_t)2 * P.B * N2 + (size_t)2 * P.H * N2) * sizeof(double) + (size_t)P.H * sizeof(int2) + (size_t)P.B * 12 * sizeof(int) + 16;
+    if (sl <= 227 * 1024 - 1024) P.smem_line = sl;
+  }
   if (P.smem > 227 * 1024 - 1024) { delete Pp; return 0; } // does not fit: caller falls back to the general kernel
   std::vector<int2> flat((size_t)P.n_batches * P.H, make_int2(0, 0));
   std::vector<int32_t> cnt(P.n_batches);
@@ -1042,9 +1246,9 @@ static void launch_cart(const DeviceOperator & op, double * dst, const double * 
       else launch_n<5>(op, *plan, dst, src, add, which, stream, list, n_list);
       break;
     }
-    case 6: launch_n<6>(op, *plan, dst, src, add, which, stream, list, n_list); break;
-    case 7: launch_n<7>(op, *plan, dst, src, add, which, stream, list, n_list); break;
-    case 8: launch_n<8>(op, *plan, dst, src, add, which, stream, list, n_list); break;
+    case 6: if (plan->smem_line) launch_line<6>(op, *plan, dst, src, add, which, stream, list, n_list); else launch_n<6>(op, *plan, dst, src, add, which, stream, list, n_list); break;
+    case 7: if (plan->smem_line) launch_line<7>(op, *plan, dst, src, add, which, stream, list, n_list); else launch_n<7>(op, *plan, dst, src, add, which, stream, list, n_list); break;
+    case 8: if (plan->smem_line) launch_line<8>(op, *plan, dst, src, add, which, stream, list, n_list); else launch_n<8>(op, *plan, dst, src, add, which, stream, list, n_list); break;
     default: throw std::runtime_error("Cartesian fast path supports degrees 1..7");
   }
 }
