@@ -36,6 +36,7 @@ EXPORTED_SYMBOLS = [
     "exadg_b200_set_kernel_variant", "exadg_b200_get_kernel_variant",
     "exadg_b200_n_boundary_faces", "exadg_b200_boundary_quadrature_points", "exadg_b200_set_boundary_values", "exadg_b200_rhs", "exadg_b200_rhs_add",
     "exadg_b200_evaluate", "exadg_b200_evaluate_add", "exadg_b200_cell_quadrature_points", "exadg_b200_integrate_source_add", "exadg_b200_l2_error",
+    "exadg_b200_subtract_mean_value",
 ]
 
 
@@ -81,6 +82,7 @@ def load_library():
         getattr(L, name).restype = i64
         getattr(L, name).argtypes = [vp]
     L.exadg_b200_is_cartesian_path.argtypes = [vp]
+    L.exadg_b200_subtract_mean_value.argtypes = [vp, dp]
     L.exadg_b200_n_boundary_faces.argtypes = [vp, C.POINTER(i64)]
     L.exadg_b200_boundary_quadrature_points.argtypes = [vp, vp, vp]
     L.exadg_b200_set_boundary_values.argtypes = [vp, vp]

@@ -794,6 +794,22 @@ int exadg_b200_calculate_inverse_diagonal(exadg_b200_operator * op, double * d)
 }
 
 
+/* dealii::VectorTools::subtract_mean_value as used for the singular pressure-Poisson system (SURVEY 8 f-2;
+ * incompressible_navier_stokes/time_integration/time_int_bdf_dual_splitting.cpp:655-656, compute_eigenvalues.h:52-53): global mean over all ranks */
+int exadg_b200_subtract_mean_value(exadg_b200_operator * op, double * vec)
+{
+  return guarded([&]() {
+    if (!op) throw std::invalid_argument("null operator");
+    require_self_contained(op, "exadg_b200_subtract_mean_value");
+    check_ptr(vec, "vec");
+    sum(op->red, 4, vec, op->n_local, op->stream); op->launches++;
+    allreduce(op, op->red.result + 4, 1);
+    const double mean = read_scalar(op, 4) / (double)op->dev.n_global_dofs;
+    add_scalar(vec, -mean, op->n_local, op->stream); op->launches++;
+    return EXADG_B200_OK;
+  });
+}
+
 /* ---- inhomogeneous boundary data, right-hand side, error norms ---- */
 static void * post_of(exadg_b200_operator * op) { return post_get(op->post, op->dev, op->mesh, 0.0, op->stream); }
 

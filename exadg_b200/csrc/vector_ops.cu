@@ -1,5 +1,7 @@
 #include "vector_ops.cuh"
 
+#include <algorithm>
+
 #include "operator.cuh"
 
 namespace exadg_b200
@@ -174,6 +176,45 @@ __global__ void add_scalar_kernel(double * __restrict__ x, double a, int64_t n)
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] += a;
 }
 
+// one CTA per cell; three tensor sweeps through shared memory.  PROLONG: in = coarse (nc^3), out = fine (nf^3), matrix I;
+// otherwise in = fine, out = coarse, matrix I^T.  Fixed summation order.
+template<bool PROLONG>
+__global__ void __launch_bounds__(128) transfer_kernel(const TransferTable t, double * __restrict__ out, const double * __restrict__ in, int64_t n_cells)
+{
+  __shared__ double A[512], B[512];
+  const int ni = PROLONG ? t.nc : t.nf, no = PROLONG ? t.nf : t.nc;
+  for (int64_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
+    const double * src = in + cell * ni * ni * ni;
+    for (int i = threadIdx.x; i < ni * ni * ni; i += blockDim.x) A[i] = src[i];
+    __syncthreads();
+    // x: B[o, j, k] = sum_i M[o][i] A[i, j, k]      (extents: no x ni x ni)
+    for (int e = threadIdx.x; e < no * ni * ni; e += blockDim.x) {
+      const int o = e % no, jk = e / no;
+      double v = 0.0;
+      for (int i = 0; i < ni; ++i) v = fma(PROLONG ? t.I[o * t.nc + i] : t.I[i * t.nc + o], A[i + ni * jk], v);
+      B[e] = v;
+    }
+    __syncthreads();
+    // y: A[o1, o, k] = sum_j M[o][j] B[o1, j, k]    (no x no x ni)
+    for (int e = threadIdx.x; e < no * no * ni; e += blockDim.x) {
+      const int o1 = e % no, o = (e / no) % no, k = e / (no * no);
+      double v = 0.0;
+      for (int j = 0; j < ni; ++j) v = fma(PROLONG ? t.I[o * t.nc + j] : t.I[j * t.nc + o], B[o1 + no * (j + ni * k)], v);
+      A[e] = v;
+    }
+    __syncthreads();
+    // z: out[o1, o2, o] += sum_k M[o][k] A[o1, o2, k]
+    double * dst = out + cell * no * no * no;
+    for (int e = threadIdx.x; e < no * no * no; e += blockDim.x) {
+      const int o12 = e % (no * no), o = e / (no * no);
+      double v = 0.0;
+      for (int k = 0; k < ni; ++k) v = fma(PROLONG ? t.I[o * t.nc + k] : t.I[k * t.nc + o], A[o12 + no * no * k], v);
+      dst[e] += v;
+    }
+    __syncthreads();
+  }
+}
+
 inline unsigned ew_grid(int64_t n) { const int64_t g = (n + 255) / 256; return (unsigned)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g)); }
 inline unsigned red_grid(int64_t n) { const int64_t g = (n + RED_THREADS - 1) / RED_THREADS; return (unsigned)(g < 1 ? 1 : (g > RED_BLOCKS ? RED_BLOCKS : g)); }
 } // namespace
@@ -193,6 +234,10 @@ void reducer_free(Reducer & r)
 
 void dot(const Reducer & r, int slot, const double * a, const double * b, int64_t n, cudaStream_t s)
 { dot_kernel<<<red_grid(n), RED_THREADS, 0, s>>>(a, b, n, r.partial, r.result, slot); }
+void prolongate_add(const TransferTable & t, double * fine, const double * coarse, int64_t n_cells, cudaStream_t s)
+{ if (n_cells > 0) transfer_kernel<true><<<(unsigned)std::min<int64_t>(n_cells, 148 * 16), 128, 0, s>>>(t, fine, coarse, n_cells); }
+void restrict_add(const TransferTable & t, double * coarse, const double * fine, int64_t n_cells, cudaStream_t s)
+{ if (n_cells > 0) transfer_kernel<false><<<(unsigned)std::min<int64_t>(n_cells, 148 * 16), 128, 0, s>>>(t, coarse, fine, n_cells); }
 void sum(const Reducer & r, int slot, const double * a, int64_t n, cudaStream_t s)
 { sum_kernel<<<red_grid(n), RED_THREADS, 0, s>>>(a, n, r.partial, r.result, slot); }
 void cg_update_x_g(const Reducer & r, int slot, int num, int den, double * x, const double * d, double * g, const double * h, int64_t n, cudaStream_t s)

@@ -48,6 +48,12 @@ void cheb_step(double * x, double * xold, const double * inv_diag, const double 
 // start vector of PreconditionChebyshev's eigenvalue estimate: (global index mod 11)
 void fill_mod11(double * x, int64_t global_offset, int64_t n, cudaStream_t s);
 void add_scalar(double * x, double a, int64_t n, cudaStream_t s);
+// polynomial transfer between FE_DGQ(k_fine) and FE_DGQ(k_coarse) on the same cells (dealii::MGTwoLevelTransfer, p-transfer of
+// I/solvers_and_preconditioners/multigrid/transfer.cpp:28-69): prolongation = embedding (coarse Lagrange basis evaluated at the fine
+// Gauss-Lobatto nodes, tensor product of the 1-D matrix I[nf][nc]), restriction = its transpose; both add into dst
+struct TransferTable { int nf, nc; double I[8 * 8]; };
+void prolongate_add(const TransferTable & t, double * fine, const double * coarse, int64_t n_cells, cudaStream_t s);
+void restrict_add(const TransferTable & t, double * coarse, const double * fine, int64_t n_cells, cudaStream_t s);
 // sum of entries -> result[slot]
 void sum(const Reducer & r, int slot, const double * a, int64_t n, cudaStream_t s);
 

@@ -209,6 +209,12 @@ class LaplaceOperator:
     def is_empty_locally(self):
         return self.n_cells_owned == 0
 
+    def subtract_mean_value(self, vec):
+        """dealii::VectorTools::subtract_mean_value (global mean): consistency of the singular system (operator_is_singular)."""
+        self._order_after_torch()
+        _check(_lib().exadg_b200_subtract_mean_value(self._h, _ptr(vec, self._n_local)))
+        self.synchronize()
+
     # -- inhomogeneous boundary data, right-hand side, error (operator_base.h:314-344; error_calculation.cpp) ------
     def boundary_quadrature_points(self):
         """(xyz [n_faces, (k+1)^2, 3], type [n_faces]) of the boundary faces of the owned cells."""

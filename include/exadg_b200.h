@@ -126,6 +126,13 @@ int exadg_b200_calculate_diagonal(exadg_b200_operator *op, double *diagonal);
 int exadg_b200_add_diagonal(exadg_b200_operator *op, double *diagonal);
 int exadg_b200_calculate_inverse_diagonal(exadg_b200_operator *op, double *diagonal);
 
+/* dealii::VectorTools::subtract_mean_value on a device vector (global mean over all ranks): what the callers of a singular
+ * operator (operator_is_singular, e.g. the pressure Poisson operator of the dual splitting scheme without pressure Dirichlet
+ * boundary) apply to the right-hand side to make the system consistent
+ * (I/incompressible_navier_stokes/time_integration/time_int_bdf_dual_splitting.cpp:655-656) and to the start vector of the
+ * eigenvalue estimate (I/solvers_and_preconditioners/utilities/compute_eigenvalues.h:52-53) */
+int exadg_b200_subtract_mean_value(exadg_b200_operator *op, double *vec);
+
 /* Inhomogeneous boundary data, right-hand side and error norms on the GPU.  The reference evaluates
  * dealii::Function objects at quadrature points; the C ABI hands out the physical coordinates of its quadrature points and takes
  * the function values back as HOST arrays (the binding evaluates BoundaryDescriptor / FieldFunctions there).

@@ -91,6 +91,9 @@ public:
   void evaluate(VectorType & dst, VectorType const & src) const { check(exadg_b200_evaluate(op, dst.data(), src.data())); }
   void evaluate_add(VectorType & dst, VectorType const & src) const { check(exadg_b200_evaluate_add(op, dst.data(), src.data())); }
 
+  // dealii::VectorTools::subtract_mean_value for the singular (pressure Poisson) system
+  void subtract_mean_value(VectorType & v) const { check(exadg_b200_subtract_mean_value(op, v.data())); }
+
   std::int64_t m() const { return n(); }
   std::int64_t n() const { return exadg_b200_n(op); }
   double el(unsigned int, unsigned int) const { throw std::runtime_error("Matrix-free does not allow for entry access"); }

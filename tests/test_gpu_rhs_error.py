@@ -90,3 +90,25 @@ def test_operator_is_singular_follows_the_boundary_conditions():
     assert exadg_b200.LaplaceOperator.hypercube(2, 1, 1).operator_is_singular()                      # all-periodic box
     assert exadg_b200.LaplaceOperator.hypercube(2, 1, 1, boundary=(2,) * 6).operator_is_singular()   # pure Neumann
     assert not exadg_b200.LaplaceOperator.hypercube(2, 1, 1, boundary=SINE_BC).operator_is_singular()
+
+
+def test_singular_pressure_poisson_system_is_solved_after_subtracting_the_mean():
+    """SURVEY 8 f-2: the pressure Poisson operator without Dirichlet boundary is singular (operator_projection_methods.cpp:88-153);
+    its callers subtract the mean of the right-hand side (time_int_bdf_dual_splitting.cpp:655-656) and CG then converges to the
+    mean-free solution.  Periodic box, k = 3, Jacobi-preconditioned CG as configured for the pressure solve."""
+    import exadg_b200
+    op = exadg_b200.LaplaceOperator.hypercube(3, 1, 2)
+    assert op.operator_is_singular()
+    ref = OracleOperator(3, 1, 2)
+    rng = np.random.default_rng(5)
+    b = torch.from_numpy(rng.uniform(-1, 1, ref.n_dofs) + 0.3).cuda()   # inconsistent: mean != 0 is not in the range of A
+    op.subtract_mean_value(b)
+    assert abs(b.sum().item()) < 1e-9
+    x = op.initialize_dof_vector()
+    its = exadg_b200.KrylovSolverCG(op, exadg_b200.JacobiPreconditioner(op), exadg_b200.SolverData(2000, 1e-20, 1e-8)).solve(x, b)
+    assert 0 < its < 2000
+    r = op.initialize_dof_vector()
+    op.vmult(r, x)
+    assert ((r - b).norm() / b.norm()).item() < 1e-7
+    op.subtract_mean_value(x)   # adjust_pressure_level_if_undefined: mean-free representative
+    assert abs(x.sum().item()) < 1e-8 * x.abs().sum().item()
