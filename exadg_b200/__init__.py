@@ -37,6 +37,8 @@ EXPORTED_SYMBOLS = [
     "exadg_b200_n_boundary_faces", "exadg_b200_boundary_quadrature_points", "exadg_b200_set_boundary_values", "exadg_b200_rhs", "exadg_b200_rhs_add",
     "exadg_b200_evaluate", "exadg_b200_evaluate_add", "exadg_b200_cell_quadrature_points", "exadg_b200_integrate_source_add", "exadg_b200_l2_error",
     "exadg_b200_subtract_mean_value",
+    "exadg_b200_multigrid_levels", "exadg_b200_multigrid_create", "exadg_b200_multigrid_destroy", "exadg_b200_multigrid_vmult", "exadg_b200_multigrid_info",
+    "exadg_b200_multigrid_smoother", "exadg_b200_cg_solve_multigrid",
 ]
 
 
@@ -113,6 +115,13 @@ def load_library():
     L.exadg_b200_chebyshev_set_interval.argtypes = [vp, C.c_double, C.c_double]
     L.exadg_b200_chebyshev_vmult.argtypes = [vp, dp, dp]
     L.exadg_b200_chebyshev_step.argtypes = [vp, dp, dp]
+    L.exadg_b200_multigrid_levels.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.exadg_b200_multigrid_create.argtypes = [C.c_int, C.POINTER(vp), C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(vp)]
+    L.exadg_b200_multigrid_destroy.argtypes = [vp]
+    L.exadg_b200_multigrid_vmult.argtypes = [vp, dp, dp]
+    L.exadg_b200_multigrid_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(i64), C.POINTER(i64)]
+    L.exadg_b200_multigrid_smoother.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.exadg_b200_cg_solve_multigrid.argtypes = [vp, dp, dp, vp, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
     L.exadg_b200_set_nccl_comm.argtypes = [vp, vp]
     L.exadg_b200_nccl_unique_id.argtypes = [C.c_char_p]
     L.exadg_b200_nccl_init.argtypes = [vp, C.c_char_p]
@@ -136,8 +145,8 @@ def load_library():
     return L
 
 
-from .laplace_operator import (ChebyshevSmoother, ExaDGError, JacobiPreconditioner, KrylovSolverCG, PartitionPlan,  # noqa: E402
-                               LaplaceOperator, SolverData, cartesian_kernel, fp64_peak, host_pipeline_plan)
+from .laplace_operator import (ChebyshevSmoother, ExaDGError, JacobiPreconditioner, KrylovSolverCG, MultigridPreconditioner, PartitionPlan,  # noqa: E402
+                               LaplaceOperator, SolverData, cartesian_kernel, fp64_peak, host_pipeline_plan, multigrid_levels)
 
 __all__ = ["LaplaceOperator", "KrylovSolverCG", "ChebyshevSmoother", "JacobiPreconditioner", "SolverData", "ExaDGError",
            "fp64_peak", "cartesian_kernel", "host_pipeline_plan", "load_library", "PERIODIC", "DIRICHLET", "NEUMANN"]

@@ -161,6 +161,19 @@ struct exadg_b200_chebyshev
   double * inv_diag = nullptr, * xold = nullptr, * r = nullptr;
 };
 
+// MultigridPreconditionerBase / MultigridAlgorithm on a hierarchy of DG level operators; see the comments at
+// exadg_b200_multigrid_create.  Levels are ordered coarse -> fine like level_info of the reference.
+struct exadg_b200_multigrid
+{
+  std::vector<exadg_b200_operator *> ops;
+  std::vector<exadg_b200_chebyshev *> smoothers;      // [level], nullptr on level 0
+  std::vector<double *> defect, solution, t;          // MultigridAlgorithm::defect / solution / t (multigrid_algorithm.h:64-66)
+  std::vector<TransferTable> transfer;                // [level]: between level - 1 and level
+  double * coarse_inv_diag = nullptr, * coarse_rhs = nullptr;
+  double coarse_abs_tol = 1e-12, coarse_rel_tol = 1e-3; int coarse_max_iter = 10000;
+  int64_t coarse_iterations = 0, cycles = 0;
+};
+
 namespace
 {
 template<typename F>
@@ -404,11 +417,14 @@ void read_all_scalars(exadg_b200_operator * op)
 }
 
 void cheb_run(exadg_b200_chebyshev * ch, double * x, const double * b, bool zero_start);
+void mg_vmult(exadg_b200_multigrid * mg, double * dst, const double * src);
+thread_local exadg_b200_multigrid * g_cg_multigrid = nullptr; // preconditioner object of EXADG_B200_PRECOND_MULTIGRID for the running cg()
 
 void precondition(exadg_b200_operator * op, int precond, const double * inv_diag, exadg_b200_chebyshev * cheb, int slot, double * z, const double * g)
 {
   const int64_t n = op->n_local;
   if (precond == EXADG_B200_PRECOND_POINT_JACOBI) { jacobi_dot(op->red, slot, z, inv_diag, g, n, op->stream); op->launches++; }
+  else if (precond == EXADG_B200_PRECOND_MULTIGRID) { mg_vmult(g_cg_multigrid, z, g); dot(op->red, slot, g, z, n, op->stream); op->launches++; }
   else { cheb_run(cheb, z, g, true); dot(op->red, slot, g, z, n, op->stream); op->launches++; }
   allreduce(op, op->red.result + slot, 1);
 }
@@ -515,6 +531,64 @@ void cheb_run(exadg_b200_chebyshev * ch, double * x, const double * b, bool zero
     rhok = rhokp;
     cheb_step(x, ch->xold, ch->inv_diag, b, ch->r, f1, f2, n, s); op->launches++;
   }
+}
+
+// ---- multigrid ----
+// 1-D embedding matrix: Lagrange basis on the Gauss-Lobatto nodes of FE_DGQ(kc) evaluated at x = a + b xi_i, xi_i the nodes of FE_DGQ(kf)
+void embedding_1d(int kf, int kc, real_t a, real_t b, double * I /*[kf+1][kc+1]*/)
+{
+  Tables1D f(kf), c(kc);
+  std::vector<real_t> v, d;
+  for (int i = 0; i <= kf; ++i) {
+    lagrange_at(c.xn, a + b * f.xn[i], v, d);
+    for (int j = 0; j <= kc; ++j) I[i * (kc + 1) + j] = (double)v[j];
+  }
+}
+
+// MultigridAlgorithm::v_cycle (I/solvers_and_preconditioners/multigrid/multigrid_algorithm.h:173-243), preconditioner mode
+void mg_v_cycle(exadg_b200_multigrid * mg, int level)
+{
+  exadg_b200_operator * op = mg->ops[level];
+  const int64_t n = op->n_local; cudaStream_t s = op->stream;
+  if (level == 0) {
+    // MGCoarseKrylov::operator() (coarse_grid_solvers.h:166-232): r = src (minus its mean for singular operators), CG with point Jacobi
+    // from the solution vector as it stands (zero before the first cycle, the previous coarse solution afterwards, as in the reference)
+    CUDA_CHECK(cudaMemcpyAsync(mg->coarse_rhs, mg->defect[0], (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (op->mesh.pure_neumann_or_periodic()) {
+      sum(op->red, 4, mg->coarse_rhs, n, s); op->launches++;
+      allreduce(op, op->red.result + 4, 1);
+      const double mean = read_scalar(op, 4) / (double)op->dev.n_global_dofs;
+      add_scalar(mg->coarse_rhs, -mean, n, s); op->launches++;
+    }
+    int its = 0;
+    const int st = cg(op, mg->solution[0], mg->coarse_rhs, EXADG_B200_PRECOND_POINT_JACOBI, mg->coarse_inv_diag, nullptr, mg->coarse_abs_tol, mg->coarse_rel_tol,
+                      mg->coarse_max_iter, &its, nullptr, nullptr, nullptr);
+    mg->coarse_iterations += its;
+    if (st != EXADG_B200_OK) throw std::runtime_error("multigrid: the coarse-grid CG solver did not converge (SolverControl::NoConvergence)");
+    return;
+  }
+  exadg_b200_operator * opc = mg->ops[level - 1];
+  cheb_run(mg->smoothers[level], mg->solution[level], mg->defect[level], true);      // pre-smoothing, zero initial guess
+  apply(op, mg->t[level], mg->solution[level], false);                                // vmult_interface_down
+  axpby(1.0, mg->defect[level], -1.0, mg->t[level], n, s); op->launches++;            // t = defect - A solution
+  restrict_add(mg->transfer[level], mg->defect[level - 1], mg->t[level], opc->dev.n_owned, s); op->launches++;
+  mg_v_cycle(mg, level - 1);
+  prolongate_add(mg->transfer[level], mg->solution[level], mg->solution[level - 1], opc->dev.n_owned, s); op->launches++;
+  cheb_run(mg->smoothers[level], mg->solution[level], mg->defect[level], false);     // post-smoothing
+}
+
+// MultigridAlgorithm::vmult (multigrid_algorithm.h:88-109)
+void mg_vmult(exadg_b200_multigrid * mg, double * dst, const double * src)
+{
+  if (!mg) throw std::invalid_argument("null multigrid");
+  const int L = (int)mg->ops.size() - 1;
+  cudaStream_t s = mg->ops[L]->stream;
+  for (int l = 0; l < L; ++l) mg->ops[l]->stream = s; // the coarser levels follow the stream of the finest operator (they do not own one)
+  for (int l = 0; l < L; ++l) { fill(mg->defect[l], 0.0, mg->ops[l]->n_local, s); mg->ops[l]->launches++; }
+  CUDA_CHECK(cudaMemcpyAsync(mg->defect[L], src, (size_t)mg->ops[L]->n_local * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  mg_v_cycle(mg, L);
+  CUDA_CHECK(cudaMemcpyAsync(dst, mg->solution[L], (size_t)mg->ops[L]->n_local * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  mg->cycles++;
 }
 } // namespace
 
@@ -983,6 +1057,147 @@ int exadg_b200_chebyshev_vmult(exadg_b200_chebyshev * ch, double * dst, const do
 { return guarded([&]() { if (!ch) throw std::invalid_argument("null smoother"); check_ptr(dst, "dst"); check_ptr(src, "src"); cheb_run(ch, dst, src, true); return EXADG_B200_OK; }); }
 int exadg_b200_chebyshev_step(exadg_b200_chebyshev * ch, double * dst, const double * src)
 { return guarded([&]() { if (!ch) throw std::invalid_argument("null smoother"); check_ptr(dst, "dst"); check_ptr(src, "src"); cheb_run(ch, dst, src, false); return EXADG_B200_OK; }); }
+
+/* ---- multigrid ---- */
+int exadg_b200_multigrid_levels(int mg_type, int p_sequence, int degree, int n_h_levels, int max_levels, int * n_levels, int * h_level, int * level_degree)
+{
+  return guarded([&]() {
+    if (!n_levels || degree < 1 || n_h_levels < 1) throw std::invalid_argument("bad argument");
+    // MultigridPreconditionerBase::initialize_levels (multigrid_preconditioner_base.cpp:97-323) for the DG-only types
+    std::vector<int> p_levels;
+    if (mg_type == EXADG_B200_MG_H) p_levels.push_back(degree);
+    else {
+      int p = degree;
+      do {
+        p_levels.push_back(p);
+        switch (p_sequence) {
+          case EXADG_B200_PSEQ_GO_TO_ONE: p = 1; break;
+          case EXADG_B200_PSEQ_DECREASE_BY_ONE: p = std::max(p - 1, 1); break;
+          case EXADG_B200_PSEQ_BISECT: p = std::max(p / 2, 1); break;
+          default: throw std::invalid_argument("No valid p-sequence selected!");
+        }
+      } while (p != p_levels.back());
+      std::reverse(p_levels.begin(), p_levels.end());
+    }
+    std::vector<std::pair<int, int>> info; // (h_level, degree), coarse -> fine
+    const bool use_h = (mg_type == EXADG_B200_MG_H || mg_type == EXADG_B200_MG_HP || mg_type == EXADG_B200_MG_PH);
+    const int nh = use_h ? n_h_levels : 1;
+    const int h_fine = n_h_levels - 1, h_first = use_h ? 0 : h_fine;
+    if (mg_type == EXADG_B200_MG_H) for (int h = 0; h < nh; ++h) info.push_back({h, p_levels.front()});
+    else if (mg_type == EXADG_B200_MG_P) for (int p : p_levels) info.push_back({h_fine, p});
+    else if (mg_type == EXADG_B200_MG_PH) {
+      for (int h = 0; h < nh - 1; ++h) info.push_back({h_first + h, p_levels.front()});
+      for (int p : p_levels) info.push_back({h_fine, p});
+    } else if (mg_type == EXADG_B200_MG_HP) {
+      for (size_t p = 0; p + 1 < p_levels.size(); ++p) info.push_back({h_first, p_levels[p]});
+      for (int h = 0; h < nh; ++h) info.push_back({h_first + h, p_levels.back()});
+    } else throw std::invalid_argument("This multigrid type is not implemented! (DG-only types: hMG, pMG, hpMG, phMG)");
+    *n_levels = (int)info.size();
+    if (h_level && level_degree) {
+      if ((int)info.size() > max_levels) throw std::invalid_argument("max_levels too small");
+      for (size_t l = 0; l < info.size(); ++l) { h_level[l] = info[l].first; level_degree[l] = info[l].second; }
+    }
+    return EXADG_B200_OK;
+  });
+}
+
+int exadg_b200_multigrid_destroy(exadg_b200_multigrid * mg)
+{
+  if (!mg) return EXADG_B200_OK;
+  cudaDeviceSynchronize();
+  for (auto * c : mg->smoothers) exadg_b200_chebyshev_destroy(c);
+  for (auto * v : mg->defect) cudaFree(v);
+  for (auto * v : mg->solution) cudaFree(v);
+  for (auto * v : mg->t) cudaFree(v);
+  cudaFree(mg->coarse_inv_diag); cudaFree(mg->coarse_rhs);
+  delete mg;
+  return EXADG_B200_OK;
+}
+
+int exadg_b200_multigrid_create(int n_levels, exadg_b200_operator * const * ops, int smoother_degree, double smoothing_range, int eig_cg_n_iterations, double coarse_abs_tol,
+                                double coarse_rel_tol, int coarse_max_iter, exadg_b200_multigrid ** out)
+{
+  return guarded([&]() {
+    if (n_levels < 1 || !ops || !out) throw std::invalid_argument("bad argument");
+    std::unique_ptr<exadg_b200_multigrid, int (*)(exadg_b200_multigrid *)> mg(new exadg_b200_multigrid, exadg_b200_multigrid_destroy);
+    mg->coarse_abs_tol = coarse_abs_tol; mg->coarse_rel_tol = coarse_rel_tol; mg->coarse_max_iter = coarse_max_iter;
+    exadg_b200_operator * fine = ops[n_levels - 1];
+    if (!fine) throw std::invalid_argument("null level operator");
+    mg->smoothers.assign(n_levels, nullptr); mg->transfer.resize(n_levels);
+    for (int l = 0; l < n_levels; ++l) {
+      exadg_b200_operator * op = ops[l];
+      if (!op) throw std::invalid_argument("null level operator");
+      require_self_contained(op, "exadg_b200_multigrid_create");
+      // all levels run on the stream of the finest operator (one V-cycle is one ordered sequence of launches)
+      if (op != fine) { CUDA_CHECK(cudaStreamSynchronize(op->stream)); if (op->own_stream && op->stream) { CUDA_CHECK(cudaStreamDestroy(op->stream)); } op->stream = fine->stream; op->own_stream = false; }
+      mg->ops.push_back(op);
+      const size_t bytes = (size_t)std::max<int64_t>(op->n_local, 1) * sizeof(double);
+      double * v[3];
+      for (auto & x : v) { CUDA_CHECK(cudaMalloc(&x, bytes)); CUDA_CHECK(cudaMemsetAsync(x, 0, bytes, fine->stream)); }
+      mg->defect.push_back(v[0]); mg->solution.push_back(v[1]); mg->t.push_back(v[2]);
+      if (l > 0) {
+        // only one type of transfer between two consecutive levels (multigrid_preconditioner_base.cpp:309-318)
+        exadg_b200_operator * c = ops[l - 1];
+        TransferTable & T = mg->transfer[l];
+        std::memset(&T, 0, sizeof(T));
+        T.nf = op->dev.n; T.nc = c->dev.n;
+        if (op->dev.n_owned == c->dev.n_owned && op->dev.degree > c->dev.degree && op->mesh.global_offset == c->mesh.global_offset) {
+          T.h = 0; embedding_1d(op->dev.degree, c->dev.degree, 0, 1, T.I[0]);
+        } else if (op->dev.degree == c->dev.degree && op->dev.n_owned == 8 * c->dev.n_owned && op->mesh.global_offset == 8 * c->mesh.global_offset) {
+          T.h = 1; embedding_1d(op->dev.degree, op->dev.degree, 0, 0.5L, T.I[0]); embedding_1d(op->dev.degree, op->dev.degree, 0.5L, 0.5L, T.I[1]);
+        } else
+          throw std::invalid_argument("Between two consecutive multigrid levels, only one type of transfer is allowed: either the degree decreases on the same cells, or "
+                                      "every coarse cell c has the children 8 c .. 8 c + 7 on this rank (global refinement, aligned partition)");
+        exadg_b200_chebyshev * ch = nullptr;
+        const int st = exadg_b200_chebyshev_create(op, smoother_degree, smoothing_range, eig_cg_n_iterations, &ch);
+        if (st != EXADG_B200_OK) throw std::runtime_error(g_last_error);
+        mg->smoothers[l] = ch;
+      }
+    }
+    exadg_b200_operator * c0 = mg->ops[0];
+    const size_t b0 = (size_t)std::max<int64_t>(c0->n_local, 1) * sizeof(double);
+    CUDA_CHECK(cudaMalloc(&mg->coarse_inv_diag, b0)); CUDA_CHECK(cudaMalloc(&mg->coarse_rhs, b0));
+    diagonal(c0, mg->coarse_inv_diag, false);
+    invert_diagonal(mg->coarse_inv_diag, c0->n_local, c0->stream); c0->launches++;
+    CUDA_CHECK(cudaStreamSynchronize(fine->stream));
+    *out = mg.release();
+    return EXADG_B200_OK;
+  });
+}
+
+int exadg_b200_multigrid_vmult(exadg_b200_multigrid * mg, double * dst, const double * src)
+{ return guarded([&]() { check_ptr(dst, "dst"); check_ptr(src, "src"); mg_vmult(mg, dst, src); return EXADG_B200_OK; }); }
+
+int exadg_b200_multigrid_info(const exadg_b200_multigrid * mg, int * n_levels, int64_t * coarse_iterations, int64_t * cycles)
+{
+  if (!mg) return EXADG_B200_ERR_ARG;
+  if (n_levels) *n_levels = (int)mg->ops.size();
+  if (coarse_iterations) *coarse_iterations = mg->coarse_iterations;
+  if (cycles) *cycles = mg->cycles;
+  return EXADG_B200_OK;
+}
+
+int exadg_b200_multigrid_smoother(const exadg_b200_multigrid * mg, int level, exadg_b200_chebyshev ** smoother)
+{
+  if (!mg || !smoother || level < 1 || level >= (int)mg->ops.size()) return EXADG_B200_ERR_ARG;
+  *smoother = mg->smoothers[level];
+  return EXADG_B200_OK;
+}
+
+int exadg_b200_cg_solve_multigrid(exadg_b200_operator * op, double * x, const double * b, exadg_b200_multigrid * mg, double abs_tol, double rel_tol, int max_iter,
+                                  int * n_iter, double * residuals)
+{
+  return guarded([&]() {
+    if (!op || !mg) throw std::invalid_argument("null argument");
+    require_self_contained(op, "exadg_b200_cg_solve_multigrid");
+    check_ptr(x, "x"); check_ptr(b, "b");
+    if (mg->ops.back()->n_local != op->n_local) throw std::invalid_argument("the finest multigrid level does not match the operator");
+    if (mg->ops.back()->stream != op->stream) throw std::invalid_argument("the finest multigrid level must run on the operator's stream (exadg_b200_set_stream)");
+    g_cg_multigrid = mg;
+    struct Reset { ~Reset() { g_cg_multigrid = nullptr; } } reset;
+    return cg(op, x, b, EXADG_B200_PRECOND_MULTIGRID, nullptr, nullptr, abs_tol, rel_tol, max_iter, n_iter, residuals, nullptr, nullptr);
+  });
+}
 
 int exadg_b200_set_nccl_comm(exadg_b200_operator * op, void * comm)
 {

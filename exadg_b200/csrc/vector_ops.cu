@@ -176,42 +176,54 @@ __global__ void add_scalar_kernel(double * __restrict__ x, double a, int64_t n)
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] += a;
 }
 
-// one CTA per cell; three tensor sweeps through shared memory.  PROLONG: in = coarse (nc^3), out = fine (nf^3), matrix I;
-// otherwise in = fine, out = coarse, matrix I^T.  Fixed summation order.
+// one CTA per COARSE cell; three tensor sweeps through shared memory per fine cell (p: the same cell, h: its eight children
+// 8 c + child, child = x + 2 y + 4 z).  PROLONG: in = coarse, out = fine, matrices I_d; otherwise in = fine, out = coarse, matrices
+// I_d^T, the children summed in child order.  Fixed summation order, no atomics.
 template<bool PROLONG>
-__global__ void __launch_bounds__(128) transfer_kernel(const TransferTable t, double * __restrict__ out, const double * __restrict__ in, int64_t n_cells)
+__global__ void __launch_bounds__(128) transfer_kernel(const TransferTable t, double * __restrict__ out, const double * __restrict__ in, int64_t n_coarse_cells)
 {
-  __shared__ double A[512], B[512];
-  const int ni = PROLONG ? t.nc : t.nf, no = PROLONG ? t.nf : t.nc;
-  for (int64_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
-    const double * src = in + cell * ni * ni * ni;
-    for (int i = threadIdx.x; i < ni * ni * ni; i += blockDim.x) A[i] = src[i];
-    __syncthreads();
-    // x: B[o, j, k] = sum_i M[o][i] A[i, j, k]      (extents: no x ni x ni)
-    for (int e = threadIdx.x; e < no * ni * ni; e += blockDim.x) {
-      const int o = e % no, jk = e / no;
-      double v = 0.0;
-      for (int i = 0; i < ni; ++i) v = fma(PROLONG ? t.I[o * t.nc + i] : t.I[i * t.nc + o], A[i + ni * jk], v);
-      B[e] = v;
+  __shared__ double A[512], B[512], C[512];
+  const int nc = t.nc, nf = t.nf;
+  const int ni = PROLONG ? nc : nf, no = PROLONG ? nf : nc;
+  const int n_child = t.h ? 8 : 1;
+  for (int64_t cell = blockIdx.x; cell < n_coarse_cells; cell += gridDim.x) {
+    if (!PROLONG) for (int i = threadIdx.x; i < no * no * no; i += blockDim.x) C[i] = 0.0;
+    for (int child = 0; child < n_child; ++child) {
+      const int64_t fine = t.h ? cell * 8 + child : cell;
+      const double * src = in + (PROLONG ? cell * (int64_t)(nc * nc * nc) : fine * (int64_t)(nf * nf * nf));
+      const double * Mx = t.I[t.h ? (child & 1) : 0], * My = t.I[t.h ? ((child >> 1) & 1) : 0], * Mz = t.I[t.h ? ((child >> 2) & 1) : 0];
+      for (int i = threadIdx.x; i < ni * ni * ni; i += blockDim.x) A[i] = src[i];
+      __syncthreads();
+      // x: B[o, j, k] = sum_i M[o][i] A[i, j, k]      (extents: no x ni x ni)
+      for (int e = threadIdx.x; e < no * ni * ni; e += blockDim.x) {
+        const int o = e % no, jk = e / no;
+        double v = 0.0;
+        for (int i = 0; i < ni; ++i) v = fma(PROLONG ? Mx[o * nc + i] : Mx[i * nc + o], A[i + ni * jk], v);
+        B[e] = v;
+      }
+      __syncthreads();
+      // y: A[o1, o, k] = sum_j M[o][j] B[o1, j, k]    (no x no x ni)
+      for (int e = threadIdx.x; e < no * no * ni; e += blockDim.x) {
+        const int o1 = e % no, o = (e / no) % no, k = e / (no * no);
+        double v = 0.0;
+        for (int j = 0; j < ni; ++j) v = fma(PROLONG ? My[o * nc + j] : My[j * nc + o], B[o1 + no * (j + ni * k)], v);
+        A[e] = v;
+      }
+      __syncthreads();
+      // z: out[o1, o2, o] += sum_k M[o][k] A[o1, o2, k]
+      double * dst = out + fine * (int64_t)(nf * nf * nf);
+      for (int e = threadIdx.x; e < no * no * no; e += blockDim.x) {
+        const int o12 = e % (no * no), o = e / (no * no);
+        double v = 0.0;
+        for (int k = 0; k < ni; ++k) v = fma(PROLONG ? Mz[o * nc + k] : Mz[k * nc + o], A[o12 + no * no * k], v);
+        if (PROLONG) dst[e] += v; else C[e] += v; // every thread owns its entries of C
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    // y: A[o1, o, k] = sum_j M[o][j] B[o1, j, k]    (no x no x ni)
-    for (int e = threadIdx.x; e < no * no * ni; e += blockDim.x) {
-      const int o1 = e % no, o = (e / no) % no, k = e / (no * no);
-      double v = 0.0;
-      for (int j = 0; j < ni; ++j) v = fma(PROLONG ? t.I[o * t.nc + j] : t.I[j * t.nc + o], B[o1 + no * (j + ni * k)], v);
-      A[e] = v;
+    if (!PROLONG) {
+      double * dst = out + cell * (int64_t)(nc * nc * nc);
+      for (int e = threadIdx.x; e < no * no * no; e += blockDim.x) dst[e] += C[e];
     }
-    __syncthreads();
-    // z: out[o1, o2, o] += sum_k M[o][k] A[o1, o2, k]
-    double * dst = out + cell * no * no * no;
-    for (int e = threadIdx.x; e < no * no * no; e += blockDim.x) {
-      const int o12 = e % (no * no), o = e / (no * no);
-      double v = 0.0;
-      for (int k = 0; k < ni; ++k) v = fma(PROLONG ? t.I[o * t.nc + k] : t.I[k * t.nc + o], A[o12 + no * no * k], v);
-      dst[e] += v;
-    }
-    __syncthreads();
   }
 }
 
@@ -234,10 +246,10 @@ void reducer_free(Reducer & r)
 
 void dot(const Reducer & r, int slot, const double * a, const double * b, int64_t n, cudaStream_t s)
 { dot_kernel<<<red_grid(n), RED_THREADS, 0, s>>>(a, b, n, r.partial, r.result, slot); }
-void prolongate_add(const TransferTable & t, double * fine, const double * coarse, int64_t n_cells, cudaStream_t s)
-{ if (n_cells > 0) transfer_kernel<true><<<(unsigned)std::min<int64_t>(n_cells, 148 * 16), 128, 0, s>>>(t, fine, coarse, n_cells); }
-void restrict_add(const TransferTable & t, double * coarse, const double * fine, int64_t n_cells, cudaStream_t s)
-{ if (n_cells > 0) transfer_kernel<false><<<(unsigned)std::min<int64_t>(n_cells, 148 * 16), 128, 0, s>>>(t, coarse, fine, n_cells); }
+void prolongate_add(const TransferTable & t, double * fine, const double * coarse, int64_t n_coarse_cells, cudaStream_t s)
+{ if (n_coarse_cells > 0) transfer_kernel<true><<<(unsigned)std::min<int64_t>(n_coarse_cells, 148 * 16), 128, 0, s>>>(t, fine, coarse, n_coarse_cells); }
+void restrict_add(const TransferTable & t, double * coarse, const double * fine, int64_t n_coarse_cells, cudaStream_t s)
+{ if (n_coarse_cells > 0) transfer_kernel<false><<<(unsigned)std::min<int64_t>(n_coarse_cells, 148 * 16), 128, 0, s>>>(t, coarse, fine, n_coarse_cells); }
 void sum(const Reducer & r, int slot, const double * a, int64_t n, cudaStream_t s)
 { sum_kernel<<<red_grid(n), RED_THREADS, 0, s>>>(a, n, r.partial, r.result, slot); }
 void cg_update_x_g(const Reducer & r, int slot, int num, int den, double * x, const double * d, double * g, const double * h, int64_t n, cudaStream_t s)

@@ -48,12 +48,14 @@ void cheb_step(double * x, double * xold, const double * inv_diag, const double 
 // start vector of PreconditionChebyshev's eigenvalue estimate: (global index mod 11)
 void fill_mod11(double * x, int64_t global_offset, int64_t n, cudaStream_t s);
 void add_scalar(double * x, double a, int64_t n, cudaStream_t s);
-// polynomial transfer between FE_DGQ(k_fine) and FE_DGQ(k_coarse) on the same cells (dealii::MGTwoLevelTransfer, p-transfer of
-// I/solvers_and_preconditioners/multigrid/transfer.cpp:28-69): prolongation = embedding (coarse Lagrange basis evaluated at the fine
-// Gauss-Lobatto nodes, tensor product of the 1-D matrix I[nf][nc]), restriction = its transpose; both add into dst
-struct TransferTable { int nf, nc; double I[8 * 8]; };
-void prolongate_add(const TransferTable & t, double * fine, const double * coarse, int64_t n_cells, cudaStream_t s);
-void restrict_add(const TransferTable & t, double * coarse, const double * fine, int64_t n_cells, cudaStream_t s);
+// two-level transfers of the DG multigrid hierarchy (dealii::MGTwoLevelTransfer as set up by
+// I/solvers_and_preconditioners/multigrid/transfer.cpp:28-69), prolongation = embedding, restriction = its transpose, both add into dst:
+//   p-transfer (h = 0): FE_DGQ(nc - 1) -> FE_DGQ(nf - 1) on the same cells; I[0] = [nf][nc] coarse Lagrange basis at the fine Gauss-Lobatto nodes;
+//   h-transfer (h = 1): parent cell c -> children 8 c + (x + 2 y + 4 z) of a global refinement, nf = nc = n; I[b] = [n][n] parent basis at the
+//   nodes of the child covering the lower (b = 0) / upper (b = 1) half of the parent interval.
+struct TransferTable { int nf, nc, h; double I[2][8 * 8]; };
+void prolongate_add(const TransferTable & t, double * fine, const double * coarse, int64_t n_coarse_cells, cudaStream_t s);
+void restrict_add(const TransferTable & t, double * coarse, const double * fine, int64_t n_coarse_cells, cudaStream_t s);
 // sum of entries -> result[slot]
 void sum(const Reducer & r, int slot, const double * a, int64_t n, cudaStream_t s);
 

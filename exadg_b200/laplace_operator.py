@@ -396,6 +396,92 @@ class ChebyshevSmoother:
         self.op.synchronize()
 
 
+MG_TYPES = {"hMG": 0, "pMG": 1, "hpMG": 2, "phMG": 3}
+P_SEQUENCES = {"GoToOne": 0, "DecreaseByOne": 1, "Bisect": 2}
+
+
+def multigrid_levels(mg_type, p_sequence, degree, n_h_levels):
+    """MultigridPreconditionerBase::initialize_levels (multigrid_preconditioner_base.cpp:97-323) for the DG-only multigrid types:
+    list of (h_level, degree), coarse -> fine.  No CUDA call."""
+    if mg_type not in MG_TYPES:
+        raise ExaDGError("This multigrid type is not implemented! (%s; the c-transfer types need a continuous FE_Q operator)" % mg_type)
+    n = C.c_int(0)
+    _check(_lib().exadg_b200_multigrid_levels(MG_TYPES[mg_type], P_SEQUENCES[p_sequence], degree, n_h_levels, 0, C.byref(n), None, None))
+    h = (C.c_int * n.value)()
+    k = (C.c_int * n.value)()
+    _check(_lib().exadg_b200_multigrid_levels(MG_TYPES[mg_type], P_SEQUENCES[p_sequence], degree, n_h_levels, n.value, C.byref(n), h, k))
+    return [(h[i], k[i]) for i in range(n.value)]
+
+
+class MultigridPreconditioner:
+    """Poisson::MultigridPreconditioner / MultigridPreconditionerBase (I/poisson/preconditioners/multigrid_preconditioner.h:41-54,
+    I/solvers_and_preconditioners/multigrid/multigrid_preconditioner_base.cpp) on DG levels: Chebyshev(point Jacobi) smoothers,
+    CG + point Jacobi on the coarsest level, V-cycle of multigrid_algorithm.h:173-243."""
+
+    def __init__(self, level_operators, smoother_iterations=5, smoothing_range=20.0, iterations_eigenvalue_estimation=20,
+                 coarse_abs_tol=1e-12, coarse_rel_tol=1e-3, coarse_max_iter=10000):
+        self.operators = list(level_operators)  # coarse -> fine; kept alive here
+        arr = (C.c_void_p * len(self.operators))(*[op._h for op in self.operators])
+        h = C.c_void_p()
+        for op in self.operators:
+            op._order_after_torch()
+        _check(_lib().exadg_b200_multigrid_create(len(self.operators), arr, smoother_iterations, smoothing_range, iterations_eigenvalue_estimation,
+                                                 coarse_abs_tol, coarse_rel_tol, coarse_max_iter, C.byref(h)))
+        self._h = h
+        self.op = self.operators[-1]
+
+    @classmethod
+    def hypercube(cls, fine_operator_args, mg_type="phMG", p_sequence="Bisect", fine_operator=None, **kw):
+        """Level operators for a hypercube grid: fine_operator_args are the keyword arguments of LaplaceOperator.hypercube of the
+        finest level; level (h, k) is the same grid with n_refinements = h and degree = k (what initialize_operator does per level,
+        multigrid_preconditioner_base.cpp:593-640)."""
+        a = dict(fine_operator_args)
+        levels = multigrid_levels(mg_type, p_sequence, a["degree"], a.get("n_refinements", 0) + 1)
+        ops = []
+        for i, (h, k) in enumerate(levels):
+            if i == len(levels) - 1 and fine_operator is not None:
+                ops.append(fine_operator)
+            else:
+                b = dict(a)
+                b["degree"], b["n_refinements"] = k, h
+                ops.append(LaplaceOperator.hypercube(**b))
+        mg = cls(ops, **kw)
+        mg.levels = levels
+        return mg
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib().exadg_b200_multigrid_destroy(h)
+            except Exception:
+                pass
+
+    def vmult(self, dst, src):
+        self.op._order_after_torch()
+        _check(_lib().exadg_b200_multigrid_vmult(self._h, _ptr(dst, self.op.local_size()), _ptr(src, self.op.local_size())))
+        self.op.synchronize()
+
+    def info(self):
+        n, ci, cy = C.c_int(0), C.c_int64(0), C.c_int64(0)
+        _check(_lib().exadg_b200_multigrid_info(self._h, C.byref(n), C.byref(ci), C.byref(cy)))
+        return {"n_levels": n.value, "coarse_iterations": ci.value, "cycles": cy.value}
+
+    def smoother_interval(self, level):
+        """(lambda_min_est, lambda_max_est, theta, delta) of the Chebyshev smoother of a level >= 1."""
+        ch = C.c_void_p()
+        _check(_lib().exadg_b200_multigrid_smoother(self._h, level, C.byref(ch)))
+        v = [C.c_double() for _ in range(4)]
+        _check(_lib().exadg_b200_chebyshev_get(ch, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
+    def set_smoother_interval(self, level, theta, delta):
+        ch = C.c_void_p()
+        _check(_lib().exadg_b200_multigrid_smoother(self._h, level, C.byref(ch)))
+        _check(_lib().exadg_b200_chebyshev_set_interval(ch, theta, delta))
+
+
+
 @dataclass
 class SolverData:
     """solver_data.h: SolverData(max_iter, abs_tol, rel_tol); Poisson defaults parameters.cpp:47."""
@@ -423,13 +509,19 @@ class KrylovSolverCG:
             kind = 1
         elif isinstance(self.preconditioner, ChebyshevSmoother):
             kind, cheb = 2, self.preconditioner._h
+        elif isinstance(self.preconditioner, MultigridPreconditioner):
+            kind = 3
         elif self.preconditioner is not None:
             raise ExaDGError("unsupported preconditioner")
         hist = np.zeros(sd.max_iter + 1)
         it = C.c_int(0)
         self.op._order_after_torch()
-        status = _lib().exadg_b200_cg_solve(self.op._h, _ptr(dst), _ptr(rhs), kind, cheb, sd.abs_tol, sd.rel_tol, sd.max_iter,
-                                           C.byref(it), hist.ctypes.data_as(C.POINTER(C.c_double)))
+        if kind == 3:
+            status = _lib().exadg_b200_cg_solve_multigrid(self.op._h, _ptr(dst), _ptr(rhs), self.preconditioner._h, sd.abs_tol, sd.rel_tol, sd.max_iter,
+                                                         C.byref(it), hist.ctypes.data_as(C.POINTER(C.c_double)))
+        else:
+            status = _lib().exadg_b200_cg_solve(self.op._h, _ptr(dst), _ptr(rhs), kind, cheb, sd.abs_tol, sd.rel_tol, sd.max_iter,
+                                               C.byref(it), hist.ctypes.data_as(C.POINTER(C.c_double)))
         self.n = it.value
         self.residuals = hist[: it.value + 1].copy()
         if status == 4:

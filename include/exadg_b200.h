@@ -31,10 +31,14 @@ extern "C" {
 
 typedef struct exadg_b200_operator exadg_b200_operator;
 typedef struct exadg_b200_chebyshev exadg_b200_chebyshev;
+typedef struct exadg_b200_multigrid exadg_b200_multigrid;
 
 enum { EXADG_B200_OK = 0, EXADG_B200_ERR_ARG = 1, EXADG_B200_ERR_CUDA = 2, EXADG_B200_ERR_UNSUPPORTED = 3, EXADG_B200_ERR_NOT_CONVERGED = 4 };
 enum { EXADG_B200_PERIODIC = 0, EXADG_B200_DIRICHLET = 1, EXADG_B200_NEUMANN = 2 };
-enum { EXADG_B200_PRECOND_NONE = 0, EXADG_B200_PRECOND_POINT_JACOBI = 1, EXADG_B200_PRECOND_CHEBYSHEV = 2 };
+enum { EXADG_B200_PRECOND_NONE = 0, EXADG_B200_PRECOND_POINT_JACOBI = 1, EXADG_B200_PRECOND_CHEBYSHEV = 2, EXADG_B200_PRECOND_MULTIGRID = 3 };
+/* MultigridType / PSequenceType of I/solvers_and_preconditioners/multigrid/multigrid_parameters.h:38-63 (the types that stay in the DG space) */
+enum { EXADG_B200_MG_H = 0, EXADG_B200_MG_P = 1, EXADG_B200_MG_HP = 2, EXADG_B200_MG_PH = 3 };
+enum { EXADG_B200_PSEQ_GO_TO_ONE = 0, EXADG_B200_PSEQ_DECREASE_BY_ONE = 1, EXADG_B200_PSEQ_BISECT = 2 };
 
 /* Hypercube grids of the reference's benchmark/test applications
  * (I/grid/periodic_box.h:35-88, applications/poisson/throughput/application.h:93-165,
@@ -177,6 +181,35 @@ int exadg_b200_chebyshev_set_interval(exadg_b200_chebyshev *cheb, double theta, 
 /* SmootherBase::vmult (zero initial guess) and ::step (chebyshev_smoother.h:79-119) */
 int exadg_b200_chebyshev_vmult(exadg_b200_chebyshev *cheb, double *dst, const double *src);
 int exadg_b200_chebyshev_step(exadg_b200_chebyshev *cheb, double *dst, const double *src);
+
+/* Multigrid preconditioner on a hierarchy of DG level operators.
+ *  - exadg_b200_multigrid_levels: MultigridPreconditionerBase::initialize_levels
+ *    (I/solvers_and_preconditioners/multigrid/multigrid_preconditioner_base.cpp:97-323) for hMG / pMG / hpMG / phMG with is_dg = true:
+ *    level l (coarse -> fine) lives on h-level h_level[l] (0 = coarsest of n_h_levels global refinement levels) with degree
+ *    level_degree[l]; call with null arrays to query n_levels.  The c-transfer types (cphMG, ...) need a continuous FE_Q Laplace
+ *    operator, which this library does not have: they return EXADG_B200_ERR_ARG.
+ *  - exadg_b200_multigrid_create: takes the level operators the caller created for that list (as the reference creates one
+ *    operator per level, multigrid_preconditioner_base.cpp:593-640), coarse -> fine.  Between consecutive levels either the degree
+ *    changes on the same cells (p-transfer) or every cell c of the coarser level has the children 8 c .. 8 c + 7 (h-transfer of a
+ *    global refinement; partitions must be aligned) - dealii::MGTwoLevelTransfer as set up by multigrid/transfer.cpp:28-69
+ *    (prolongation = embedding, restriction = its transpose).  Smoother on every level > 0: ChebyshevSmoother with point Jacobi
+ *    (multigrid_preconditioner_base.cpp:706-733; defaults degree 5, smoothing range 20, 20 CG iterations for the eigenvalue
+ *    estimate, multigrid_parameters.h:169-178); coarse solver: MGCoarseKrylov = CG + point Jacobi to coarse_rel_tol
+ *    (coarse_grid_solvers.h:62-232; defaults abs 1e-12, rel 1e-3, 1e4 iterations), mean value removed for singular operators.
+ *    The level operators are re-bound to the stream of the finest one and must outlive the multigrid object.
+ *    Level arithmetic is FP64 (the reference instantiates the level operators in float, multigrid_preconditioner_base.h:60).
+ *  - exadg_b200_multigrid_vmult: MultigridPreconditionerBase::vmult = MultigridAlgorithm::vmult, one V-cycle with zero initial guess
+ *    (multigrid_algorithm.h:88-109, 173-243).
+ *  - exadg_b200_cg_solve_multigrid: exadg_b200_cg_solve with Preconditioner::Multigrid. */
+int exadg_b200_multigrid_levels(int mg_type, int p_sequence, int degree, int n_h_levels, int max_levels, int *n_levels, int *h_level, int *level_degree);
+int exadg_b200_multigrid_create(int n_levels, exadg_b200_operator *const *level_operators, int smoother_degree, double smoothing_range, int eig_cg_n_iterations,
+                                double coarse_abs_tol, double coarse_rel_tol, int coarse_max_iter, exadg_b200_multigrid **mg);
+int exadg_b200_multigrid_destroy(exadg_b200_multigrid *mg);
+int exadg_b200_multigrid_vmult(exadg_b200_multigrid *mg, double *dst, const double *src);
+int exadg_b200_multigrid_info(const exadg_b200_multigrid *mg, int *n_levels, int64_t *coarse_iterations, int64_t *cycles);
+int exadg_b200_multigrid_smoother(const exadg_b200_multigrid *mg, int level, exadg_b200_chebyshev **smoother); /* owned by mg */
+int exadg_b200_cg_solve_multigrid(exadg_b200_operator *op, double *x, const double *b, exadg_b200_multigrid *mg, double abs_tol, double rel_tol, int max_iter,
+                                  int *n_iter, double *residuals);
 
 /* Multi-GPU halo exchange of src (the update_ghost_values of MatrixFree::loop).
  * The library packs the owned cells each peer needs; transport is pluggable:

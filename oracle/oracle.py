@@ -43,6 +43,8 @@ def lib():
             getattr(L, name).restype = C.c_long
             getattr(L, name).argtypes = [C.c_void_p]
         L.orc_get_tau.argtypes = [C.c_void_p, dp]
+        L.orc_mass_vmult.argtypes = [C.c_void_p, dp, dp]
+        L.orc_get_cell_jxw.argtypes = [C.c_void_p, dp]
         L.orc_get_mesh.argtypes = [C.c_void_p, dp, C.POINTER(C.c_long), C.POINTER(C.c_ubyte), C.POINTER(C.c_ubyte)]
         L.orc_vmult.argtypes = [C.c_void_p, dp, dp]
         L.orc_vmult_add.argtypes = [C.c_void_p, dp, dp]
@@ -154,6 +156,17 @@ class OracleOperator:
         lib().orc_dof_coordinates(self.h, _p(xyz))
         return xyz
 
+    def mass_vmult(self, src):
+        """MassKernel with QGauss(k+1) (mass_kernel.h:32-93), one component."""
+        dst = self._vec()
+        lib().orc_mass_vmult(self.h, _p(dst), _p(np.ascontiguousarray(src, dtype=np.float64)))
+        return dst
+
+    def cell_jxw(self):
+        w = np.zeros((self.n_cells, (self.degree + 1) ** 3))
+        lib().orc_get_cell_jxw(self.h, _p(w))
+        return w
+
     def tau(self):
         t = np.zeros(self.n_cells)
         lib().orc_get_tau(self.h, _p(t))
@@ -167,6 +180,43 @@ class OracleOperator:
         bt = np.zeros((self.n_cells, 6), dtype=np.uint8)
         lib().orc_get_mesh(self.h, _p(xmap), nb.ctypes.data_as(C.POINTER(C.c_long)), nbface.ctypes.data_as(C.POINTER(C.c_ubyte)), bt.ctypes.data_as(C.POINTER(C.c_ubyte)))
         return xmap, nb, nbface, bt
+
+
+class OracleHelmholtz:
+    """scaling_factor_mass * M + viscosity * A_SIPG applied to every component of a vector-valued DG field (FESystem(FE_DGQ(k)^n):
+    cell-major, then component, then lexicographic node): the momentum / viscous operator of the incompressible Navier-Stokes module in
+    Laplace formulation with constant viscosity (momentum_operator.cpp:376-426, viscous_operator.h:365-386, 489-560)."""
+
+    def __init__(self, op, n_components=3, scaling_factor_mass=1.0, viscosity=1.0):
+        self.op, self.nc, self.alpha, self.nu = op, n_components, scaling_factor_mass, viscosity
+        self.n_dofs = op.n_dofs * n_components
+
+    def _split(self, v):
+        n3 = (self.op.degree + 1) ** 3
+        return np.ascontiguousarray(v, dtype=np.float64).reshape(self.op.n_cells, self.nc, n3)
+
+    def _each(self, f, v):
+        u = self._split(v)
+        out = np.empty_like(u)
+        for c in range(self.nc):
+            out[:, c, :] = f(np.ascontiguousarray(u[:, c, :]).ravel()).reshape(self.op.n_cells, -1)
+        return out.ravel()
+
+    def vmult(self, src):
+        return self._each(lambda u: self.alpha * self.op.mass_vmult(u) + self.nu * self.op.vmult(u), src)
+
+    def mass_vmult(self, src):
+        return self._each(self.op.mass_vmult, src)
+
+    def diagonal(self):
+        e = np.ones(self.op.n_dofs)
+        n = self.op.degree + 1
+        S = basis_tables(self.op.degree)["S"]  # S[q, j] = l_j(x_q)
+        S2 = S * S
+        w = self.op.cell_jxw().reshape(self.op.n_cells, n, n, n)
+        dm = np.einsum("qi,rj,sk,nsrq->nkji", S2, S2, S2, w, optimize=True).ravel()
+        d = self.alpha * dm + self.nu * self.op.diagonal()
+        return np.repeat(d.reshape(self.op.n_cells, 1, -1), self.nc, axis=1).ravel() + 0 * e[0]
 
 
 class OracleChebyshev:

@@ -664,6 +664,23 @@ long orc_n_dofs(void *h) { return ((Op *)h)->n_dofs; }
 long orc_n_cells(void *h) { return ((Op *)h)->n_cells; }
 long orc_n_interior_faces(void *h) { return ((Op *)h)->n_faces; }
 long orc_n_boundary_faces(void *h) { return ((Op *)h)->n_bfaces; }
+/* MassKernel (I/operators/mass_kernel.h:32-93): dst = (phi_i, u) with QGauss(k+1): gather_evaluate(values) -> submit_value(u JxW)
+ * -> integrate_scatter; one component.  The Helmholtz / viscous operator of the incompressible Navier-Stokes module in Laplace
+ * formulation with constant viscosity is scaling_factor_mass * M + nu * A_SIPG, component by component (SURVEY 8 f-3;
+ * momentum_operator.cpp:376-426, viscous_operator.h:365-386, 489-560). */
+void orc_mass_vmult(void *h, double *dst, const double *src)
+{
+  Op *op = (Op *)h; const Basis *b = &op->b; int n3 = b->n * b->n * b->n, nq3 = b->nq * b->nq * b->nq;
+#pragma omp parallel for schedule(static)
+  for (long c = 0; c < op->n_cells; ++c) {
+    double v[MAXP];
+    eval_cell_val(b, src + c * n3, v);
+    for (int q = 0; q < nq3; ++q) v[q] *= op->JxW_c[c * nq3 + q];
+    for (int i = 0; i < n3; ++i) dst[c * n3 + i] = 0.0;
+    integrate_cell(b, NULL, NULL, NULL, v, dst + c * n3);
+  }
+}
+void orc_get_cell_jxw(void *h, double *jxw) { Op *op = (Op *)h; int nq3 = op->b.nq * op->b.nq * op->b.nq; memcpy(jxw, op->JxW_c, sizeof(double) * op->n_cells * nq3); }
 void orc_get_tau(void *h, double *tau) { Op *op = (Op *)h; memcpy(tau, op->tauK, sizeof(double) * op->n_cells); }
 void orc_get_mesh(void *h, double *xmap, long *nb, unsigned char *nbface, unsigned char *bt)
 {
