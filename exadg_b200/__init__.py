@@ -37,6 +37,8 @@ EXPORTED_SYMBOLS = [
     "exadg_b200_n_boundary_faces", "exadg_b200_boundary_quadrature_points", "exadg_b200_set_boundary_values", "exadg_b200_rhs", "exadg_b200_rhs_add",
     "exadg_b200_evaluate", "exadg_b200_evaluate_add", "exadg_b200_cell_quadrature_points", "exadg_b200_integrate_source_add", "exadg_b200_l2_error",
     "exadg_b200_subtract_mean_value",
+    "exadg_b200_create_hypercube_helmholtz", "exadg_b200_create_helmholtz", "exadg_b200_n_components", "exadg_b200_set_scaling_factor_mass",
+    "exadg_b200_inverse_mass_vmult",
     "exadg_b200_multigrid_levels", "exadg_b200_multigrid_create", "exadg_b200_multigrid_destroy", "exadg_b200_multigrid_vmult", "exadg_b200_multigrid_info",
     "exadg_b200_multigrid_smoother", "exadg_b200_cg_solve_multigrid",
 ]
@@ -55,6 +57,10 @@ class MeshDesc(C.Structure):
                 ("global_cell_offset", C.c_int64), ("force_general", C.c_int), ("operator_is_singular", C.c_int)]
 
 
+class HelmholtzData(C.Structure):
+    _fields_ = [("n_components", C.c_int), ("scaling_factor_mass", C.c_double), ("viscosity", C.c_double)]
+
+
 _lib = None
 
 
@@ -71,6 +77,11 @@ def load_library():
     L.exadg_b200_last_error.restype = C.c_char_p
     L.exadg_b200_create_hypercube.argtypes = [C.POINTER(HypercubeDesc), C.POINTER(vp)]
     L.exadg_b200_create.argtypes = [C.POINTER(MeshDesc), C.POINTER(vp)]
+    L.exadg_b200_create_hypercube_helmholtz.argtypes = [C.POINTER(HypercubeDesc), C.POINTER(HelmholtzData), C.POINTER(vp)]
+    L.exadg_b200_create_helmholtz.argtypes = [C.POINTER(MeshDesc), C.POINTER(HelmholtzData), C.POINTER(vp)]
+    L.exadg_b200_n_components.argtypes = [vp]
+    L.exadg_b200_set_scaling_factor_mass.argtypes = [vp, C.c_double]
+    L.exadg_b200_inverse_mass_vmult.argtypes = [vp, dp, dp]
     L.exadg_b200_destroy.argtypes = [vp]
     L.exadg_b200_set_stream.argtypes = [vp, vp]
     L.exadg_b200_synchronize.argtypes = [vp]

@@ -216,10 +216,12 @@ void finish_setup(exadg_b200_operator * op, double ip_factor, bool force_general
   D.n = D.degree + 1;
   D.n_owned = M.n_owned; D.n_ghost = M.n_ghost; D.n_faces = M.n_faces;
   const int64_t n3 = (int64_t)D.n * D.n * D.n;
-  D.n_global_dofs = M.n_global_cells * n3;
-  op->n_local = M.n_owned * n3;
+  D.n_global_dofs = M.n_global_cells * n3 * D.n_components;
+  op->n_local = M.n_owned * n3 * D.n_components;
   for (int e = 0; e < 3; ++e) D.h[e] = M.h[e];
-  D.cartesian = M.cartesian_uniform && M.all_interior() && !force_general && cartesian_supported(D.n);
+  if (D.helmholtz && M.world > 1) throw std::runtime_error("the Helmholtz / viscous operator is not partitioned yet (world must be 1)");
+  // the mass term and the component blocks live in the general kernel only
+  D.cartesian = M.cartesian_uniform && M.all_interior() && !force_general && !D.helmholtz && cartesian_supported(D.n);
   if (D.cartesian) {
     // tau_hat is needed by the kernel tables: uniform box => tau_K = sum_d 1/h_d (interior_penalty_parameter.h:68-98)
     double tk = 0.0;
@@ -571,9 +573,10 @@ void mg_v_cycle(exadg_b200_multigrid * mg, int level)
   cheb_run(mg->smoothers[level], mg->solution[level], mg->defect[level], true);      // pre-smoothing, zero initial guess
   apply(op, mg->t[level], mg->solution[level], false);                                // vmult_interface_down
   axpby(1.0, mg->defect[level], -1.0, mg->t[level], n, s); op->launches++;            // t = defect - A solution
-  restrict_add(mg->transfer[level], mg->defect[level - 1], mg->t[level], opc->dev.n_owned, s); op->launches++;
+  const int64_t n_coarse_blocks = opc->dev.n_owned * opc->dev.n_components; // p-transfer of a vector-valued field: block by block
+  restrict_add(mg->transfer[level], mg->defect[level - 1], mg->t[level], n_coarse_blocks, s); op->launches++;
   mg_v_cycle(mg, level - 1);
-  prolongate_add(mg->transfer[level], mg->solution[level], mg->solution[level - 1], opc->dev.n_owned, s); op->launches++;
+  prolongate_add(mg->transfer[level], mg->solution[level], mg->solution[level - 1], n_coarse_blocks, s); op->launches++;
   cheb_run(mg->smoothers[level], mg->solution[level], mg->defect[level], false);     // post-smoothing
 }
 
@@ -597,7 +600,14 @@ extern "C" {
 const char * exadg_b200_last_error(void) { return g_last_error.c_str(); }
 int exadg_b200_version(void) { return 100; }
 
-int exadg_b200_create_hypercube(const exadg_b200_hypercube_desc * desc, exadg_b200_operator ** out)
+static void set_helmholtz(exadg_b200_operator * op, const exadg_b200_helmholtz_data * hd)
+{
+  if (!hd) return;
+  if (hd->n_components < 1 || hd->n_components > 3) throw std::invalid_argument("n_components must be 1..3");
+  op->dev.helmholtz = true; op->dev.n_components = hd->n_components; op->dev.mass_coeff = hd->scaling_factor_mass; op->dev.laplace_coeff = hd->viscosity;
+}
+
+static int create_hypercube(const exadg_b200_hypercube_desc * desc, const exadg_b200_helmholtz_data * hdata, exadg_b200_operator ** out)
 {
   return guarded([&]() {
     if (!desc || !out) throw std::invalid_argument("null argument");
@@ -609,6 +619,7 @@ int exadg_b200_create_hypercube(const exadg_b200_hypercube_desc * desc, exadg_b2
     hd.rank = desc->rank; hd.world = desc->world < 1 ? 1 : desc->world;
     std::unique_ptr<exadg_b200_operator> op(new exadg_b200_operator);
     op->dev.degree = desc->degree;
+    set_helmholtz(op.get(), hdata);
     op->mesh = make_hypercube(hd);
     finish_setup(op.get(), desc->ip_factor, desc->force_general != 0);
     *out = op.release();
@@ -616,7 +627,7 @@ int exadg_b200_create_hypercube(const exadg_b200_hypercube_desc * desc, exadg_b2
   });
 }
 
-int exadg_b200_create(const exadg_b200_mesh_desc * desc, exadg_b200_operator ** out)
+static int create_from_mesh(const exadg_b200_mesh_desc * desc, const exadg_b200_helmholtz_data * hdata, exadg_b200_operator ** out)
 {
   return guarded([&]() {
     if (!desc || !out || !desc->mapping_points || !desc->neighbors || !desc->neighbor_face || !desc->boundary_type) throw std::invalid_argument("null argument");
@@ -624,6 +635,7 @@ int exadg_b200_create(const exadg_b200_mesh_desc * desc, exadg_b200_operator ** 
     if (desc->mapping_degree < 1 || desc->mapping_degree > 8) throw std::invalid_argument("mapping_degree must be in 1..8");
     std::unique_ptr<exadg_b200_operator> op(new exadg_b200_operator);
     op->dev.degree = desc->degree;
+    set_helmholtz(op.get(), hdata);
     HostMesh & M = op->mesh;
     M.mapping_degree = desc->mapping_degree; M.n_owned = desc->n_cells_owned; M.n_ghost = desc->n_cells_ghost;
     M.n_global_cells = desc->n_global_cells > 0 ? desc->n_global_cells : desc->n_cells_owned;
@@ -643,8 +655,38 @@ int exadg_b200_create(const exadg_b200_mesh_desc * desc, exadg_b200_operator ** 
     M.cartesian_uniform = detect_cartesian_uniform(M, h);
     if (M.cartesian_uniform) for (int e = 0; e < 3; ++e) M.h[e] = h[e];
     M.build_faces();
+    if (op->dev.helmholtz && M.n_ghost > 0) throw std::runtime_error("the Helmholtz / viscous operator is not partitioned yet (n_cells_ghost must be 0)");
     finish_setup(op.get(), desc->ip_factor, desc->force_general != 0);
     *out = op.release();
+    return EXADG_B200_OK;
+  });
+}
+
+int exadg_b200_create_hypercube(const exadg_b200_hypercube_desc * desc, exadg_b200_operator ** out) { return create_hypercube(desc, nullptr, out); }
+int exadg_b200_create(const exadg_b200_mesh_desc * desc, exadg_b200_operator ** out) { return create_from_mesh(desc, nullptr, out); }
+int exadg_b200_create_hypercube_helmholtz(const exadg_b200_hypercube_desc * desc, const exadg_b200_helmholtz_data * data, exadg_b200_operator ** out)
+{ if (!data) { g_last_error = "null helmholtz data"; return EXADG_B200_ERR_ARG; } return create_hypercube(desc, data, out); }
+int exadg_b200_create_helmholtz(const exadg_b200_mesh_desc * desc, const exadg_b200_helmholtz_data * data, exadg_b200_operator ** out)
+{ if (!data) { g_last_error = "null helmholtz data"; return EXADG_B200_ERR_ARG; } return create_from_mesh(desc, data, out); }
+
+int exadg_b200_n_components(const exadg_b200_operator * op) { return op ? op->dev.n_components : -1; }
+/* MomentumOperator::set_scaling_factor_mass_operator (momentum_operator.cpp:147-153): gamma_0 / dt changes with the time step */
+int exadg_b200_set_scaling_factor_mass(exadg_b200_operator * op, double scaling_factor_mass)
+{
+  return guarded([&]() {
+    if (!op) throw std::invalid_argument("null operator");
+    if (!op->dev.helmholtz) throw std::runtime_error("exadg_b200_set_scaling_factor_mass: not a Helmholtz operator (create it with exadg_b200_create_*_helmholtz)");
+    op->dev.mass_coeff = scaling_factor_mass;
+    return EXADG_B200_OK;
+  });
+}
+/* InverseMassOperator::apply (I/operators/inverse_mass_operator.h) */
+int exadg_b200_inverse_mass_vmult(exadg_b200_operator * op, double * dst, const double * src)
+{
+  return guarded([&]() {
+    if (!op) throw std::invalid_argument("null operator");
+    check_ptr(dst, "dst"); check_ptr(src, "src");
+    launch_inverse_mass(op->dev, dst, src, op->stream); op->launches++;
     return EXADG_B200_OK;
   });
 }
@@ -656,6 +698,7 @@ int exadg_b200_destroy(exadg_b200_operator * op)
   DeviceOperator & D = op->dev;
   cartesian_plan_destroy(D);
   if (op->p2p) D.ghost = op->ghost_alloc;
+  cudaFree(D.cellJxW);
   cudaFree(D.nb); cudaFree(D.face_id); cudaFree(D.face_info); cudaFree(D.cellG); cudaFree(D.faceG); cudaFree(D.tau_f); cudaFree(D.tau_cell); cudaFree(D.ghost);
   for (auto p : op->p2p_peer_regions) if (p) cudaIpcCloseMemHandle(p);
   if (op->p2p_region) cudaFree(op->p2p_region);
@@ -885,7 +928,11 @@ int exadg_b200_subtract_mean_value(exadg_b200_operator * op, double * vec)
 }
 
 /* ---- inhomogeneous boundary data, right-hand side, error norms ---- */
-static void * post_of(exadg_b200_operator * op) { return post_get(op->post, op->dev, op->mesh, 0.0, op->stream); }
+static void * post_of(exadg_b200_operator * op)
+{
+  if (op->dev.helmholtz) throw std::runtime_error("rhs / evaluate / error norms are implemented for the scalar Laplace operator only");
+  return post_get(op->post, op->dev, op->mesh, 0.0, op->stream);
+}
 
 int exadg_b200_n_boundary_faces(exadg_b200_operator * op, int64_t * n_faces)
 {
@@ -1141,6 +1188,8 @@ int exadg_b200_multigrid_create(int n_levels, exadg_b200_operator * const * ops,
         TransferTable & T = mg->transfer[l];
         std::memset(&T, 0, sizeof(T));
         T.nf = op->dev.n; T.nc = c->dev.n;
+        if (op->dev.n_components != c->dev.n_components) throw std::invalid_argument("multigrid levels with different numbers of components");
+        if (op->dev.n_components > 1 && op->dev.degree == c->dev.degree) throw std::runtime_error("h-transfer of vector-valued fields is not implemented");
         if (op->dev.n_owned == c->dev.n_owned && op->dev.degree > c->dev.degree && op->mesh.global_offset == c->mesh.global_offset) {
           T.h = 0; embedding_1d(op->dev.degree, c->dev.degree, 0, 1, T.I[0]);
         } else if (op->dev.degree == c->dev.degree && op->dev.n_owned == 8 * c->dev.n_owned && op->mesh.global_offset == 8 * c->mesh.global_offset) {

@@ -117,7 +117,7 @@ __global__ void tau_kernel(MapTables t, const double * __restrict__ xmap, const 
   tau[c] = surface / volume;
 }
 
-__global__ void cell_metric_kernel(MapTables t, const double * __restrict__ xmap, int64_t n_cells, double * __restrict__ cellG)
+__global__ void cell_metric_kernel(MapTables t, const double * __restrict__ xmap, int64_t n_cells, double * __restrict__ cellG, double * __restrict__ cellJxW)
 {
   const int nq = t.nq, nq3 = nq * nq * nq;
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -128,6 +128,7 @@ __global__ void cell_metric_kernel(MapTables t, const double * __restrict__ xmap
   jacobian_dev(t, xmap, c, xi, J);
   const double det = det3(J); inv3(J, det, Ji);
   const double jxw = det * t.w[q0] * t.w[q1] * t.w[q2];
+  if (cellJxW) cellJxW[idx] = jxw;
   // G[e][g] = sum_i Ji[e][i] Ji[g][i] * JxW
   double * out = cellG + (size_t)c * 6 * nq3 + q;
   const int e1[6] = {0, 1, 2, 0, 0, 1}, e2[6] = {0, 1, 2, 1, 2, 2};
@@ -223,7 +224,8 @@ void setup_geometry(DeviceOperator & op, const HostMesh & mesh, double ip_factor
   CUDA_CHECK(cudaMalloc(&op.tau_f, (size_t)mesh.n_faces * sizeof(double)));
   const int B = 128;
   tau_kernel<<<(unsigned)((nloc + B - 1) / B), B, 0, stream>>>(t, xmap, bt, nloc, op.tau_cell);
-  cell_metric_kernel<<<(unsigned)((mesh.n_owned * nq3 + B - 1) / B), B, 0, stream>>>(t, xmap, mesh.n_owned, op.cellG);
+  if (op.helmholtz) CUDA_CHECK(cudaMalloc(&op.cellJxW, (size_t)mesh.n_owned * nq3 * sizeof(double)));
+  cell_metric_kernel<<<(unsigned)((mesh.n_owned * nq3 + B - 1) / B), B, 0, stream>>>(t, xmap, mesh.n_owned, op.cellG, op.cellJxW);
   face_metric_kernel<<<(unsigned)((mesh.n_faces * nq2 + B - 1) / B), B, 0, stream>>>(t, xmap, op.tau_cell, face_cells, face_nos, face_bt, mesh.n_faces,
                                                                                      penalty_factor, op.faceG, op.tau_f);
   CUDA_CHECK(cudaGetLastError());

@@ -27,6 +27,9 @@ struct DeviceOperator
   double * faceG = nullptr;     // [n_faces][7][n^2] a_minus(3), a_plus(3), JxW
   double * tau_f = nullptr;     // [n_faces] penalty incl. (k+1)^2 IP_factor
   double * tau_cell = nullptr;  // [owned+ghost] surface/volume
+  double * cellJxW = nullptr;   // [owned][n^3] JxW at the cell quadrature points (mass term / inverse mass; Helmholtz operators only)
+  // Helmholtz / viscous operator: mass_coeff (v,u) + laplace_coeff a_SIPG(u,v) on each of n_components components
+  bool helmholtz = false; int n_components = 1; double mass_coeff = 0.0, laplace_coeff = 1.0;
   // ghost values of src, filled by the halo exchange
   double * ghost = nullptr;     // [n_ghost][n^3]
   // Cartesian fast path
@@ -44,6 +47,9 @@ void setup_geometry(DeviceOperator & op, const HostMesh & mesh, double ip_factor
 // dst (+)= A src on owned cells listed in cells[0..n_cells) (or all owned cells if cells == nullptr)
 void launch_vmult_general(const DeviceOperator & op, double * dst, const double * src, bool add, const int32_t * cells, int64_t n_cells, cudaStream_t stream);
 void launch_diagonal_general(const DeviceOperator & op, double * diag, bool add, cudaStream_t stream);
+// InverseMassOperator (I/operators/inverse_mass_operator.h; dealii CellwiseInverseMassMatrix): dst = M^-1 src cell by cell,
+// M_K = S^T diag(JxW) S with as many Gauss points as basis functions per direction => M_K^-1 = S^-1 diag(1/JxW) S^-T
+void launch_inverse_mass(const DeviceOperator & op, double * dst, const double * src, cudaStream_t stream);
 
 // ---- vmult_cartesian.cu ----
 bool cartesian_supported(int n);

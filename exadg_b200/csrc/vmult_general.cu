@@ -14,6 +14,9 @@
 //   u_q = S u;  cell: R = sum_e Dq_e^T [G (Dq u_q)];  faces: rank-1 updates of R along normal lines;
 //   y = S^T R   (S^T maps test coefficients back to the nodal basis since span{psi} = span{l}).
 // Quadrature-point physics follows laplace_operator.cpp:129-265 and laplace_operator.h:180-197.
+#include <algorithm>
+#include <stdexcept>
+
 #include "operator.cuh"
 
 namespace exadg_b200
@@ -32,6 +35,9 @@ struct GenArgs
   const double * cellG; const double * faceG; const double * tau_f;
   const double * src; const double * ghost; double * dst;
   const int32_t * cells; int64_t n_items; int64_t n_owned; int add;
+  // Helmholtz / viscous operator: mass * (v, u) + lap * a_SIPG(u, v) on each of ncomp components; an item is a
+  // (cell, component) pair and doubles as the block index of the vector (cell-major, then component)
+  int ncomp; double mass, lap; const double * cellJxW;
 };
 
 template<int N, bool TRANSPOSE>
@@ -67,7 +73,8 @@ __global__ void __launch_bounds__(N * N * CPB, GenCfg<N>::MIN_BLOCKS) vmult_gene
   double * W = F2 + SZ; // [10][N2]
   const int64_t item = (int64_t)blockIdx.x * CPB + lc;
   const bool valid = item < A.n_items;
-  const int64_t cell = valid ? (A.cells ? (int64_t)A.cells[item] : item) : (A.cells ? (int64_t)A.cells[0] : 0);
+  const int64_t block = valid ? (A.cells ? (int64_t)A.cells[item] : item) : (A.cells ? (int64_t)A.cells[0] : 0); // (cell, component)
+  const int64_t cell = block / A.ncomp; const int comp = (int)(block % A.ncomp);
 
   const int lbase[3] = {NP * (a + N * b), a + NP * N * b, a + NP * b};
   const int lstr[3] = {1, NP, NP * N};
@@ -80,7 +87,7 @@ __global__ void __launch_bounds__(N * N * CPB, GenCfg<N>::MIN_BLOCKS) vmult_gene
       const int nodal = a + N * (b + N * k);
       double v;
       if (MODE == 1) v = (nodal == col) ? 1.0 : 0.0;
-      else v = A.src[cell * N3 + nodal];
+      else v = A.src[block * N3 + nodal];
       Uq[a + NP * (b + N * k)] = v;
     }
     __syncthreads();
@@ -100,9 +107,9 @@ __global__ void __launch_bounds__(N * N * CPB, GenCfg<N>::MIN_BLOCKS) vmult_gene
       const double * g = A.cellG + (size_t)cell * 6 * N3 + q;
       const double gxx = g[0], gyy = g[N3], gzz = g[2 * N3], gxy = g[3 * N3], gxz = g[4 * N3], gyz = g[5 * N3];
       const double d0 = F0[s], d1 = F1[s], d2 = F2[s];
-      F0[s] = gxx * d0 + gxy * d1 + gxz * d2;
-      F1[s] = gxy * d0 + gyy * d1 + gyz * d2;
-      F2[s] = gxz * d0 + gyz * d1 + gzz * d2;
+      F0[s] = A.lap * (gxx * d0 + gxy * d1 + gxz * d2);
+      F1[s] = A.lap * (gxy * d0 + gyy * d1 + gyz * d2);
+      F2[s] = A.lap * (gxz * d0 + gyz * d1 + gzz * d2);
     }
     __syncthreads();
     // ---- P4: test with grad psi ----
@@ -113,6 +120,10 @@ __global__ void __launch_bounds__(N * N * CPB, GenCfg<N>::MIN_BLOCKS) vmult_gene
     double * R = F0;
 #pragma unroll
     for (int k = 0; k < N; ++k) { const int s = a + NP * (b + N * k); R[s] += F1[s] + F2[s]; }
+    if (A.cellJxW) { // MassKernel::get_volume_flux (mass_kernel.h:76-82): submit_value(scaling_factor * u)
+#pragma unroll
+      for (int k = 0; k < N; ++k) { const int s = a + NP * (b + N * k); R[s] = fma(A.mass * A.cellJxW[(size_t)cell * N3 + a + N * (b + N * k)], Uq[s], R[s]); }
+    }
     __syncthreads();
 
     // ---- P5: faces, one direction (two faces) at a time ----
@@ -141,7 +152,7 @@ __global__ void __launch_bounds__(N * N * CPB, GenCfg<N>::MIN_BLOCKS) vmult_gene
         nbc[s] = A.nb[cell * 6 + f]; F[s] = A.face_id[cell * 6 + f]; info[s] = A.face_info[cell * 6 + f];
         double v2 = 0.0, d2 = 0.0;
         if (MODE == 0 && nbc[s] >= 0) {
-          const double * un = (nbc[s] < A.n_owned) ? A.src + (size_t)nbc[s] * N3 : A.ghost + (size_t)(nbc[s] - A.n_owned) * N3;
+          const double * un = (nbc[s] < A.n_owned) ? A.src + ((size_t)nbc[s] * A.ncomp + comp) * N3 : A.ghost + ((size_t)(nbc[s] - A.n_owned) * A.ncomp + comp) * N3;
           const int sp = info[s] & 1; // side of the neighbour's face (standard orientation: same direction d)
           const int off = a * nstr[t1] + b * nstr[t2];
 #pragma unroll
@@ -198,8 +209,8 @@ __global__ void __launch_bounds__(N * N * CPB, GenCfg<N>::MIN_BLOCKS) vmult_gene
         else if (bt == BT_NEUMANN) { vpl = vm[s]; dnp = -dnm; }     // :45,124-127
         else if (MODE == 1) { vpl = 0.0; dnp = 0.0; }               // exterior function zero
         const double jump = vm[s] - vpl;
-        const double gf = -0.5 * jump;                              // laplace_operator.h:180-185
-        const double vf = 0.5 * (dnm + dnp) - tau * jump;           // laplace_operator.h:187-197
+        const double gf = A.lap * (-0.5 * jump);                    // laplace_operator.h:180-185 (viscous_operator.h:489-525 with nu)
+        const double vf = A.lap * (0.5 * (dnm + dnp) - tau * jump); // laplace_operator.h:187-197
         zc[s] = -vf * jxw;                                          // submit_value(-value_flux)
         cgd[s] = am[d] * gf * jxw;                                  // submit_normal_derivative(gradient_flux)
         Wv2t[s * N2 + r] = am[t1] * gf * jxw;
@@ -230,14 +241,14 @@ __global__ void __launch_bounds__(N * N * CPB, GenCfg<N>::MIN_BLOCKS) vmult_gene
       const int k = col / N2;
       if (valid && r == col % N2) {
         const double v = R[a + NP * (b + N * k)];
-        if (A.add) A.dst[cell * N3 + col] += v; else A.dst[cell * N3 + col] = v;
+        if (A.add) A.dst[block * N3 + col] += v; else A.dst[block * N3 + col] = v;
       }
     } else if (valid) {
 #pragma unroll
       for (int k = 0; k < N; ++k) {
         const int nodal = a + N * (b + N * k);
         const double v = R[a + NP * (b + N * k)];
-        if (A.add) A.dst[cell * N3 + nodal] += v; else A.dst[cell * N3 + nodal] = v;
+        if (A.add) A.dst[block * N3 + nodal] += v; else A.dst[block * N3 + nodal] = v;
       }
     }
     __syncthreads();
@@ -266,6 +277,7 @@ void launch_n(const DeviceOperator & op, double * dst, const double * src, bool 
   GenArgs A;
   A.nb = op.nb; A.face_id = op.face_id; A.face_info = op.face_info; A.cellG = op.cellG; A.faceG = op.faceG; A.tau_f = op.tau_f;
   A.src = src; A.ghost = op.ghost; A.dst = dst; A.cells = cells; A.n_items = n_items; A.n_owned = op.n_owned; A.add = add ? 1 : 0;
+  A.ncomp = op.n_components; A.mass = op.mass_coeff; A.lap = op.laplace_coeff; A.cellJxW = op.mass_coeff != 0.0 ? op.cellJxW : nullptr;
   if (n_items == 0) return;
   const unsigned grid = (unsigned)((n_items + CPB - 1) / CPB);
   vmult_general_kernel<N, CPB, MODE><<<grid, N * N * CPB, smem, stream>>>(T, A);
@@ -286,16 +298,74 @@ void dispatch(const DeviceOperator & op, double * dst, const double * src, bool 
     default: throw std::runtime_error("unsupported degree (1..7)");
   }
 }
+struct InvMassTable { int n; double Sinv[EXADG_MAX_N * EXADG_MAX_N]; };
+
+// one CTA per (cell, component) block: t = S^-T r (three sweeps), t /= JxW, dst = S^-1 t (three sweeps); fixed summation order
+__global__ void __launch_bounds__(128) inverse_mass_kernel(const InvMassTable T, const double * __restrict__ jxw, int ncomp, double * __restrict__ dst,
+                                                           const double * __restrict__ src, int64_t n_blocks)
+{
+  __shared__ double A[512], B[512];
+  const int n = T.n, n2 = n * n, n3 = n2 * n;
+  for (int64_t block = blockIdx.x; block < n_blocks; block += gridDim.x) {
+    const int64_t cell = block / ncomp;
+    for (int i = threadIdx.x; i < n3; i += blockDim.x) A[i] = src[block * n3 + i];
+    __syncthreads();
+    for (int pass = 0; pass < 2; ++pass) {
+      // pass 0: matrix S^-T (entry [o][i] = Sinv[i][o]); pass 1: matrix S^-1
+      for (int e = threadIdx.x; e < n3; e += blockDim.x) { // x
+        const int o = e % n, jk = e / n;
+        double v = 0.0;
+        for (int i = 0; i < n; ++i) v = fma(pass == 0 ? T.Sinv[i * n + o] : T.Sinv[o * n + i], A[i + n * jk], v);
+        B[e] = v;
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < n3; e += blockDim.x) { // y
+        const int i = e % n, o = (e / n) % n, k = e / n2;
+        double v = 0.0;
+        for (int j = 0; j < n; ++j) v = fma(pass == 0 ? T.Sinv[j * n + o] : T.Sinv[o * n + j], B[i + n * (j + n * k)], v);
+        A[e] = v;
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < n3; e += blockDim.x) { // z
+        const int ij = e % n2, o = e / n2;
+        double v = 0.0;
+        for (int k = 0; k < n; ++k) v = fma(pass == 0 ? T.Sinv[k * n + o] : T.Sinv[o * n + k], A[ij + n2 * k], v);
+        B[e] = pass == 0 ? v / jxw[cell * n3 + e] : v;
+      }
+      __syncthreads();
+      if (pass == 0) { for (int e = threadIdx.x; e < n3; e += blockDim.x) A[e] = B[e]; __syncthreads(); }
+    }
+    for (int e = threadIdx.x; e < n3; e += blockDim.x) dst[block * n3 + e] = B[e];
+    __syncthreads();
+  }
+}
+} // namespace
+
+void launch_inverse_mass(const DeviceOperator & op, double * dst, const double * src, cudaStream_t stream)
+{
+  if (!op.cellJxW) throw std::runtime_error("inverse mass: the operator was created without the mass data (exadg_b200_create_*_helmholtz)");
+  Tables1D tab(op.degree);
+  InvMassTable T; T.n = op.n;
+  const std::vector<real_t> Si = invert(tab.S, op.n);
+  for (int i = 0; i < op.n * op.n; ++i) T.Sinv[i] = (double)Si[i];
+  const int64_t n_blocks = op.n_owned * op.n_components;
+  if (n_blocks == 0) return;
+  inverse_mass_kernel<<<(unsigned)std::min<int64_t>(n_blocks, 148 * 16), 128, 0, stream>>>(T, op.cellJxW, op.n_components, dst, src, n_blocks);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+namespace
+{
 } // namespace
 
 void launch_vmult_general(const DeviceOperator & op, double * dst, const double * src, bool add, const int32_t * cells, int64_t n_cells, cudaStream_t stream)
 {
-  dispatch<0>(op, dst, src, add, cells, cells ? n_cells : op.n_owned, stream);
+  dispatch<0>(op, dst, src, add, cells, cells ? n_cells : op.n_owned * op.n_components, stream);
 }
 
 void launch_diagonal_general(const DeviceOperator & op, double * diag, bool add, cudaStream_t stream)
 {
-  dispatch<1>(op, diag, nullptr, add, nullptr, op.n_owned, stream);
+  dispatch<1>(op, diag, nullptr, add, nullptr, op.n_owned * op.n_components, stream);
 }
 
 } // namespace exadg_b200

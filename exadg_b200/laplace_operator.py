@@ -73,6 +73,33 @@ class LaplaceOperator:
         return op
 
     @classmethod
+    def hypercube_helmholtz(cls, degree, n_components=3, scaling_factor_mass=1.0, viscosity=1.0, n_subdivisions=1, n_refinements=0, mapping_degree=1,
+                            deformation=0.0, frequency=2, boundary=(0,) * 6, ip_factor=1.0):
+        """IncNS::MomentumOperator with the viscous term in Laplace formulation and constant viscosity (momentum_operator.cpp:376-480,
+        viscous_operator.h:365-560): scaling_factor_mass * M + viscosity * A_SIPG on every component."""
+        from . import HelmholtzData
+        _torch()
+        d = _desc(degree, n_subdivisions, n_refinements, mapping_degree, deformation, frequency, boundary, ip_factor, 0, 1, False)
+        hd = HelmholtzData(n_components, scaling_factor_mass, viscosity)
+        h = C.c_void_p()
+        _check(_lib().exadg_b200_create_hypercube_helmholtz(C.byref(d), C.byref(hd), C.byref(h)))
+        op = cls(h)
+        op.degree = degree
+        op.n_components = n_components
+        return op
+
+    def set_scaling_factor_mass(self, scaling_factor_mass):
+        """MomentumOperator::set_scaling_factor_mass_operator: gamma_0 / dt of the current time step."""
+        self.synchronize()
+        _check(_lib().exadg_b200_set_scaling_factor_mass(self._h, float(scaling_factor_mass)))
+
+    def inverse_mass_vmult(self, dst, src):
+        """InverseMassOperator::apply (inverse_mass_operator.h): the InverseMassPreconditioner of the momentum equation."""
+        self._order_after_torch()
+        _check(_lib().exadg_b200_inverse_mass_vmult(self._h, _ptr(dst, self._n_local), _ptr(src, self._n_local)))
+        self.synchronize()
+
+    @classmethod
     def from_mesh(cls, degree, mapping_degree, mapping_points, neighbors, neighbor_face, boundary_type, n_cells_ghost=0,
                   ip_factor=1.0, force_general=False):
         """What a reference-side binding passes after extracting the mesh from dealii::MatrixFree."""

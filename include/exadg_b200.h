@@ -82,6 +82,24 @@ int exadg_b200_version(void);
 int exadg_b200_create_hypercube(const exadg_b200_hypercube_desc *desc, exadg_b200_operator **op);
 int exadg_b200_create(const exadg_b200_mesh_desc *desc, exadg_b200_operator **op);
 int exadg_b200_destroy(exadg_b200_operator *op);
+
+/* Helmholtz / viscous operator of the incompressible Navier-Stokes module: the momentum operator with the viscous
+ * term in Laplace formulation and constant viscosity,  scaling_factor_mass * (v, u) + viscosity * a_SIPG(u, v)  on each of
+ * n_components components (I/incompressible_navier_stokes/spatial_discretization/operators/momentum_operator.cpp:376-480,
+ * viscous_operator.h:365-386 volume flux nu grad u, :489-560 gradient flux -1/2 nu [u] n and value flux nu ({dn u} - tau [u]),
+ * I/operators/mass_kernel.h:32-93; penalty as for the Laplace operator, interior_penalty_parameter.h:43-128).  Vectors hold
+ * FESystem(FE_DGQ(k)^n_components) DoFs: cell by cell, component blocks of (k+1)^3 values inside a cell.  Boundary types apply to
+ * every component (velocity Dirichlet walls / Neumann outflow / periodic).  These operators run the general kernel on one GPU
+ * (world = 1); vmult, vmult_add, calculate_(inverse_)diagonal, the Jacobi / Chebyshev / CG entry points and the multigrid apply. */
+typedef struct { int n_components; double scaling_factor_mass; double viscosity; } exadg_b200_helmholtz_data;
+int exadg_b200_create_hypercube_helmholtz(const exadg_b200_hypercube_desc *desc, const exadg_b200_helmholtz_data *data, exadg_b200_operator **op);
+int exadg_b200_create_helmholtz(const exadg_b200_mesh_desc *desc, const exadg_b200_helmholtz_data *data, exadg_b200_operator **op);
+int exadg_b200_n_components(const exadg_b200_operator *op);
+/* MomentumOperator::set_scaling_factor_mass_operator (momentum_operator.cpp): gamma_0 / dt of the current time step */
+int exadg_b200_set_scaling_factor_mass(exadg_b200_operator *op, double scaling_factor_mass);
+/* InverseMassOperator::apply (I/operators/inverse_mass_operator.h): dst = M^-1 src, cell-wise exact inverse of the DG mass matrix
+ * (Gauss(k+1) quadrature: M_K = S^T diag(JxW) S); the InverseMassPreconditioner of the momentum equation */
+int exadg_b200_inverse_mass_vmult(exadg_b200_operator *op, double *dst, const double *src);
 /* bind to a CUDA stream (cudaStream_t passed as void*); default: a stream owned by the operator */
 int exadg_b200_set_stream(exadg_b200_operator *op, void *cuda_stream);
 int exadg_b200_synchronize(exadg_b200_operator *op);

@@ -21,6 +21,7 @@
 #include <stdexcept>
 #include <string>
 #include <utility>
+#include <vector>
 
 #include "../exadg_b200.h"
 
@@ -64,6 +65,10 @@ public:
   explicit LaplaceOperator(exadg_b200_hypercube_desc const & desc) { check(exadg_b200_create_hypercube(&desc, &op)); }
   // general mesh extracted from dealii::MatrixFree by the reference-side binding
   explicit LaplaceOperator(exadg_b200_mesh_desc const & desc) { check(exadg_b200_create(&desc, &op)); }
+  // IncNS::MomentumOperator with the viscous term in Laplace formulation (momentum_operator.cpp:376-480, viscous_operator.h:365-560):
+  // scaling_factor_mass * M + viscosity * A_SIPG on every component
+  LaplaceOperator(exadg_b200_hypercube_desc const & desc, exadg_b200_helmholtz_data const & data) { check(exadg_b200_create_hypercube_helmholtz(&desc, &data, &op)); }
+  LaplaceOperator(exadg_b200_mesh_desc const & desc, exadg_b200_helmholtz_data const & data) { check(exadg_b200_create_helmholtz(&desc, &data, &op)); }
   LaplaceOperator(LaplaceOperator const &) = delete;
   LaplaceOperator & operator=(LaplaceOperator const &) = delete;
   ~LaplaceOperator() { exadg_b200_destroy(op); }
@@ -90,6 +95,11 @@ public:
   void rhs_add(VectorType & dst) const { check(exadg_b200_rhs_add(op, dst.data())); }
   void evaluate(VectorType & dst, VectorType const & src) const { check(exadg_b200_evaluate(op, dst.data(), src.data())); }
   void evaluate_add(VectorType & dst, VectorType const & src) const { check(exadg_b200_evaluate_add(op, dst.data(), src.data())); }
+
+  // MomentumOperator::set_scaling_factor_mass_operator, InverseMassOperator::apply (Helmholtz operators)
+  void set_scaling_factor_mass_operator(double const factor) const { check(exadg_b200_set_scaling_factor_mass(op, factor)); }
+  void apply_inverse_mass(VectorType & dst, VectorType const & src) const { check(exadg_b200_inverse_mass_vmult(op, dst.data(), src.data())); }
+  unsigned int n_components() const { return (unsigned int)exadg_b200_n_components(op); }
 
   // dealii::VectorTools::subtract_mean_value for the singular (pressure Poisson) system
   void subtract_mean_value(VectorType & v) const { check(exadg_b200_subtract_mean_value(op, v.data())); }
@@ -147,6 +157,37 @@ public:
 private:
   exadg_b200_operator * op = nullptr;
   mutable double time = 0.0; // operator_base.h:473
+};
+
+// MultigridPreconditionerBase on DG levels (I/solvers_and_preconditioners/multigrid/multigrid_preconditioner_base.cpp): the level
+// operators are created by the caller (coarse -> fine, exadg_b200_multigrid_levels gives the list), vmult = one V-cycle
+class MultigridPreconditioner
+{
+public:
+  typedef DeviceVector VectorType;
+  explicit MultigridPreconditioner(std::vector<LaplaceOperator const *> const & levels, int smoother_iterations = 5, double smoothing_range = 20.0,
+                                   int iterations_eigenvalue_estimation = 20, double coarse_abs_tol = 1e-12, double coarse_rel_tol = 1e-3, int coarse_max_iter = 10000)
+  {
+    std::vector<exadg_b200_operator *> h;
+    for (auto const * l : levels) h.push_back(l->handle());
+    check(exadg_b200_multigrid_create((int)h.size(), h.data(), smoother_iterations, smoothing_range, iterations_eigenvalue_estimation, coarse_abs_tol, coarse_rel_tol,
+                                      coarse_max_iter, &mg));
+  }
+  MultigridPreconditioner(MultigridPreconditioner const &) = delete;
+  MultigridPreconditioner & operator=(MultigridPreconditioner const &) = delete;
+  ~MultigridPreconditioner() { exadg_b200_multigrid_destroy(mg); }
+  void vmult(VectorType & dst, VectorType const & src) const { check(exadg_b200_multigrid_vmult(mg, dst.data(), src.data())); }
+  // Krylov::KrylovSolver::solve with "cg" and Preconditioner::Multigrid
+  unsigned int solve_cg(LaplaceOperator const & A, VectorType & dst, VectorType const & rhs, double abs_tol, double rel_tol, unsigned int max_iter) const
+  {
+    int n_iter = 0;
+    check(exadg_b200_cg_solve_multigrid(A.handle(), dst.data(), rhs.data(), mg, abs_tol, rel_tol, (int)max_iter, &n_iter, nullptr));
+    return (unsigned int)n_iter;
+  }
+  exadg_b200_multigrid * handle() const { return mg; }
+
+private:
+  exadg_b200_multigrid * mg = nullptr;
 };
 
 } // namespace B200
