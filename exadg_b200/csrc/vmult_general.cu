@@ -15,6 +15,7 @@
 //   y = S^T R   (S^T maps test coefficients back to the nodal basis since span{psi} = span{l}).
 // Quadrature-point physics follows laplace_operator.cpp:129-265 and laplace_operator.h:180-197.
 #include <algorithm>
+#include <cstdlib>
 #include <stdexcept>
 
 #include "operator.cuh"
