@@ -345,6 +345,84 @@ def callers_block(op, src, n_global, degree):
     return out
 
 
+def applications_block():
+    """Secondary figures for the solver-level configurations of BASELINE.json (N=1, after the timed region; freed before returning):
+    config 3 - full Poisson solve of applications/poisson/sine (curved mesh, k=4, CG + multigrid with Chebyshev/point-Jacobi smoothers),
+    config 4 - the two operators of the dual-splitting Navier-Stokes solver (pressure Poisson k=4, viscous Helmholtz k=5, 3 components)."""
+    import numpy as np
+    import torch
+    import exadg_b200
+    out = {}
+    w = 3.0 * np.pi
+
+    def solution(x):
+        return np.sin(w * x[..., 0]) * np.sin(w * x[..., 1]) * np.sin(w * x[..., 2])
+
+    def timed(fn, reps=1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / reps
+
+    # ---- config 3: applications/poisson/sine (application.h:134-178): deformation 0.15, MappingQ(3), Dirichlet + Neumann, rel 1e-10 ----
+    args = dict(degree=4, n_subdivisions=2, n_refinements=4, mapping_degree=3, deformation=0.15, boundary=(1, 2, 1, 1, 1, 1))
+    t0 = time.perf_counter()
+    op = exadg_b200.LaplaceOperator.hypercube(**args)
+    op.use_torch_stream()
+    mg = exadg_b200.MultigridPreconditioner.hypercube(args, "phMG", "Bisect", fine_operator=op)
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t0
+    xyz, bt = op.boundary_quadrature_points()
+    neumann = w * np.cos(w * xyz[..., 0]) * np.sin(w * xyz[..., 1]) * np.sin(w * xyz[..., 2])
+    op.set_boundary_values(np.where((bt == exadg_b200.DIRICHLET)[:, None], solution(xyz), neumann))
+    b = op.initialize_dof_vector()
+    op.rhs(b)
+    op.integrate_source_add(b, 3.0 * w * w * solution(op.cell_quadrature_points(5)))
+    x = op.initialize_dof_vector()
+    solver = exadg_b200.KrylovSolverCG(op, mg, exadg_b200.SolverData(1000, 1e-20, 1e-10))
+    solver.solve(x, b)  # warm-up (work vectors, coarse solution)
+    x.zero_()
+    t = timed(lambda: solver.solve(x, b))
+    err = op.l2_error(x, solution(op.cell_quadrature_points(7)))
+    jac = exadg_b200.KrylovSolverCG(op, exadg_b200.JacobiPreconditioner(op), exadg_b200.SolverData(10000, 1e-20, 1e-10))
+    xj = op.initialize_dof_vector()
+    tj = timed(lambda: jac.solve(xj, b))
+    out["poisson_solve"] = {"dofs": op.n(), "levels": mg.levels, "cg_iterations": solver.n, "solve_ms": t * 1e3, "dofs_per_s": op.n() / t, "setup_s": t_setup,
+                            "relative_l2_error": err, "coarse_cg_iterations_total": mg.info()["coarse_iterations"],
+                            "jacobi_cg_iterations": jac.n, "jacobi_solve_ms": tj * 1e3,
+                            "what": "applications/poisson/sine: k=4, 32^3 cells, sine-deformed (0.15) MappingQ(3) mesh, Dirichlet + Neumann, CG rel 1e-10 with phMG "
+                                    "(DG levels k=4,2,1 then h-coarsening, Chebyshev(5)/point-Jacobi smoothers, CG + point Jacobi to 1e-3 on the coarsest level); FP64 levels"}
+    del solver, jac, mg, op, x, xj, b
+    torch.cuda.empty_cache()
+
+    # ---- config 4: Taylor-Green vortex operators (periodic box, k_u = 5, k_p = 4): pressure Poisson vmult, viscous Helmholtz vmult ----
+    cells = dict(n_subdivisions=3, n_refinements=4)  # 48^3 cells
+    pres = exadg_b200.LaplaceOperator.hypercube(degree=4, **cells)
+    pres.use_torch_stream()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    u = torch.rand(pres.local_size(), dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    y = pres.initialize_dof_vector()
+    pres.vmult_async(y, u)
+    tp = timed(lambda: pres.vmult_async(y, u), 20)
+    visc = exadg_b200.LaplaceOperator.hypercube_helmholtz(5, 3, 200.0, 1.0 / 1600.0, **cells)
+    visc.use_torch_stream()
+    uv = torch.rand(visc.local_size(), dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    yv = visc.initialize_dof_vector()
+    visc.vmult_async(yv, uv)
+    tv = timed(lambda: visc.vmult_async(yv, uv), 5)
+    out["ins_operators"] = {"cells": 48 ** 3, "pressure_poisson": {"degree": 4, "dofs": pres.n(), "vmult_ms": tp * 1e3, "dofs_per_s": pres.n() / tp, "singular": bool(pres.operator_is_singular())},
+                            "viscous_helmholtz": {"degree": 5, "components": 3, "dofs": visc.n(), "vmult_ms": tv * 1e3, "dofs_per_s": visc.n() / tv, "kernel": "general (stored metrics)"},
+                            "what": "operators of the dual-splitting scheme on the Taylor-Green box (periodic, 48^3 cells): pressure Poisson = the SIPG Laplace fast path at k=4; "
+                                    "viscous step = gamma0/dt M + nu A_SIPG on 3 velocity components at k=5 (general kernel)"}
+    del pres, visc, u, y, uv, yv
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu(args):
     import torch
     import exadg_b200
@@ -539,6 +617,12 @@ def run_gpu(args):
                 out["callers"] = callers_block(op, src, n_global, degree)
             except Exception as e:  # secondary figures must not take the headline down
                 out["callers"] = {"error": str(e)[:200]}
+            try:
+                del src, dst
+                torch.cuda.empty_cache()
+                out["applications"] = applications_block()
+            except Exception as e:
+                out["applications"] = {"error": str(e)[:300]}
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(degree, seconds=args.cpu_seconds, cells_1d=n_sub << refine)[0]
         if not args.no_fp64_peak:

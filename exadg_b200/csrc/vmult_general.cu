@@ -59,16 +59,33 @@ __device__ __forceinline__ void sweep(const double * __restrict__ M, const doubl
 // MODE 0: dst (+)= A src.  MODE 1: diagonal (unit vectors column by column, neighbour function zero:
 // do_face_int_integral, laplace_operator.cpp:165-191; operator_base.cpp:1552-1616).
 // resident CTAs per SM the register allocation is tuned for (measured per degree on B200, curved periodic box)
-template<int N> struct GenCfg { static constexpr int MIN_BLOCKS = (N == 5 || N == 7) ? 2 : 4; };
+// N^2 <= 32: the lines of a cell live in ONE warp (32 / N^2 cells per warp; spare lanes shadow line 0 of the warp's first cell: same
+// addresses, same values), so every barrier between the sweeps is a __syncwarp and the warps of a CTA run decoupled from each
+// other; larger N: N^2 threads per cell and block barriers
+template<int N> struct GenCfg
+{
+  static constexpr int MIN_BLOCKS = (N == 5 || N == 7) ? 2 : 4;
+  static constexpr bool WARP_CELLS = (N * N <= 32);
+  static constexpr int CPW = WARP_CELLS ? 32 / (N * N) : 0;                      // cells per warp
+  static constexpr int WARPS = (N == 5) ? 8 : 4;                                  // warps per CTA (warp-cell layout)
+  static constexpr int CPB = WARP_CELLS ? CPW * WARPS : ((N * N >= 64) ? 2 : 4);  // cells per CTA
+  static constexpr int THREADS = WARP_CELLS ? 32 * WARPS : N * N * CPB;
+};
+template<int N>
+__device__ __forceinline__ void gen_sync() { if (GenCfg<N>::WARP_CELLS) __syncwarp(); else __syncthreads(); }
+
 template<int N, int CPB, int MODE>
-__global__ void __launch_bounds__(N * N * CPB, GenCfg<N>::MIN_BLOCKS) vmult_general_kernel(const __grid_constant__ GenTables<N> T, const GenArgs A)
+__global__ void __launch_bounds__(GenCfg<N>::THREADS, GenCfg<N>::MIN_BLOCKS) vmult_general_kernel(const __grid_constant__ GenTables<N> T, const GenArgs A)
 {
   constexpr int NP = N | 1;          // odd x-extent: conflict-free 64-bit shared accesses in every direction
   constexpr int SZ = NP * N * N;
   constexpr int N2 = N * N, N3 = N * N * N;
   constexpr int FS = 10 * N2;        // face scratch per cell
   extern __shared__ double smem[];
-  const int t = threadIdx.x, lc = t / N2, r = t % N2, a = r % N, b = r / N;
+  const int t = threadIdx.x;
+  const int lane_ok = GenCfg<N>::WARP_CELLS ? ((t & 31) < GenCfg<N>::CPW * N2) : 1;
+  const int lc = GenCfg<N>::WARP_CELLS ? (t >> 5) * GenCfg<N>::CPW + (lane_ok ? (t & 31) / N2 : 0) : t / N2;
+  const int r = GenCfg<N>::WARP_CELLS ? (lane_ok ? (t & 31) % N2 : 0) : t % N2, a = r % N, b = r / N;
   double * Uq = smem + (size_t)lc * (4 * SZ + FS);
   double * F0 = Uq + SZ, * F1 = F0 + SZ, * F2 = F1 + SZ;
   double * W = F2 + SZ; // [10][N2]
@@ -91,16 +108,16 @@ __global__ void __launch_bounds__(N * N * CPB, GenCfg<N>::MIN_BLOCKS) vmult_gene
       else v = A.src[block * N3 + nodal];
       Uq[a + NP * (b + N * k)] = v;
     }
-    __syncthreads();
+    gen_sync<N>();
     // ---- P1: to the collocation basis ----
-    sweep<N, false>(T.S, Uq, Uq, lbase[0], lstr[0]); __syncthreads();
-    sweep<N, false>(T.S, Uq, Uq, lbase[1], lstr[1]); __syncthreads();
-    sweep<N, false>(T.S, Uq, Uq, lbase[2], lstr[2]); __syncthreads();
+    sweep<N, false>(T.S, Uq, Uq, lbase[0], lstr[0]); gen_sync<N>();
+    sweep<N, false>(T.S, Uq, Uq, lbase[1], lstr[1]); gen_sync<N>();
+    sweep<N, false>(T.S, Uq, Uq, lbase[2], lstr[2]); gen_sync<N>();
     // ---- P2: reference gradient ----
     sweep<N, false>(T.Dq, Uq, F0, lbase[0], lstr[0]);
     sweep<N, false>(T.Dq, Uq, F1, lbase[1], lstr[1]);
     sweep<N, false>(T.Dq, Uq, F2, lbase[2], lstr[2]);
-    __syncthreads();
+    gen_sync<N>();
     // ---- P3: flux = G grad (get_gradient + submit_gradient, laplace_operator.cpp:135) ----
 #pragma unroll
     for (int k = 0; k < N; ++k) {
@@ -112,12 +129,12 @@ __global__ void __launch_bounds__(N * N * CPB, GenCfg<N>::MIN_BLOCKS) vmult_gene
       F1[s] = A.lap * (gxy * d0 + gyy * d1 + gyz * d2);
       F2[s] = A.lap * (gxz * d0 + gyz * d1 + gzz * d2);
     }
-    __syncthreads();
+    gen_sync<N>();
     // ---- P4: test with grad psi ----
     sweep<N, true>(T.Dq, F0, F0, lbase[0], lstr[0]);
     sweep<N, true>(T.Dq, F1, F1, lbase[1], lstr[1]);
     sweep<N, true>(T.Dq, F2, F2, lbase[2], lstr[2]);
-    __syncthreads();
+    gen_sync<N>();
     double * R = F0;
 #pragma unroll
     for (int k = 0; k < N; ++k) { const int s = a + NP * (b + N * k); R[s] += F1[s] + F2[s]; }
@@ -125,7 +142,7 @@ __global__ void __launch_bounds__(N * N * CPB, GenCfg<N>::MIN_BLOCKS) vmult_gene
 #pragma unroll
       for (int k = 0; k < N; ++k) { const int s = a + NP * (b + N * k); R[s] = fma(A.mass * A.cellJxW[(size_t)cell * N3 + a + N * (b + N * k)], Uq[s], R[s]); }
     }
-    __syncthreads();
+    gen_sync<N>();
 
     // ---- P5: faces, one direction (two faces) at a time ----
 #pragma unroll
@@ -166,7 +183,7 @@ __global__ void __launch_bounds__(N * N * CPB, GenCfg<N>::MIN_BLOCKS) vmult_gene
         }
         Wv2[s * N2 + r] = v2; Wd2[s * N2 + r] = d2;
       }
-      __syncthreads();
+      gen_sync<N>();
       // nodal -> collocation on the face, first tangential direction
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
@@ -175,7 +192,7 @@ __global__ void __launch_bounds__(N * N * CPB, GenCfg<N>::MIN_BLOCKS) vmult_gene
         for (int p = 0; p < N; ++p) { x = fma(T.S[a * N + p], Wv2[s * N2 + p + N * b], x); y = fma(T.S[a * N + p], Wd2[s * N2 + p + N * b], y); }
         Wv2t[s * N2 + r] = x; Wd2t[s * N2 + r] = y;
       }
-      __syncthreads();
+      gen_sync<N>();
       double vp[2], dp[2];
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
@@ -185,7 +202,7 @@ __global__ void __launch_bounds__(N * N * CPB, GenCfg<N>::MIN_BLOCKS) vmult_gene
         vp[s] = x; dp[s] = y;
         Wv2[s * N2 + r] = x;
       }
-      __syncthreads();
+      gen_sync<N>();
       double zc[2], cgd[2];
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
@@ -217,7 +234,7 @@ __global__ void __launch_bounds__(N * N * CPB, GenCfg<N>::MIN_BLOCKS) vmult_gene
         Wv2t[s * N2 + r] = am[t1] * gf * jxw;
         Wd2t[s * N2 + r] = am[t2] * gf * jxw;
       }
-      __syncthreads();
+      gen_sync<N>();
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         double z = zc[s];
@@ -232,12 +249,12 @@ __global__ void __launch_bounds__(N * N * CPB, GenCfg<N>::MIN_BLOCKS) vmult_gene
         x = fma(T.sv[1][i], zc[1], x); x = fma(T.sd[1][i], cgd[1], x);
         R[lbase[d] + i * lstr[d]] = x;
       }
-      __syncthreads();
+      gen_sync<N>();
     }
     // ---- P6: back to the nodal basis, write ----
-    sweep<N, true>(T.S, R, R, lbase[0], lstr[0]); __syncthreads();
-    sweep<N, true>(T.S, R, R, lbase[1], lstr[1]); __syncthreads();
-    sweep<N, true>(T.S, R, R, lbase[2], lstr[2]); __syncthreads();
+    sweep<N, true>(T.S, R, R, lbase[0], lstr[0]); gen_sync<N>();
+    sweep<N, true>(T.S, R, R, lbase[1], lstr[1]); gen_sync<N>();
+    sweep<N, true>(T.S, R, R, lbase[2], lstr[2]); gen_sync<N>();
     if (MODE == 1) {
       const int k = col / N2;
       if (valid && r == col % N2) {
@@ -252,7 +269,7 @@ __global__ void __launch_bounds__(N * N * CPB, GenCfg<N>::MIN_BLOCKS) vmult_gene
         if (A.add) A.dst[block * N3 + nodal] += v; else A.dst[block * N3 + nodal] = v;
       }
     }
-    __syncthreads();
+    gen_sync<N>();
   }
 }
 
@@ -269,7 +286,7 @@ GenTables<N> make_tables()
 template<int N, int MODE>
 void launch_n(const DeviceOperator & op, double * dst, const double * src, bool add, const int32_t * cells, int64_t n_items, cudaStream_t stream)
 {
-  constexpr int CPB = (N * N >= 64) ? 2 : (N * N >= 36 ? 4 : (N * N >= 16 ? 8 : 16));
+  constexpr int CPB = GenCfg<N>::CPB;
   constexpr int NP = N | 1;
   static const GenTables<N> T = make_tables<N>();
   const size_t smem = (size_t)CPB * (4 * NP * N * N + 10 * N * N) * sizeof(double);
@@ -281,7 +298,7 @@ void launch_n(const DeviceOperator & op, double * dst, const double * src, bool 
   A.ncomp = op.n_components; A.mass = op.mass_coeff; A.lap = op.laplace_coeff; A.cellJxW = op.mass_coeff != 0.0 ? op.cellJxW : nullptr;
   if (n_items == 0) return;
   const unsigned grid = (unsigned)((n_items + CPB - 1) / CPB);
-  vmult_general_kernel<N, CPB, MODE><<<grid, N * N * CPB, smem, stream>>>(T, A);
+  vmult_general_kernel<N, CPB, MODE><<<grid, GenCfg<N>::THREADS, smem, stream>>>(T, A);
   CUDA_CHECK(cudaGetLastError());
 }
 
