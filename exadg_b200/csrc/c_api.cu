@@ -130,6 +130,9 @@ struct exadg_b200_operator
   void * comm = nullptr; bool own_comm = false;
   std::vector<int32_t *> d_send_lists; std::vector<double *> d_send_bufs;
   int32_t * d_interior = nullptr, * d_boundary = nullptr; int64_t n_interior = 0, n_boundary = 0;
+  // uniform box with Dirichlet / Neumann faces: batches of cells that see the interior penalty on all their faces run the affine fast
+  // kernel, the two cell layers next to the boundary (and the batches they share) the general kernel
+  bool hybrid = false; int32_t * d_hyb_batches = nullptr, * d_hyb_cells = nullptr; int64_t n_hyb_batches = 0, n_hyb_cells = 0;
   // peer-memory halo (NVLink): one region [ghost A | ghost B | flags[world]] mapped by all peers
   bool p2p = false; char * p2p_region = nullptr; size_t p2p_ghost_bytes = 0; long long p2p_epoch = 0;
   unsigned long long * d_put_done = nullptr; long long put_seq = 0; int put_grid = 0; int * d_work_counter = nullptr; // ticket counters of the in-launch export (GhostSync)
@@ -229,6 +232,41 @@ void finish_setup(exadg_b200_operator * op, double ip_factor, bool force_general
     D.tau_hat = tk * ip_factor * (D.degree + 1.0) * (D.degree + 1.0);
     if (cartesian_plan_create(D, M) == 0) D.cartesian = false;
   }
+  if (!D.cartesian && M.cartesian_uniform && !M.all_interior() && !force_general && !D.helmholtz && M.world <= 1 && M.n_ghost == 0 && cartesian_supported(D.n)
+      && !getenv("EXADG_B200_NO_HYBRID")) {
+    // tau_K counts true boundary faces with weight 1 (interior_penalty_parameter.h:88-89), and an interior face takes the larger of its two
+    // cells' values (laplace_operator.h:128-140): a cell sees the uniform interior penalty on all its faces iff neither it nor any of its
+    // neighbours has a boundary face.  Batches made of such cells only go to the fast kernel (they read, but never write, the others).
+    std::vector<uint8_t> has_bf(M.n_owned, 0);
+    for (int64_t c = 0; c < M.n_owned; ++c) for (int f = 0; f < 6; ++f) if (M.nb[c * 6 + f] < 0) has_bf[c] = 1;
+    std::vector<uint8_t> regular(M.n_owned, 1);
+    for (int64_t c = 0; c < M.n_owned; ++c) {
+      if (has_bf[c]) { regular[c] = 0; continue; }
+      for (int f = 0; f < 6; ++f) if (has_bf[M.nb[c * 6 + f]]) regular[c] = 0;
+    }
+    double tk = 0.0;
+    for (int e = 0; e < 3; ++e) tk += 1.0 / M.h[e];
+    D.tau_hat = tk * ip_factor * (D.degree + 1.0) * (D.degree + 1.0);
+    const std::vector<int32_t> nb_saved = M.nb;
+    for (int64_t i = 0; i < M.n_owned * 6; ++i) if (M.nb[i] < 0) M.nb[i] = (int32_t)(i / 6); // the plan of such batches is never launched
+    const size_t ok = cartesian_plan_create(D, M);
+    M.nb = nb_saved;
+    if (ok != 0) {
+      const int B = cartesian_batch_size(D), nbatch = cartesian_n_batches(D);
+      std::vector<int32_t> fast, slow;
+      for (int b = 0; b < nbatch; ++b) {
+        const int64_t b0 = (int64_t)b * B, b1 = std::min<int64_t>(b0 + B, M.n_owned);
+        bool reg = true;
+        for (int64_t c = b0; c < b1; ++c) reg &= (regular[c] != 0);
+        if (reg) fast.push_back(b); else for (int64_t c = b0; c < b1; ++c) slow.push_back((int32_t)c);
+      }
+      if (!fast.empty()) {
+        op->hybrid = true; op->n_hyb_batches = (int64_t)fast.size(); op->n_hyb_cells = (int64_t)slow.size();
+        CUDA_CHECK(cudaMalloc(&op->d_hyb_batches, fast.size() * 4)); CUDA_CHECK(cudaMemcpy(op->d_hyb_batches, fast.data(), fast.size() * 4, cudaMemcpyHostToDevice));
+        if (!slow.empty()) { CUDA_CHECK(cudaMalloc(&op->d_hyb_cells, slow.size() * 4)); CUDA_CHECK(cudaMemcpy(op->d_hyb_cells, slow.data(), slow.size() * 4, cudaMemcpyHostToDevice)); }
+      } else cartesian_plan_destroy(D);
+    }
+  }
   CUDA_CHECK(cudaStreamCreateWithFlags(&op->stream, cudaStreamNonBlocking));
   {
     // the halo exchange must not queue behind the interior-cell kernel: highest priority for its stream
@@ -268,6 +306,10 @@ void launch_vmult(exadg_b200_operator * op, double * dst, const double * src, bo
 {
   if (!stream) stream = op->stream;
   if (op->dev.cartesian) launch_vmult_cartesian_part(op->dev, dst, src, add, which, stream);
+  else if (op->hybrid && which == 0) {
+    launch_vmult_cartesian_list(op->dev, dst, src, add, op->d_hyb_batches, (int)op->n_hyb_batches, stream);
+    if (op->n_hyb_cells > 0) { launch_vmult_general(op->dev, dst, src, add, op->d_hyb_cells, op->n_hyb_cells, stream); op->launches++; }
+  }
   else if (which == 0) launch_vmult_general(op->dev, dst, src, add, nullptr, 0, stream);
   else {
     const int64_t nc = which == 1 ? op->n_interior : op->n_boundary;
@@ -698,7 +740,7 @@ int exadg_b200_destroy(exadg_b200_operator * op)
   DeviceOperator & D = op->dev;
   cartesian_plan_destroy(D);
   if (op->p2p) D.ghost = op->ghost_alloc;
-  cudaFree(D.cellJxW);
+  cudaFree(D.cellJxW); cudaFree(op->d_hyb_batches); cudaFree(op->d_hyb_cells);
   cudaFree(D.nb); cudaFree(D.face_id); cudaFree(D.face_info); cudaFree(D.cellG); cudaFree(D.faceG); cudaFree(D.tau_f); cudaFree(D.tau_cell); cudaFree(D.ghost);
   for (auto p : op->p2p_peer_regions) if (p) cudaIpcCloseMemHandle(p);
   if (op->p2p_region) cudaFree(op->p2p_region);
@@ -772,7 +814,7 @@ int64_t exadg_b200_n(const exadg_b200_operator * op) { return op ? op->dev.n_glo
 int64_t exadg_b200_local_size(const exadg_b200_operator * op) { return op ? op->n_local : -1; }
 int64_t exadg_b200_n_cells_owned(const exadg_b200_operator * op) { return op ? op->dev.n_owned : -1; }
 int64_t exadg_b200_n_cells_ghost(const exadg_b200_operator * op) { return op ? op->dev.n_ghost : -1; }
-int exadg_b200_is_cartesian_path(const exadg_b200_operator * op) { return op && op->dev.cartesian ? 1 : 0; }
+int exadg_b200_is_cartesian_path(const exadg_b200_operator * op) { return op ? (op->dev.cartesian ? 1 : (op->hybrid ? 2 : 0)) : 0; }
 int exadg_b200_kernel_launches(const exadg_b200_operator * op, int64_t * count) { if (!op || !count) return EXADG_B200_ERR_ARG; *count = op->launches; return EXADG_B200_OK; }
 
 int exadg_b200_initialize_dof_vector(const exadg_b200_operator * op, double ** vec)

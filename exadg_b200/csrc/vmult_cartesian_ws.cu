@@ -286,7 +286,8 @@ void ws_launch(const DeviceOperator & op, const void * p, double * dst, const do
   if (put.done) { // tickets are counted per launch of a fixed grid
     // with a work counter the first 64 CTAs export and join the batches late (they claim fewer items); otherwise every CTA does
     int * const counter = depth < 100 ? gs->counter : nullptr; // the warp-private kernel strides statically
-    put.n_export = counter ? std::min(grid, 64) : grid;
+    static const int n_export_ctas = []() { const char * e = std::getenv("EXADG_B200_EXPORT_CTAS"); const int v = e ? std::atoi(e) : 64; return v > 0 ? v : 64; }();
+    put.n_export = counter ? std::min(grid, n_export_ctas) : grid;
     A.counter = counter;
     if (counter) CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), stream));
     if (*gs->put_grid != grid) { CUDA_CHECK(cudaMemsetAsync(put.done, 0, 16 * sizeof(unsigned long long), stream)); *gs->put_seq = 0; *gs->put_grid = grid; }

@@ -114,7 +114,10 @@ int64_t exadg_b200_n(const exadg_b200_operator *op);
 int64_t exadg_b200_local_size(const exadg_b200_operator *op);   /* locally owned DoFs */
 int64_t exadg_b200_n_cells_owned(const exadg_b200_operator *op);
 int64_t exadg_b200_n_cells_ghost(const exadg_b200_operator *op);
-int exadg_b200_is_cartesian_path(const exadg_b200_operator *op);  /* 1 if the Cartesian fast kernel is used */
+/* 1: the affine fast kernels run on all cells (uniform box, all faces interior/periodic); 2: uniform box with Dirichlet / Neumann
+ * faces - the fast kernels run on the batches whose cells see the interior penalty on all their faces, the general kernel on the two
+ * cell layers next to the boundary; 0: general kernel */
+int exadg_b200_is_cartesian_path(const exadg_b200_operator *op);
 /* OperatorBase::operator_is_singular (I/operators/operator_base.h:196; OperatorBaseData::operator_is_singular): 1 if constants
  * lie in the kernel (no Dirichlet face: all-periodic or pure Neumann box) */
 int exadg_b200_operator_is_singular(const exadg_b200_operator *op);

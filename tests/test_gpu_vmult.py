@@ -81,6 +81,31 @@ def test_vmult_cartesian_with_boundaries(bc):
     assert rel(gpu_vmult(op, x), ref.vmult(x)) < TOL
 
 
+@pytest.mark.parametrize("degree", [1, 2, 3, 4, 5, 6, 7])
+def test_uniform_box_with_boundaries_takes_the_hybrid_fast_path(degree):
+    """Uniform box with Dirichlet / Neumann / periodic faces (the Cartesian sine case, laplace_operator.cpp:221-265): batches whose cells
+    see the interior penalty on all faces run the affine fast kernels, the two cell layers next to the boundary the general kernel."""
+    import exadg_b200
+    bc = (1, 2, 1, 1, 0, 0) if degree % 2 else (1, 1, 2, 1, 1, 1)
+    op, ref = make_pair(degree, 1, 4, 1, 0.0, bc)
+    assert op.is_cartesian_path == 2
+    x = synthetic_vector(ref.n_dofs)
+    y_ref = ref.vmult_cellwise(x)
+    assert rel(gpu_vmult(op, x), y_ref) < TOL
+    # vmult_add, diagonal and the general-only run of the same mesh
+    src = torch.from_numpy(x).cuda()
+    dst = torch.from_numpy(y_ref).cuda()
+    op.vmult_add(dst, src)
+    assert rel(dst.cpu().numpy(), 2 * y_ref) < TOL
+    gen, _ = make_pair(degree, 1, 4, 1, 0.0, bc, force_general=True)
+    assert gen.is_cartesian_path == 0
+    assert rel(gpu_vmult(gen, x), y_ref) < TOL
+    if degree <= 3:
+        d = op.initialize_dof_vector()
+        op.calculate_diagonal(d)
+        assert rel(d.cpu().numpy(), ref.diagonal()) < TOL
+
+
 def test_single_cell_periodic_is_its_own_neighbour():
     for degree in (2, 4, 5):
         op, ref = make_pair(degree, 1, 0)
