@@ -4,9 +4,10 @@
 Contract (see the task description): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line.
 A step = one vmult over the whole DoF vector.  Workload at N=1: BASELINE.json configs[1] at the degree the
 metric is quoted on (k=4): periodic Cartesian box, 96^3 cells, 110,592,000 DoFs (885 MB per vector, i.e.
-inputs larger than the 126 MB L2).  N>1 is weak scaling (per-GPU cell count kept ~constant: 120^3, 152^3,
-192^3 cells for N=2,4,8; N=8 is BASELINE.json configs[4]), cells partitioned p4est-style, ghost import over
-NCCL overlapped with interior cells.
+inputs larger than the 126 MB L2).  N>1 is weak scaling on the reference's admissible grids n_1d in {1,3,5} x 2^l
+(hypercube_resolution_parameters.h:114-165) closest to a constant per-GPU size: 128^3, 160^3, 192^3 cells for N=2,4,8
+(131 / 128 / 111 M DoFs per GPU; N=8 is BASELINE.json configs[4]), cells partitioned p4est-style, ghost import by NVLink
+peer-memory stores inside the operator launch.
 `--impl reference` times the CPU restatement of the reference (oracle/, OpenMP over all host cores) on a
 bounded sample of the same workload; the real deal.II/ExaDG binary cannot be built here.
 """
@@ -23,7 +24,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "DoFs/s of 3D SIPG Laplace matrix-free vmult (fp64, k=4)"
 B_ALG = 16.0  # algorithmic bytes per DoF of the affine vmult: read src once + write dst once
-GRIDS = {1: (3, 5), 2: (15, 3), 4: (19, 3), 8: (3, 6)}  # n_gpus -> (n_subdivisions, n_refinements): 96, 120, 152, 192 cells per direction
+GRIDS = {1: (3, 5), 2: (1, 7), 4: (5, 5), 8: (3, 6)}  # n_gpus -> (n_subdivisions, n_refinements): 96, 128, 160, 192 cells per direction
 
 
 def measured_peak():

@@ -363,12 +363,14 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
 // and 18 - 32 resident warps per SM.  Rows are padded to an odd stride so that consecutive lanes (consecutive lines) never share a
 // bank in any of the three sweep directions.
 // =====================================================================================================
-template<int N> struct LineCfg { static constexpr int B = 16; static constexpr int NT = B * N * N; static constexpr int RS = N | 1; static constexpr int CS = RS * N * N; };
+// BB cells per CTA: 16 (two octets) or 8 (one octet: half the shared memory and threads per CTA, so two to four CTAs share an SM and
+// the load / trace / sweep / store phases of different batches overlap, at the price of 3.0 instead of 2.5 out-of-batch faces per cell)
+template<int N, int BB> struct LineCfg { static constexpr int B = BB; static constexpr int NT = B * N * N; static constexpr int RS = N | 1; static constexpr int CS = RS * N * N; };
 
-template<int N>
-__global__ void __launch_bounds__(LineCfg<N>::NT, 1) vmult_cartesian_line_kernel(const __grid_constant__ CartTables<N> T, const CartArgs A)
+template<int N, int BB>
+__global__ void __launch_bounds__(LineCfg<N, BB>::NT, 1) vmult_cartesian_line_kernel(const __grid_constant__ CartTables<N> T, const CartArgs A)
 {
-  constexpr int B = LineCfg<N>::B, NT = LineCfg<N>::NT, RS = LineCfg<N>::RS, CS = LineCfg<N>::CS;
+  constexpr int B = LineCfg<N, BB>::B, NT = LineCfg<N, BB>::NT, RS = LineCfg<N, BB>::RS, CS = LineCfg<N, BB>::CS;
   constexpr int N2 = N * N, N3 = N2 * N;
   extern __shared__ __align__(128) double smem[];
   double * U = smem;                   // [B][N][N][RS] src values (x fastest, rows padded to RS)
@@ -1016,13 +1018,13 @@ void launch_n(const DeviceOperator & op, const CartPlan & plan, double * dst, co
   vmult_cartesian_kernel<N><<<A.n_items, B * N, plan.smem, stream>>>(T, A);
   CUDA_CHECK(cudaGetLastError());
 }
-template<int N>
-void launch_line(const DeviceOperator & op, const CartPlan & plan, double * dst, const double * src, bool add, int which, cudaStream_t stream, const int32_t * list = nullptr,
-                 int n_list = 0)
+template<int N, int BB>
+void launch_line_b(const DeviceOperator & op, const CartPlan & plan, double * dst, const double * src, bool add, int which, cudaStream_t stream, const int32_t * list,
+                   int n_list)
 {
   const CartTables<N> & T = *reinterpret_cast<const CartTables<N> *>(plan.tables.data());
-  if (first_use_on_device((const void *)vmult_cartesian_line_kernel<N>))
-    CUDA_CHECK(cudaFuncSetAttribute(vmult_cartesian_line_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+  if (first_use_on_device((const void *)vmult_cartesian_line_kernel<N, BB>))
+    CUDA_CHECK(cudaFuncSetAttribute(vmult_cartesian_line_kernel<N, BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
   CartArgs A;
   A.nb = op.nb; A.halo = plan.d_halo; A.halo_cnt = plan.d_cnt; A.src = src; A.ghost = op.ghost; A.dst = dst;
   A.n_owned = op.n_owned; A.H = plan.H; A.add = add ? 1 : 0;
@@ -1030,8 +1032,15 @@ void launch_line(const DeviceOperator & op, const CartPlan & plan, double * dst,
   A.n_items = which == 0 ? plan.n_batches : (which == 1 ? plan.n_interior : plan.n_boundary);
   if (list) { A.batches = list; A.n_items = n_list; }
   if (A.n_items == 0) return;
-  vmult_cartesian_line_kernel<N><<<A.n_items, LineCfg<N>::NT, plan.smem_line, stream>>>(T, A);
+  vmult_cartesian_line_kernel<N, BB><<<A.n_items, LineCfg<N, BB>::NT, plan.smem_line, stream>>>(T, A);
   CUDA_CHECK(cudaGetLastError());
+}
+template<int N>
+void launch_line(const DeviceOperator & op, const CartPlan & plan, double * dst, const double * src, bool add, int which, cudaStream_t stream, const int32_t * list = nullptr,
+                 int n_list = 0)
+{
+  if (plan.B == 8) launch_line_b<N, 8>(op, plan, dst, src, add, which, stream, list, n_list);
+  else launch_line_b<N, 16>(op, plan, dst, src, add, which, stream, list, n_list);
 }
 template<int N>
 void launch_pipe(const DeviceOperator & op, const CartPlan & plan, double * dst, const double * src, bool add, int which, cudaStream_t stream, const int32_t * list = nullptr,
@@ -1073,6 +1082,7 @@ void store_tables(CartPlan & P, const DeviceOperator & op)
 }
 
 static size_t plan_create(DeviceOperator & op, const HostMesh & mesh, bool allow_pipe);
+static int line_batch_default(int n) { (void)n; return 16; }
 
 // builds the batch plan (halo lists, interior/boundary batches, tables); returns the dynamic shared
 // memory per CTA, or 0 if the batch does not fit (caller falls back to the general kernel)
@@ -1085,6 +1095,11 @@ static size_t plan_create(DeviceOperator & op, const HostMesh & mesh, bool allow
   P.n = op.n;
   const int N = op.n;
   P.B = (N >= 6) ? 16 : ((N >= 4) ? 32 : 64);
+  if (N >= 6 && !getenv("EXADG_B200_NO_LINE")) { // line kernel: 8 or 16 cells per CTA (EXADG_B200_LINE_B; default per degree from the measurements)
+    const char * e = getenv("EXADG_B200_LINE_B");
+    const int want = e ? std::atoi(e) : line_batch_default(N);
+    P.B = (want == 8) ? 8 : 16;
+  }
   P.pipe = allow_pipe && (N == 5) && !getenv("EXADG_B200_NO_PIPE"); // n = 3 measured slower than the 64-cell kernel (0.99 vs 0.86 ms) // pipelined 4-warp kernel (EXADG_B200_NO_PIPE=1: the 5-warp kernel)
   if (P.pipe) P.B = (N == 3) ? PipeCfg<3>::B : PipeCfg<5>::B;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&P.n_sm, cudaDevAttrMultiProcessorCount, dev); if (P.n_sm < 1) P.n_sm = 148; }
@@ -1135,11 +1150,12 @@ static size_t plan_create(DeviceOperator & op, const HostMesh & mesh, bool allow
   }
   const int N2 = N * N, PS = N2 | 1, CS = N * PS;
   if (!P.pipe) P.smem = ((size_t)2 * P.B * CS + (size_t)P.B * 2 * N2 + (size_t)2 * P.H * N2) * sizeof(double) + (size_t)P.H * sizeof(int2) + (size_t)P.B * 12 * sizeof(int) + 16;
-  if (N >= 6 && P.B == 16 && !getenv("EXADG_B200_NO_LINE")) {
+  if (N >= 6 && (P.B == 16 || P.B == 8) && !getenv("EXADG_B200_NO_LINE")) {
     const int RS = N | 1;
     const size_t sl = ((size_t)2 * P.B * RS * N2 + (size_t)2 * P.B * N2 + (size_t)2 * P.H * N2) * sizeof(double) + (size_t)P.H * sizeof(int2) + (size_t)P.B * 12 * sizeof(int) + 16;
     if (sl <= 227 * 1024 - 1024) P.smem_line = sl;
   }
+  if (N >= 6 && P.B == 8 && !P.smem_line) { delete Pp; return 0; } // the plane kernel has 16-cell batches only
   if (P.smem > 227 * 1024 - 1024) { delete Pp; return 0; } // does not fit: caller falls back to the general kernel
   std::vector<int2> flat((size_t)P.n_batches * P.H, make_int2(0, 0));
   std::vector<int32_t> cnt(P.n_batches);

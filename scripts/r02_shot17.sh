@@ -1,0 +1,8 @@
+#!/bin/bash
+# N GPUs: bench line on the admissible grid of this N (128^3 / 160^3 / 192^3)
+mkdir -p gpurun_out
+N=${1:-2}
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 50 --warmup 5 > gpurun_out/r02_s17_bench_n${N}.json 2> gpurun_out/r02_s17_bench_n${N}.err
+echo "rc $?"
+python -c "import json;d=json.loads(open('gpurun_out/r02_s17_bench_n${N}.json').read().strip().splitlines()[-1]);print('n$N',d['value']/1e9,d['ms_per_step'],d['config']['workload'][:90],d['config']['invariants'], 'e2e', d['e2e']['value']/1e9, d['clocks'])"
+tail -2 gpurun_out/r02_s17_bench_n${N}.err
