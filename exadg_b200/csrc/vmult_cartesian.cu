@@ -84,7 +84,8 @@ __device__ __forceinline__ void tma_store_1d(void * gdst, const void * smem_src,
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-template<int N> struct CartCfg { static constexpr int B = (N >= 6) ? 16 : ((N >= 4) ? 32 : 64); };
+// cells per batch = consecutive cells of the Morton curve: 4x4x4 bricks (1.5 out-of-batch faces per cell) while 2 CTAs of B n threads fit an SM
+template<int N> struct CartCfg { static constexpr int B = (N >= 6) ? 16 : ((N >= 5) ? 32 : 64); };
 
 template<int N>
 __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_cartesian_kernel(const __grid_constant__ CartTables<N> T, const CartArgs A)
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(LineCfg<N, BB>::NT, 1) vmult_cartesian_line_ke
   const bool valid = c < nvalid;
 
   // ---- stage the batch (coalesced loads, 8 in flight per thread), its neighbour table and the halo list ----
-  const int cnt = A.halo_cnt[batch];
+  const int cnt = (A.add & 2) ? 0 : A.halo_cnt[batch]; // bit 1: timing experiment without the out-of-batch traces (results wrong)
   for (int i = t; i < B * 6; i += NT) { nbS[i] = (i / 6 < nvalid) ? A.nb[b0 * 6 + i] : -1; slotS[i] = -1; }
   for (int i = t; i < cnt; i += NT) hlS[i] = A.halo[(size_t)batch * A.H + i];
   {
@@ -533,7 +534,7 @@ __global__ void __launch_bounds__(LineCfg<N, BB>::NT, 1) vmult_cartesian_line_ke
   for (int i = t; i < nvalid * N3; i += NT) {
     const int cc = i / N3, rem = i % N3;
     const double v = Tt[cc * CS + (rem / N) * RS + rem % N];
-    if (A.add) A.dst[b0 * N3 + i] += v; else A.dst[b0 * N3 + i] = v;
+    if (A.add & 1) A.dst[b0 * N3 + i] += v; else A.dst[b0 * N3 + i] = v;
   }
 }
 
@@ -1032,6 +1033,8 @@ void launch_line_b(const DeviceOperator & op, const CartPlan & plan, double * ds
   A.n_items = which == 0 ? plan.n_batches : (which == 1 ? plan.n_interior : plan.n_boundary);
   if (list) { A.batches = list; A.n_items = n_list; }
   if (A.n_items == 0) return;
+  static const bool skip_halo = getenv("EXADG_B200_LINE_SKIP_HALO") != nullptr; // timing experiment only (results wrong)
+  if (skip_halo) A.add |= 2;
   vmult_cartesian_line_kernel<N, BB><<<A.n_items, LineCfg<N, BB>::NT, plan.smem_line, stream>>>(T, A);
   CUDA_CHECK(cudaGetLastError());
 }
@@ -1094,7 +1097,7 @@ static size_t plan_create(DeviceOperator & op, const HostMesh & mesh, bool allow
   CartPlan & P = *Pp;
   P.n = op.n;
   const int N = op.n;
-  P.B = (N >= 6) ? 16 : ((N >= 4) ? 32 : 64);
+  P.B = (N >= 6) ? 16 : ((N >= 5) ? 32 : 64);
   if (N >= 6 && !getenv("EXADG_B200_NO_LINE")) { // line kernel: 8 or 16 cells per CTA (EXADG_B200_LINE_B; default per degree from the measurements)
     const char * e = getenv("EXADG_B200_LINE_B");
     const int want = e ? std::atoi(e) : line_batch_default(N);
