@@ -62,6 +62,16 @@ struct WsCfg
   static constexpr int HLMAX = 64; // halo entries per batch the producers can stage (two per lane)
 };
 
+// Staged variant (four producer warps, R = 3): the out-of-batch neighbour cells are not read with strided 8-byte loads into registers but
+// copied whole and asynchronously (cp.async, 16 bytes per lane and instruction, 1008 bytes per cell) into a per-warp staging ring in
+// shared memory, two rounds of R cells deep, and reduced to traces from there.  (cp.async.bulk was measured first: one bulk copy of 1 KB
+// costs its issuing thread ~670 cycles, scripts/tma_small_copy_bench.cu - 64 of them per batch would keep the producers as busy as today.)  The room for the ring comes from a SINGLE trace buffer: the traces of the x and y faces (slots [0, HA)) are
+// produced one batch ahead, once the compute warps have left the y phase of the current batch ("A free"), those of the z faces
+// (slots [HA, HA + HB)) at the start of their own batch, before its z phase ("B ready").
+template<int N, int R, int NP> struct WsStaged { static constexpr bool value = (NP == 4 && R == 3); };
+constexpr int WS_STAGE_SLOT = 128;       // doubles per staged cell (1024 bytes: 1000 bytes of the cell + 8 bytes of alignment slack on either side)
+constexpr unsigned WS_STAGE_BYTES = 1008; // bytes copied per cell: the cell, extended to 16-byte granularity (63 chunks of 16 bytes)
+
 struct WsArgs
 {
   const i2 * halo;          // [n_batches][HL]: (local cell << 3 | face, neighbour cell), out-of-batch faces of the batch, x faces first, then y, z
@@ -78,6 +88,7 @@ struct WsArgs
   // optional work counter (zeroed before the launch): the CTAs claim their items dynamically instead of striding through them -
   // CTAs that start late (those that export this rank's cells first) then simply process fewer items
   int * counter;
+  int HA, HT; // staged variant: first trace slot of the z faces = maximum number of x and y entries of a batch; HT = HA + HB trace slots
 };
 
 // all peers have stored this vmult's ghost cells (every lane acquires every flag: its later loads are ordered behind them)
@@ -94,6 +105,17 @@ inline size_t ws_smem_bytes(int HL)
   constexpr int B = WsCfg<N>::B, N2 = N * N, N3 = N2 * N;
   return ((size_t)2 * B * N3 + (size_t)2 * B * N2 + (size_t)4 * HL * N2) * sizeof(double) + (size_t)2 * B * 6 * sizeof(int)
          + (size_t)NP * WsCfg<N>::HLMAX * sizeof(i2) + 16 + 16 /* item ring */;
+}
+
+// staged variant: single trace buffer of HL = HA + HB slots (rounded to 16 bytes), two index tables, two halo lists per producer warp,
+// the staging ring and two mbarriers per producer warp
+template<int N, int NP, int R>
+inline size_t ws_smem_bytes_staged(int HL)
+{
+  constexpr int B = WsCfg<N>::B, N2 = N * N, N3 = N2 * N;
+  const size_t trs = ((size_t)HL * N2 + 1) & ~(size_t)1;
+  return ((size_t)2 * B * N3 + (size_t)2 * B * N2 + 2 * trs + (size_t)NP * 2 * R * WS_STAGE_SLOT) * sizeof(double) + (size_t)2 * B * 6 * sizeof(int)
+         + (size_t)NP * 2 * WsCfg<N>::HLMAX * sizeof(i2) + 16 + 16 + (size_t)NP * 2 * 8;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -139,6 +161,7 @@ inline WsTables<N> make_ws_tables(const double h[3], double tau_op)
 struct WsHostPlan
 {
   int B = 0, HL = 0, n_batches = 0;
+  int HA = 0, HB = 0;              // maxima over the batches of the x + y entries and of the z entries (staged variant)
   std::vector<i2> halo;            // [n_batches][HL]
   std::vector<int32_t> cnt, nloc;  // [n_batches], [n_batches][B * 6]
   std::vector<int64_t> nloc8;      // [n_batches][B], empty if a value does not fit a signed byte
@@ -166,8 +189,10 @@ inline WsHostPlan ws_build_plan(const int32_t * nb, int64_t n_owned, int B)
         }
     P.cnt[b] = c[0] | (c[1] << 10) | (c[2] << 20);
     P.HL = std::max(P.HL, (int)lists[b].size());
+    P.HA = std::max(P.HA, c[0] + c[1]); P.HB = std::max(P.HB, c[2]);
   }
   P.HL = std::max(P.HL, 1);
+  P.HA = std::max(P.HA, 1); P.HB = std::max(P.HB, 1);
   if (B <= 127 && P.HL <= 128) {
     P.nloc8.assign((size_t)P.n_batches * B, 0);
     for (size_t i = 0; i < P.nloc8.size(); ++i) {
@@ -272,6 +297,105 @@ WS_FN void ws_produce(RT & rt, const WsTables<N> & T, const WsArgs & A, int bt, 
   // hl is overwritten by the next call only behind the CTA-wide hand-over barrier
 }
 
+// ---- staged variant: producers ----
+// per-warp state of the staging ring: the buffer the next round goes to
+struct WsStage { int buf; };
+
+// entries [e_begin, e_end) of the halo list hl -> trace slots slot0 + (e - e_begin).  Rounds of up to R entries are dealt to the producer
+// warps in turn; a warp keeps two rounds in the ring: the asynchronous copies (cp.async, 16 bytes per lane and instruction, one commit
+// group per round) of its next round are in flight while the current one is reduced - no registers are tied up by loads in flight.
+template<int N, int R, bool GH, int NP, class RT>
+WS_FN void ws_produce_staged(RT & rt, const WsTables<N> & T, const WsArgs & A, int pw, int lane, const i2 * hl, int e_begin, int e_end, int slot0, int & round,
+                             double * TRV, double * TRG, double * stage, WsStage & st)
+{
+  constexpr int N2 = N * N, N3 = N2 * N;
+  const bool act = lane < N2;
+  const int ab = act ? lane : 0;
+  const int nr = (e_end - e_begin + R - 1) / R;
+  int j = ((pw - round) % NP + NP) % NP; // the j-th round of this call has the running index round + j
+  round += nr;
+  if (j >= nr) return;
+  const double * const ghost0 = GH ? A.ghost - A.n_owned * N3 : A.src; // ghost cells are numbered from n_owned
+  auto issue = [&](int jj, int b) {
+    const int e0 = e_begin + jj * R;
+    const int cnt = (e_end - e0 < R) ? e_end - e0 : R;
+    WS_UNROLL
+    for (int q = 0; q < R; ++q)
+      if (q < cnt) { // warp-uniform
+        const i2 h = hl[e0 + q];
+        const double * p = ((!GH || h.y < A.n_owned) ? A.src : ghost0) + (size_t)h.y * N3;
+        const int shift = (int)((reinterpret_cast<uintptr_t>(p) >> 3) & 1); // cells start on odd multiples of 8 bytes every other time
+        rt.stage_cell(stage + (size_t)(b * R + q) * WS_STAGE_SLOT, p - shift, lane); // 1008 bytes from the 16-byte aligned address below the cell
+      }
+    rt.stage_commit();
+  };
+  auto process = [&](int jj, int b) {
+    const int e0 = e_begin + jj * R;
+    const int cnt = (e_end - e0 < R) ? e_end - e0 : R;
+    WS_UNROLL
+    for (int q = 0; q < R; ++q)
+      if (q < cnt) { // warp-uniform
+        const i2 h = hl[e0 + q];
+        const int f = h.x & 7, d = f >> 1, side = f & 1;
+        const double * p = ((!GH || h.y < A.n_owned) ? A.src : ghost0) + (size_t)h.y * N3;
+        const int shift = (int)((reinterpret_cast<uintptr_t>(p) >> 3) & 1);
+        const int sd = (d == 0) ? 1 : (d == 1 ? N : N2), s1 = (d == 0) ? N : 1, s2 = (d == 2) ? N : N2;
+        const double * line = stage + (size_t)(b * R + q) * WS_STAGE_SLOT + shift + (ab % N) * s1 + (ab / N) * s2;
+        double x[N];
+        WS_UNROLL
+        for (int i = 0; i < N; ++i) x[i] = line[i * sd];
+        double g0 = T.fd[0][0] * x[0], g1 = T.fd[1][0] * x[0];
+        WS_UNROLL
+        for (int i = 1; i < N; ++i) { g0 = fma(T.fd[0][i], x[i], g0); g1 = fma(T.fd[1][i], x[i], g1); }
+        // our lower face (side 0): the neighbour is entered through its upper end
+        const double v = side ? x[0] : x[N - 1];
+        const double g = side ? g0 : g1;
+        const int slot = slot0 + (e0 - e_begin) + q;
+        if (act) { TRV[slot * N2 + ab] = v; TRG[slot * N2 + ab] = g; }
+      }
+  };
+  int b = st.buf;
+  issue(j, b);
+  for (; j < nr; j += NP) {
+    const bool more = j + NP < nr;
+    if (more) { issue(j + NP, b ^ 1); rt.stage_wait_prev(); } else rt.stage_wait_all();
+    rt.sync_producer(pw); // the copies of every lane have landed
+    process(j, b);
+    rt.sync_producer(pw); // the staged cells of this round are read: the buffer may be refilled
+    b ^= 1;
+  }
+  st.buf = b;
+}
+
+// x and y part of batch bt: halo list -> this warp's list buffer hb, index table -> nlS (z faces re-addressed to the slots behind HA),
+// traces of the x and y entries -> slots [0, cx + cy).  pre holds the list of bt and leaves with that of bt_next; returns the packed counts.
+template<int N, int R, bool GH, int NP, class RT>
+WS_FN int ws_produce_staged_xy(RT & rt, const WsTables<N> & T, const WsArgs & A, int bt, int bt_next, int pw, int lane, WsPrefetch & pre, int & round, double * TRV, double * TRG,
+                               int * nlS, i2 * hl, double * stage, WsStage & st)
+{
+  constexpr int B = WsCfg<N>::B;
+  constexpr int NL = (B * 6 + 32 * NP - 1) / (32 * NP);
+  const int c = pre.c;
+  const int cx = c & 1023, cy = (c >> 10) & 1023;
+  hl[lane] = pre.h[0]; hl[lane + 32] = pre.h[1];
+  int nl[NL];
+  WS_UNROLL
+  for (int j = 0; j < NL; ++j) { const int i = pw * 32 + lane + 32 * NP * j; nl[j] = i < B * 6 ? A.nloc[(size_t)bt * (B * 6) + i] : 0; }
+  if (bt_next >= 0) ws_prefetch(A, bt_next, lane, pre);
+  rt.sync_producer(pw);
+  ws_produce_staged<N, R, GH, NP>(rt, T, A, pw, lane, hl, 0, cx + cy, 0, round, TRV, TRG, stage, st);
+  WS_UNROLL
+  for (int j = 0; j < NL; ++j) {
+    const int i = pw * 32 + lane + 32 * NP * j;
+    if (i < B * 6) {
+      int v = nl[j];
+      if (i % 6 >= 4 && v < 0) v = -1 - (A.HA + (-1 - v) - (cx + cy)); // z faces: slot behind the x / y area
+      nlS[i] = v;
+    }
+  }
+  return c;
+}
+
 template<int N, int R, bool GH, int NP, class RT>
 WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
 {
@@ -279,17 +403,20 @@ WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
   constexpr int N2 = N * N, N3 = N2 * N;
   static_assert((N2 & 1) == 1, "odd n: contiguous cells in shared memory are conflict-free and bulk-copyable");
   static_assert(B * N <= NC, "one thread per cell plane");
+  constexpr bool ST = WsStaged<N, R, NP>::value; // bulk-copied neighbour cells, single trace buffer (see WsStaged)
   double * const smem = rt.smem();
-  const int trs = A.HL * N2;                   // doubles per trace array
+  const int trs = ST ? ((A.HT * N2 + 1) & ~1) : A.HL * N2; // doubles per trace array
   constexpr int OFF_T = B * N3;                // partial results, finally the result (bulk-store source)
   constexpr int OFF_GN = 2 * B * N3;           // [2][B][N2] own end derivatives of the current direction
-  constexpr int OFF_TR = OFF_GN + 2 * B * N2;  // [2 buffers][values, derivatives][HL][N2] traces of out-of-batch neighbours
+  constexpr int OFF_TR = OFF_GN + 2 * B * N2;  // [2 buffers (staged: 1)][values, derivatives][HL][N2] traces of out-of-batch neighbours
+  constexpr int STAGE = ST ? NP * 2 * R * WS_STAGE_SLOT : 0; // staged: [NP][2 rounds][R] cells of 1 KB
   double * const U = smem;                     // [B][N3] src values of the batch (bulk-copy destination)
   double * const Tt = smem + OFF_T;
   double * const GN = smem + OFF_GN;
-  int * const nl2 = reinterpret_cast<int *>(smem + OFF_TR + 4 * trs); // [2][B * 6]
-  i2 * const hlS = reinterpret_cast<i2 *>(nl2 + 2 * B * 6);           // [NP][HLMAX] per-warp staging of the halo list
-  void * const bar = hlS + NP * WsCfg<N>::HLMAX;
+  double * const stageS = smem + OFF_TR + 2 * trs; // (staged only)
+  int * const nl2 = reinterpret_cast<int *>(smem + OFF_TR + (ST ? 2 * trs + STAGE : 4 * trs)); // [2][B * 6]
+  i2 * const hlS = reinterpret_cast<i2 *>(nl2 + 2 * B * 6);           // [NP][HLMAX] (staged: [NP][2][HLMAX]) per-warp staging of the halo list
+  void * const bar = hlS + NP * (ST ? 2 : 1) * WsCfg<N>::HLMAX;
 
   const int t = rt.tid();
   const bool producer = t >= NC;
@@ -316,9 +443,23 @@ WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
   WsPrefetch pre;
   pre.c = 0; pre.h[0] = i2{0, 0}; pre.h[1] = i2{0, 0};
   bool ghosts_acquired = false;
+  // staged variant: state of this producer warp
+  WsStage stg; stg.buf = 0;
+  int st_round = 0, st_cnt[2] = {0, 0};
   {
     const int bt = A.batches ? A.batches[first] : first;
-    if (producer) {
+    if (producer && ST) {
+      const int it1 = q(1);
+      if (GH && A.flags && first >= A.first_ghost_item) { ws_acquire_ghosts(rt, A); ghosts_acquired = true; }
+      ws_prefetch(A, bt, lane, pre);
+      const int btn = it1 < A.n_items ? (A.batches ? A.batches[it1] : it1) : -1;
+      double * const stw = stageS + (size_t)pw * 2 * R * WS_STAGE_SLOT;
+      i2 * const hlw = hlS + (size_t)(pw * 2 + 0) * WsCfg<N>::HLMAX;
+      if (GH && (!A.flags || first >= A.first_ghost_item))
+        st_cnt[0] = ws_produce_staged_xy<N, R, GH, NP>(rt, T, A, bt, btn, pw, lane, pre, st_round, smem + OFF_TR, smem + OFF_TR + trs, nl2, hlw, stw, stg);
+      else
+        st_cnt[0] = ws_produce_staged_xy<N, R, false, NP>(rt, T, A, bt, btn, pw, lane, pre, st_round, smem + OFF_TR, smem + OFF_TR + trs, nl2, hlw, stw, stg);
+    } else if (producer) {
       const int it1 = q(1);
       if (GH && A.flags && first >= A.first_ghost_item) { ws_acquire_ghosts(rt, A); ghosts_acquired = true; }
       ws_prefetch(A, bt, lane, pre);
@@ -339,6 +480,37 @@ WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
   rt.sync_all();
 
   // The two roles run their own loops over the same batch sequence and meet at the CTA-wide barrier once per batch.
+  if (producer && ST) {
+    rt.role_producer();
+    double * const stw = stageS + (size_t)pw * 2 * R * WS_STAGE_SLOT;
+    double * const TRV = smem + OFF_TR, * const TRG = smem + OFF_TR + trs;
+    int buf = 0;
+    for (int n = 0; q(n) < A.n_items; ++n, buf ^= 1) {
+      const int itc = q(n), itn = q(n + 1), itnn = q(n + 2);
+      // z traces of the current batch (its list is in this warp's list buffer `buf`), then "B ready"
+      {
+        const int c = st_cnt[buf];
+        const int cxy = (c & 1023) + ((c >> 10) & 1023), cz = (c >> 20) & 1023;
+        const i2 * const hlw = hlS + (size_t)(pw * 2 + buf) * WsCfg<N>::HLMAX;
+        if (GH && (!A.flags || itc >= A.first_ghost_item)) ws_produce_staged<N, R, GH, NP>(rt, T, A, pw, lane, hlw, cxy, cxy + cz, A.HA, st_round, TRV, TRG, stw, stg);
+        else ws_produce_staged<N, R, false, NP>(rt, T, A, pw, lane, hlw, cxy, cxy + cz, A.HA, st_round, TRV, TRG, stw, stg);
+      }
+      rt.arrive_b();
+      rt.wait_a(); // the compute warps have left the y phase of the current batch: the x / y slots are free
+      if (itn < A.n_items) {
+        const int bn = A.batches ? A.batches[itn] : itn;
+        const int bnn = itnn < A.n_items ? (A.batches ? A.batches[itnn] : itnn) : -1;
+        if (GH && A.flags && !ghosts_acquired && itn >= A.first_ghost_item) { ws_acquire_ghosts(rt, A); ghosts_acquired = true; }
+        i2 * const hlw = hlS + (size_t)(pw * 2 + (buf ^ 1)) * WsCfg<N>::HLMAX;
+        if (GH && (!A.flags || itn >= A.first_ghost_item))
+          st_cnt[buf ^ 1] = ws_produce_staged_xy<N, R, GH, NP>(rt, T, A, bn, bnn, pw, lane, pre, st_round, TRV, TRG, nl2 + (buf ^ 1) * B * 6, hlw, stw, stg);
+        else
+          st_cnt[buf ^ 1] = ws_produce_staged_xy<N, R, false, NP>(rt, T, A, bn, bnn, pw, lane, pre, st_round, TRV, TRG, nl2 + (buf ^ 1) * B * 6, hlw, stw, stg);
+      }
+      rt.sync_all(); // hand-over: x / y traces and index table of the next batch are complete
+    }
+    return;
+  }
   if (producer) {
     rt.role_producer(); // register re-allocation between the roles where the run-time interface implements it
     int buf = 0;
@@ -373,7 +545,7 @@ WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
       const bool valid = lc < nvalid;               // also false for t >= B * N
       const bool validz = (sz < N) && (lz < nvalid);
       const int * nlS = nl2 + buf * B * 6;
-      const int off_trv = OFF_TR + buf * 2 * trs, off_trg = off_trv + trs;
+      const int off_trv = OFF_TR + (ST ? 0 : buf * 2 * trs), off_trg = off_trv + trs;
 
       int nlp[4] = {0, 0, 0, 0};
       if (valid) {
@@ -450,6 +622,7 @@ WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
         if (d == 1 && t == 0) rt.store_wait_read(); // the previous batch's bulk store has read Tt
         rt.sync_compute();                          // GN of this direction is consumed
       }
+      if (ST) rt.arrive_a(); // this thread has read its last x / y trace of the batch
       if (valid) {
         WS_UNROLL
         for (int j = 0; j < N; ++j)
@@ -475,6 +648,7 @@ WS_FN void ws_cta(RT & rt, const WsTables<N> & T, const WsArgs & A)
         for (int i = 0; i < N; ++i) { GN[(0 * B + lz) * N2 + sz * N + i] = g0[i]; GN[(1 * B + lz) * N2 + sz * N + i] = g1[i]; }
       }
       rt.sync_compute(); // Tt planes and z end derivatives visible
+      if (ST) rt.wait_b();  // the z traces of this batch are complete
       if (validz) {
         WS_UNROLL
         for (int i = 0; i < N; ++i)

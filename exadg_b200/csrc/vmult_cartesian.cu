@@ -1070,7 +1070,7 @@ bool cartesian_supported(int n) { return n >= 2 && n <= 8; }
 
 int cartesian_kernel_variant(int set)
 {
-  if (g_cart_kernel < 0) { const char * e = getenv("EXADG_B200_CART_KERNEL"); g_cart_kernel = (e && std::strcmp(e, "pipe") == 0) ? 0 : ((e && std::strcmp(e, "ws12") == 0) ? 2 : ((e && std::strcmp(e, "ws4p") == 0) ? 3 : ((e && std::strcmp(e, "wp") == 0) ? 4 : ((e && std::strcmp(e, "ws") == 0) ? 1 : 3)))); }
+  if (g_cart_kernel < 0) { const char * e = getenv("EXADG_B200_CART_KERNEL"); g_cart_kernel = (e && std::strcmp(e, "pipe") == 0) ? 0 : ((e && std::strcmp(e, "ws12") == 0) ? 2 : ((e && std::strcmp(e, "ws4p") == 0) ? 3 : ((e && std::strcmp(e, "wp") == 0) ? 4 : ((e && std::strcmp(e, "ws") == 0) ? 1 : ((e && std::strcmp(e, "wst") == 0) ? 6 : 3))))); }
   const int previous = g_cart_kernel;
   if (set >= 0) g_cart_kernel = set;
   return previous;
@@ -1216,7 +1216,7 @@ int cartesian_n_batches(const DeviceOperator & op)
 
 static void launch_cart(const DeviceOperator & op, double * dst, const double * src, bool add, int which, const int32_t * list, int n_list, cudaStream_t stream);
 
-static int ws_depth_of(int variant) { return variant == 2 ? 12 : (variant == 3 ? 4 : (variant == 4 ? 100 : (variant == 5 ? 101 : 8))); }
+static int ws_depth_of(int variant) { return variant == 2 ? 12 : (variant == 3 ? 4 : (variant == 4 ? 100 : (variant == 5 ? 101 : (variant == 6 ? 3 : 8)))); }
 
 bool launch_vmult_cartesian_fused(const DeviceOperator & op, double * dst, const double * src, bool add, const GhostSync & gs, cudaStream_t stream)
 {

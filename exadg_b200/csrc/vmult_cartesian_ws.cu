@@ -105,6 +105,20 @@ struct DeviceRT
   }
   __device__ __forceinline__ void store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
   __device__ __forceinline__ void store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+  // staged variant: a warp copies one neighbour cell (1008 bytes = 63 chunks of 16 bytes) into the staging ring, asynchronously
+  __device__ __forceinline__ void stage_cell(double * dst, const double * src, int lane)
+  {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s32(dst + 2 * lane)), "l"(src + 2 * lane) : "memory");
+    if (lane < 31) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s32(dst + 64 + 2 * lane)), "l"(src + 64 + 2 * lane) : "memory");
+  }
+  __device__ __forceinline__ void stage_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+  __device__ __forceinline__ void stage_wait_prev() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+  __device__ __forceinline__ void stage_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+  // "A free" (compute -> producers) and "B ready" (producers -> compute): named barriers 3 and 4, one side arrives, the other waits
+  __device__ __forceinline__ void arrive_a() { asm volatile("bar.arrive 3, %0;" ::"n"(NT) : "memory"); }
+  __device__ __forceinline__ void wait_a() { asm volatile("bar.sync 3, %0;" ::"n"(NT) : "memory"); }
+  __device__ __forceinline__ void arrive_b() { asm volatile("bar.arrive 4, %0;" ::"n"(NT) : "memory"); }
+  __device__ __forceinline__ void wait_b() { asm volatile("bar.sync 4, %0;" ::"n"(NT) : "memory"); }
 };
 
 // R: neighbour cells per producer round; GH: the partition has ghost cells (src of the neighbours may live in the ghost buffer);
@@ -182,7 +196,9 @@ struct WsDevPlan
 {
   i2 * d_halo = nullptr; int32_t * d_cnt = nullptr, * d_nloc = nullptr; int64_t * d_nloc8 = nullptr;
   int HL = 0, n_batches = 0, ctas_per_sm = 0;
+  int HA = 0, HB = 0;         // staged variant: slots of the x / y traces and of the z traces
   size_t smem = 0, smem4 = 0; // smem4: with 4 producer warps (0 if it does not fit)
+  size_t smem_st = 0;         // staged variant (0: not applicable to this mesh)
   size_t smem_wp = 0;         // warp-private kernel (0: not applicable to this mesh)
   WsTables<5> T;
 };
@@ -230,6 +246,16 @@ void * ws_plan_create(const DeviceOperator & op, const HostMesh & mesh)
         || configure(vmult_cartesian_ws_kernel<5, 4, true, 4>, WsCfg<5, 4>::NT, P->smem4) < 2)
       P->smem4 = 0;
   } catch (const std::exception &) { P->smem4 = 0; cudaGetLastError(); }
+  // staged variant: whole neighbour cells by bulk copies of 1008 bytes from (cell address rounded down to 16 bytes) - with an even number of
+  // owned / ghost cells no copy reaches beyond the end of the vector / ghost buffer
+  try {
+    P->HA = H.HA; P->HB = H.HB;
+    P->smem_st = ws_smem_bytes_staged<5, 4, 3>(H.HA + H.HB);
+    if (mesh.n_owned % 2 != 0 || mesh.n_ghost % 2 != 0 || H.HL > WsCfg<5>::HLMAX || P->smem_st > WS_MAX_SMEM
+        || configure(vmult_cartesian_ws_kernel<5, 3, false, 4>, WsCfg<5, 4>::NT, P->smem_st) < 2
+        || configure(vmult_cartesian_ws_kernel<5, 3, true, 4>, WsCfg<5, 4>::NT, P->smem_st) < 2)
+      P->smem_st = 0;
+  } catch (const std::exception &) { P->smem_st = 0; cudaGetLastError(); }
   // warp-private kernel: same batch plan; needs an even number of owned cells (every bulk copy a multiple of 16 bytes)
   try {
     P->smem_wp = wp::wp_smem_bytes<5, 2>();
@@ -264,8 +290,10 @@ void ws_launch(const DeviceOperator & op, const void * p, double * dst, const do
   WsArgs A;
   A.halo = P->d_halo; A.cnt = P->d_cnt; A.nloc = P->d_nloc; A.nloc8 = P->d_nloc8; A.batches = batches;
   A.src = src; A.ghost = op.ghost; A.dst = dst; A.n_owned = op.n_owned; A.n_items = n_items; A.HL = P->HL; A.add = add ? 1 : 0;
-  A.flags = nullptr; A.epoch = 0; A.first_ghost_item = 0; A.n_peers = 0; A.counter = nullptr;
+  A.flags = nullptr; A.epoch = 0; A.first_ghost_item = 0; A.n_peers = 0; A.counter = nullptr; A.HA = 0; A.HT = 0;
   for (int i = 0; i < 16; ++i) A.peer_rank[i] = 0;
+  if (depth == 3 && P->smem_st == 0) depth = 4; // staged variant not applicable to this mesh: the same kernel with strided loads
+  if (depth == 3) { A.HA = P->HA; A.HT = P->HA + P->HB; }
   PutDesc put;
   std::memset(&put, 0, sizeof(put));
   if (gs && gs->flags) {
@@ -299,6 +327,9 @@ void ws_launch(const DeviceOperator & op, const void * p, double * dst, const do
   } else if (depth == 101 && P->smem_wp > 0) { // warp-private kernel, 12 neighbour cells per producer round
     if (gh) vmult_cartesian_wp_kernel<5, 12, true, 2><<<grid, wp::WpCfg<5, 2>::NT, P->smem_wp, stream>>>(P->T, A, put);
     else vmult_cartesian_wp_kernel<5, 12, false, 2><<<grid, wp::WpCfg<5, 2>::NT, P->smem_wp, stream>>>(P->T, A, put);
+  } else if (depth == 3) { // staged variant (bulk-copied neighbour cells)
+    if (gh) vmult_cartesian_ws_kernel<5, 3, true, 4><<<grid, WsCfg<5, 4>::NT, P->smem_st, stream>>>(P->T, A, put);
+    else vmult_cartesian_ws_kernel<5, 3, false, 4><<<grid, WsCfg<5, 4>::NT, P->smem_st, stream>>>(P->T, A, put);
   } else if (depth == 4 && P->smem4 > 0) {
     if (gh) vmult_cartesian_ws_kernel<5, 4, true, 4><<<grid, WsCfg<5, 4>::NT, P->smem4, stream>>>(P->T, A, put);
     else vmult_cartesian_ws_kernel<5, 4, false, 4><<<grid, WsCfg<5, 4>::NT, P->smem4, stream>>>(P->T, A, put);

@@ -35,10 +35,18 @@ static int run_mesh(int n_sub, int refine, int steps, int only)
   CK(exadg_b200_set_stream(op, stream));
   const int64_t n = exadg_b200_local_size(op);
   std::printf("cells %d^3 dofs %lld cartesian_path %d\n", n_sub << refine, (long long)n, exadg_b200_is_cartesian_path(op));
-  constexpr int NV = 6; // 0 pipelined, 1 WS depth 8, 2 WS depth 12, 3 WS with 4 producer warps (setmaxnreg), 4 warp-private kernel
-  double * src = nullptr, * dst[NV] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // 0 pipelined, 1 WS depth 8, 2 WS depth 12, 3 WS with 4 producer warps (setmaxnreg), 4 / 5 warp-private kernel, 6 WS with 4 producer warps
+  // and neighbour cells staged in shared memory by cp.async.  TOURNAMENT_VARIANTS=036 restricts the list (0 is the parity reference).
+  constexpr int NV = 7;
+  bool use[NV];
+  for (int v = 0; v < NV; ++v) use[v] = true;
+  if (const char * e = std::getenv("TOURNAMENT_VARIANTS")) {
+    for (int v = 0; v < NV; ++v) use[v] = false;
+    for (const char * c = e; *c; ++c) if (*c >= '0' && *c < '0' + NV) use[*c - '0'] = true;
+  }
+  double * src = nullptr, * dst[NV] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   CK(exadg_b200_initialize_dof_vector(op, &src));
-  for (int v = 0; v < NV; ++v) CK(exadg_b200_initialize_dof_vector(op, &dst[v]));
+  for (int v = 0; v < NV; ++v) if (use[v]) CK(exadg_b200_initialize_dof_vector(op, &dst[v]));
   {
     std::vector<double> h(n);
     uint64_t s = 0x9E3779B97F4A7C15ull;
@@ -49,6 +57,7 @@ static int run_mesh(int n_sub, int refine, int steps, int only)
   CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
   for (int v = 0; v < NV; ++v) {
     if (only >= 0 && v != only) continue;
+    if (!use[v]) continue;
     if (only < 0 && v == 2 && std::getenv("TOURNAMENT_SKIP2")) continue;
     exadg_b200_cartesian_kernel(v);
     for (int i = 0; i < 5; ++i) CK(exadg_b200_vmult(op, dst[v], src));
@@ -70,6 +79,7 @@ static int run_mesh(int n_sub, int refine, int steps, int only)
     std::vector<double> y0(n), y(n);
     CU(cudaMemcpy(y0.data(), dst[0], n * sizeof(double), cudaMemcpyDeviceToHost));
     for (int v = 1; v < NV; ++v) {
+      if (!use[v] || !use[0]) continue;
       CU(cudaMemcpy(y.data(), dst[v], n * sizeof(double), cudaMemcpyDeviceToHost));
       std::printf("vmult     rel l2 (variant %d vs 0): %.3e\n", v, rel_diff(y, y0));
       exadg_b200_cartesian_kernel(v);
@@ -83,7 +93,7 @@ static int run_mesh(int n_sub, int refine, int steps, int only)
   }
   exadg_b200_cartesian_kernel(0);
   exadg_b200_free_dof_vector(src);
-  for (int v = 0; v < NV; ++v) exadg_b200_free_dof_vector(dst[v]);
+  for (int v = 0; v < NV; ++v) if (dst[v]) exadg_b200_free_dof_vector(dst[v]);
   exadg_b200_destroy(op);
   return 0;
 }

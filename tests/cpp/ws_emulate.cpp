@@ -12,8 +12,10 @@
 #include <sched.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <thread>
 
 #include "../../exadg_b200/csrc/cart_ws.hpp"
@@ -33,10 +35,25 @@ constexpr int N = 5;
 #endif
 constexpr int NP = WSE_NP;
 
+// named barrier where some threads only arrive (bar.arrive) and the others wait (bar.sync): `total` participants per generation
+struct NamedBar
+{
+  std::mutex m; std::condition_variable cv; int count = 0, gen = 0, total = 0;
+  void arrive() { std::unique_lock<std::mutex> l(m); if (++count == total) { count = 0; ++gen; cv.notify_all(); } }
+  void sync()
+  {
+    std::unique_lock<std::mutex> l(m);
+    const int g = gen;
+    if (++count == total) { count = 0; ++gen; cv.notify_all(); }
+    else cv.wait(l, [&] { return gen != g; });
+  }
+};
+
 struct HostCta
 {
   double * smem = nullptr;
   pthread_barrier_t ba, bc, bp[NP];
+  NamedBar na, nb;
   std::atomic<int> loads{0};
   const double * st_src = nullptr; size_t st_bytes = 0; std::vector<char> snap; bool st_pending = false;
   std::atomic<int> errors{0};
@@ -51,6 +68,20 @@ struct HostRT
   int cta() const { return c->cta; }
   int ncta() const { return c->ncta; }
   void bar_init(void *) {}
+  // staged variant: every lane copies its 16-byte chunks at issue time; the warp barrier behind the wait publishes them
+  void stage_cell(double * dst, const double * src, int lane)
+  {
+    if ((reinterpret_cast<uintptr_t>(src) & 15) != 0 || (reinterpret_cast<uintptr_t>(dst) & 15) != 0) c->errors++;
+    std::memcpy(dst + 2 * lane, src + 2 * lane, 16);
+    if (lane < 31) std::memcpy(dst + 64 + 2 * lane, src + 64 + 2 * lane, 16);
+  }
+  void stage_commit() {}
+  void stage_wait_prev() {}
+  void stage_wait_all() {}
+  void arrive_a() { c->na.arrive(); }
+  void wait_a() { c->na.sync(); }
+  void arrive_b() { c->nb.arrive(); }
+  void wait_b() { c->nb.sync(); }
   void sync_all() { pthread_barrier_wait(&c->ba); }
   void sync_compute() { pthread_barrier_wait(&c->bc); }
   void sync_producer(int pw) { pthread_barrier_wait(&c->bp[pw]); }
@@ -130,7 +161,12 @@ int64_t wse_n_ghost(void * h) { return static_cast<Emu *>(h)->mesh.n_ghost; }
 int64_t wse_global_offset(void * h) { return static_cast<Emu *>(h)->mesh.global_offset; }
 void wse_ghost_global(void * h, int64_t * out) { Emu * E = static_cast<Emu *>(h); std::copy(E->mesh.ghost_global.begin(), E->mesh.ghost_global.end(), out); }
 int wse_halo_max(void * h) { return static_cast<Emu *>(h)->plan.HL; }
-int64_t wse_smem_bytes(void * h) { return (int64_t)ws_smem_bytes<N, NP>(static_cast<Emu *>(h)->plan.HL); }
+constexpr bool STAGED = WsStaged<N, WSE_R, NP>::value;
+static size_t emu_smem_bytes(const Emu * E)
+{
+  return STAGED ? ws_smem_bytes_staged<N, NP, WSE_R>(E->plan.HA + E->plan.HB) : ws_smem_bytes<N, NP>(E->plan.HL);
+}
+int64_t wse_smem_bytes(void * h) { return (int64_t)emu_smem_bytes(static_cast<Emu *>(h)); }
 int wse_n_batches(void * h, int which) { Emu * E = static_cast<Emu *>(h); return which == 0 ? E->plan.n_batches : (which == 1 ? (int)E->interior.size() : (int)E->boundary.size()); }
 
 // 1: the CTAs claim their items from a work counter (the scheduling of the single-launch partitioned vmult)
@@ -146,7 +182,8 @@ int wse_vmult(void * h, const double * src, const double * ghost, double * dst, 
   A.batches = which == 0 ? nullptr : (which == 1 ? E->interior.data() : E->boundary.data());
   A.n_items = wse_n_batches(h, which);
   A.src = src; A.ghost = ghost; A.dst = dst; A.n_owned = E->mesh.n_owned; A.HL = E->plan.HL; A.add = add;
-  A.flags = nullptr; A.epoch = 0; A.first_ghost_item = 0; A.n_peers = 0; A.counter = nullptr;
+  A.flags = nullptr; A.epoch = 0; A.first_ghost_item = 0; A.n_peers = 0; A.counter = nullptr; A.HA = 0; A.HT = 0;
+  if (STAGED) { A.HA = E->plan.HA; A.HT = E->plan.HA + E->plan.HB; }
   if (g_dynamic) { g_counter = 0; A.counter = &g_counter; }
   if (A.n_items == 0) return 0;
   if (E->plan.HL > WsCfg<N>::HLMAX) return -1; // the library falls back to the pipelined kernel
@@ -154,8 +191,11 @@ int wse_vmult(void * h, const double * src, const double * ghost, double * dst, 
   int errors = 0;
   for (int cta = 0; cta < n_ctas; ++cta) {
     HostCta C;
-    std::vector<double> smem(ws_smem_bytes<N, NP>(E->plan.HL) / sizeof(double) + 2, -777.0);
-    C.smem = smem.data(); C.cta = cta; C.ncta = n_ctas;
+    std::vector<double> smem_store(emu_smem_bytes(E) / sizeof(double) + 4, -777.0);
+    double * smem_aligned = smem_store.data();
+    if (reinterpret_cast<uintptr_t>(smem_aligned) & 15) ++smem_aligned; // 16-byte aligned like dynamic shared memory
+    C.smem = smem_aligned; C.cta = cta; C.ncta = n_ctas;
+    C.na.total = C.nb.total = WsCfg<N, NP>::NT;
     pthread_barrier_init(&C.ba, nullptr, WsCfg<N, NP>::NT);
     pthread_barrier_init(&C.bc, nullptr, WsCfg<N>::NC);
     for (int p = 0; p < NP; ++p) pthread_barrier_init(&C.bp[p], nullptr, 32);

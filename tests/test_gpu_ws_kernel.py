@@ -11,10 +11,10 @@ TOL = 1e-12
 
 
 # every kernel variant of the k=4 affine fast path that bench.py may time (include/exadg_b200.h: exadg_b200_set_kernel_variant)
-VARIANTS = [1, 2, 3, 4]
+VARIANTS = [1, 2, 3, 4, 6]
 
 
-@pytest.fixture(params=VARIANTS, ids=["ws_depth8", "ws_depth12", "ws_4producers", "warp_private"])
+@pytest.fixture(params=VARIANTS, ids=["ws_depth8", "ws_depth12", "ws_4producers", "warp_private", "ws_staged"])
 def ws_kernel(request):
     return request.param
 

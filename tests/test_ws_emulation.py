@@ -34,7 +34,7 @@ def _build(path, extra):
     return lib
 
 
-@pytest.fixture(scope="module", params=[(8, 2), (12, 2), (4, 4)], ids=["depth8", "depth12", "depth4_4producers"])
+@pytest.fixture(scope="module", params=[(8, 2), (12, 2), (4, 4), (3, 4)], ids=["depth8", "depth12", "depth4_4producers", "staged3_4producers"])
 def emu(request, tmp_path_factory):
     """the kernel instantiations of the library: neighbour cells fetched per producer round, producer warps"""
     depth, producers = request.param
@@ -52,8 +52,16 @@ def _run(lib, n_sub, refine, rank, world, x_global, n_ctas, add=False, split=Fal
         n_owned, n_ghost, off = lib.wse_n_owned(h), lib.wse_n_ghost(h), lib.wse_global_offset(h)
         gg = np.zeros(max(n_ghost, 1), dtype=np.int64)
         lib.wse_ghost_global(h, _ptr(gg))
-        src = np.ascontiguousarray(x_global[off * N3:(off + n_owned) * N3])
-        ghost = np.ascontiguousarray(np.concatenate([x_global[g * N3:(g + 1) * N3] for g in gg[:n_ghost]]) if n_ghost else np.zeros(1))
+        # two doubles of padding behind the vectors: the staged variant copies whole neighbour cells in 16-byte granularity (the
+        # library only selects it for even cell counts, where no copy leaves the vector; the emulation runs it on every mesh)
+        src_store = np.zeros(n_owned * N3 + 2)
+        src_store[:n_owned * N3] = x_global[off * N3:(off + n_owned) * N3]
+        src = src_store[:n_owned * N3]
+        ghost_store = np.zeros(max(n_ghost, 1) * N3 + 2)
+        if n_ghost:
+            ghost_store[:n_ghost * N3] = np.concatenate([x_global[g * N3:(g + 1) * N3] for g in gg[:n_ghost]])
+        ghost = ghost_store[:max(n_ghost, 1) * N3]
+        assert src.ctypes.data % 16 == 0 and ghost.ctypes.data % 16 == 0
         dst = np.full(n_owned * N3, 3.0) if add else np.full(n_owned * N3, np.nan)
         if split:  # interior batches, then the batches with ghost neighbours (the two launches of the multi-GPU path)
             assert lib.wse_n_batches(h, 1) + lib.wse_n_batches(h, 2) == lib.wse_n_batches(h, 0)
@@ -135,11 +143,12 @@ def test_emulated_kernel_partitions(emu, n_sub, refine, world, expect_supported)
     assert supported == 2 * expect_supported
 
 
-def test_emulated_kernel_thread_sanitizer(tmp_path):
+@pytest.mark.parametrize("flags", [[], ["-DWSE_R=3", "-DWSE_NP=4"]], ids=["depth8", "staged3_4producers"])
+def test_emulated_kernel_thread_sanitizer(tmp_path, flags):
     """the same run under ThreadSanitizer: the kernel's barriers must order every shared-memory access"""
     exe = str(tmp_path / "tsan_driver.py")
     lib = str(tmp_path / "libwse_tsan.so")
-    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-g", "-march=x86-64-v3", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-fsanitize=thread", SRC, "-o", lib])
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-g", "-march=x86-64-v3", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-fsanitize=thread", *flags, SRC, "-o", lib])
     tsan_rt = subprocess.run(["/usr/bin/g++", "-print-file-name=libtsan.so"], capture_output=True, text=True).stdout.strip()
     if not os.path.isabs(tsan_rt):
         pytest.skip("libtsan not available")
