@@ -224,7 +224,7 @@ void finish_setup(exadg_b200_operator * op, double ip_factor, bool force_general
   for (int e = 0; e < 3; ++e) D.h[e] = M.h[e];
   if (D.helmholtz && M.world > 1) throw std::runtime_error("the Helmholtz / viscous operator is not partitioned yet (world must be 1)");
   // the mass term and the component blocks live in the general kernel only
-  D.cartesian = M.cartesian_uniform && M.all_interior() && !force_general && !D.helmholtz && cartesian_supported(D.n);
+  D.cartesian = M.n_owned > 0 && M.cartesian_uniform && M.all_interior() && !force_general && !D.helmholtz && cartesian_supported(D.n);
   if (D.cartesian) {
     // tau_hat is needed by the kernel tables: uniform box => tau_K = sum_d 1/h_d (interior_penalty_parameter.h:68-98)
     double tk = 0.0;
@@ -232,7 +232,7 @@ void finish_setup(exadg_b200_operator * op, double ip_factor, bool force_general
     D.tau_hat = tk * ip_factor * (D.degree + 1.0) * (D.degree + 1.0);
     if (cartesian_plan_create(D, M) == 0) D.cartesian = false;
   }
-  if (!D.cartesian && M.cartesian_uniform && !M.all_interior() && !force_general && !D.helmholtz && M.world <= 1 && M.n_ghost == 0 && cartesian_supported(D.n)
+  if (!D.cartesian && M.n_owned > 0 && M.cartesian_uniform && !M.all_interior() && !force_general && !D.helmholtz && M.world <= 1 && M.n_ghost == 0 && cartesian_supported(D.n)
       && !getenv("EXADG_B200_NO_HYBRID")) {
     // tau_K counts true boundary faces with weight 1 (interior_penalty_parameter.h:88-89), and an interior face takes the larger of its two
     // cells' values (laplace_operator.h:128-140): a cell sees the uniform interior penalty on all its faces iff neither it nor any of its
@@ -323,6 +323,7 @@ void launch_vmult(exadg_b200_operator * op, double * dst, const double * src, bo
 // with the cells that touch no ghost)
 void apply(exadg_b200_operator * op, double * dst, const double * src, bool add)
 {
+  if (op->n_local == 0 && op->mesh.peers.empty()) return; // is_empty_locally: a rank without cells (and without neighbours) has nothing to do
   check_ptr(dst, "dst"); check_ptr(src, "src");
   if (dst == src) throw std::invalid_argument("dst and src must not alias");
   HostMesh & M = op->mesh;
@@ -407,6 +408,7 @@ void apply(exadg_b200_operator * op, double * dst, const double * src, bool add)
 
 void diagonal(exadg_b200_operator * op, double * diag, bool add)
 {
+  if (op->n_local == 0) return;
   check_ptr(diag, "diagonal");
   DeviceOperator & D = op->dev;
   if (D.cartesian) {
@@ -853,8 +855,11 @@ int exadg_b200_vmult_host(exadg_b200_operator * op, double * dst_host, const dou
 // downloaded right behind its kernel on a third stream.  Unpartitioned operators only; host buffers should be pinned.
 static int64_t host_pipeline_cells_per_chunk(int batch)
 {
-  // about 1536 cells (three 8^3 blocks of the Morton curve on refined hypercubes), a multiple of the kernels' batch size
-  const int64_t per = std::max<int64_t>(1, (1536 + batch / 2) / batch);
+  // about 12288 cells (24 blocks of 8^3 cells of the Morton curve on refined hypercubes; 12 MB per copy at k = 4), a multiple of the kernels'
+  // batch size.  Measured on the 96^3 box (k = 4, scripts/r02_shot24.sh): 1536 / 4608 / 12288 / 32768 cells per chunk -> 3.76 / 4.21 / 4.34 / 3.97
+  // GDoF/s end to end: small chunks overlap best on paper but pay per-chunk launch, event and copy-setup costs.
+  static const int64_t target = []() { const char * e = getenv("EXADG_B200_HP_CELLS"); const long v = e ? std::atol(e) : 12288; return (int64_t)(v > 0 ? v : 12288); }();
+  const int64_t per = std::max<int64_t>(1, (target + batch / 2) / batch);
   return per * batch;
 }
 

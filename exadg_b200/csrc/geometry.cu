@@ -212,6 +212,7 @@ void setup_geometry(DeviceOperator & op, const HostMesh & mesh, double ip_factor
     return;
   }
 
+  if (nloc == 0 || mesh.n_owned == 0) return; // a rank without cells (more ranks than cells): nothing to set up
   double * xmap = to_device(mesh.xmap);
   uint8_t * bt = to_device(mesh.bt);
   int32_t * face_cells = to_device(mesh.face_cells);

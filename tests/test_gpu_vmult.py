@@ -106,6 +106,18 @@ def test_uniform_box_with_boundaries_takes_the_hybrid_fast_path(degree):
         assert rel(d.cpu().numpy(), ref.diagonal()) < TOL
 
 
+def test_rank_without_cells_is_empty_locally():
+    """more ranks than cells: the p4est-style partition leaves ranks empty (OperatorBase::is_empty_locally); their calls are no-ops"""
+    import exadg_b200
+    op = exadg_b200.LaplaceOperator.hypercube(2, 1, 0, rank=0, world=2)   # one cell, owned by rank 1
+    assert op.is_empty_locally() and op.local_size() == 0 and op.n() == 27
+    src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+    op.vmult(dst, src)
+    op.vmult_add(dst, src)
+    op.calculate_diagonal(dst)
+    assert dst.numel() == 0
+
+
 def test_single_cell_periodic_is_its_own_neighbour():
     for degree in (2, 4, 5):
         op, ref = make_pair(degree, 1, 0)
