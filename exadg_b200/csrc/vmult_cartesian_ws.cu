@@ -70,7 +70,9 @@ struct DeviceRT
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(bar)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __device__ __forceinline__ void sync_all() { asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory"); } // reached from both roles' loops
+  // reached from both roles' loops, i.e. from two different barrier instructions: barrier.sync WITHOUT .aligned (bar.sync = barrier.sync.aligned
+  // is meant for one instruction executed by all participating threads; compute-sanitizer synccheck reports the aligned form as divergent)
+  __device__ __forceinline__ void sync_all() { asm volatile("barrier.sync 2, %0;" ::"n"(NT) : "memory"); }
   __device__ __forceinline__ void role_compute() { if (REG) asm volatile("setmaxnreg.inc.sync.aligned.u32 160;"); }
   __device__ __forceinline__ void role_producer() { if (REG) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;"); }
   __device__ __forceinline__ void sync_compute() { asm volatile("bar.sync 1, %0;" ::"n"(WsCfg<5>::NC) : "memory"); }

@@ -59,20 +59,28 @@ __device__ __forceinline__ void sweep(const double * __restrict__ M, const doubl
 // MODE 0: dst (+)= A src.  MODE 1: diagonal (unit vectors column by column, neighbour function zero:
 // do_face_int_integral, laplace_operator.cpp:165-191; operator_base.cpp:1552-1616).
 // resident CTAs per SM the register allocation is tuned for (measured per degree on B200, curved periodic box)
-// N^2 <= 32: the lines of a cell live in ONE warp (32 / N^2 cells per warp; spare lanes shadow line 0 of the warp's first cell: same
-// addresses, same values), so every barrier between the sweeps is a __syncwarp and the warps of a CTA run decoupled from each
-// other; larger N: N^2 threads per cell and block barriers
+// N^2 <= 32: the lines of a cell live in ONE warp (32 / N^2 cells per warp; the spare lanes exit), so every barrier between the sweeps
+// is a __syncwarp of the participating lanes and the warps of a CTA run decoupled from each other; larger N: N^2 threads per cell and
+// block barriers
 template<int N> struct GenCfg
 {
   static constexpr int MIN_BLOCKS = (N == 5 || N == 7) ? 2 : 4;
   static constexpr bool WARP_CELLS = (N * N <= 32);
+  // face phase with line ownership (every 2-D operation on a face field line by line) or with a row per face point: measured per degree on
+  // the curved box (scripts/r02_shot28.sh): k=2 13.3 -> 13.9, k=4 18.4 -> 21.5 GDoF/s, but k=3 24.9 -> 18.7, k=5 18.6 -> 12.9, k=6 17.2 -> 11.2
+  static constexpr bool FACE_LINES = (N == 3 || N == 5);
   static constexpr int CPW = WARP_CELLS ? 32 / (N * N) : 0;                      // cells per warp
   static constexpr int WARPS = (N == 5) ? 8 : 4;                                  // warps per CTA (warp-cell layout)
   static constexpr int CPB = WARP_CELLS ? CPW * WARPS : ((N * N >= 64) ? 2 : 4);  // cells per CTA
   static constexpr int THREADS = WARP_CELLS ? 32 * WARPS : N * N * CPB;
 };
+// warp-cell layout: only the lanes that own a line take part (the spare lanes of a warp exit at once)
 template<int N>
-__device__ __forceinline__ void gen_sync() { if (GenCfg<N>::WARP_CELLS) __syncwarp(); else __syncthreads(); }
+__device__ __forceinline__ void gen_sync()
+{
+  constexpr int LANES = GenCfg<N>::CPW * N * N;
+  if (GenCfg<N>::WARP_CELLS) __syncwarp(LANES >= 32 ? 0xffffffffu : ((1u << (LANES & 31)) - 1u)); else __syncthreads();
+}
 
 template<int N, int CPB, int MODE>
 __global__ void __launch_bounds__(GenCfg<N>::THREADS, GenCfg<N>::MIN_BLOCKS) vmult_general_kernel(const __grid_constant__ GenTables<N> T, const GenArgs A)
@@ -80,12 +88,12 @@ __global__ void __launch_bounds__(GenCfg<N>::THREADS, GenCfg<N>::MIN_BLOCKS) vmu
   constexpr int NP = N | 1;          // odd x-extent: conflict-free 64-bit shared accesses in every direction
   constexpr int SZ = NP * N * N;
   constexpr int N2 = N * N, N3 = N * N * N;
-  constexpr int FS = 10 * N2;        // face scratch per cell
+  constexpr int FS = (GenCfg<N>::FACE_LINES ? 18 : 10) * N2; // face scratch per cell
   extern __shared__ double smem[];
   const int t = threadIdx.x;
-  const int lane_ok = GenCfg<N>::WARP_CELLS ? ((t & 31) < GenCfg<N>::CPW * N2) : 1;
-  const int lc = GenCfg<N>::WARP_CELLS ? (t >> 5) * GenCfg<N>::CPW + (lane_ok ? (t & 31) / N2 : 0) : t / N2;
-  const int r = GenCfg<N>::WARP_CELLS ? (lane_ok ? (t & 31) % N2 : 0) : t % N2, a = r % N, b = r / N;
+  if (GenCfg<N>::WARP_CELLS && (t & 31) >= GenCfg<N>::CPW * N2) return; // spare lanes of the warp-cell layout
+  const int lc = GenCfg<N>::WARP_CELLS ? (t >> 5) * GenCfg<N>::CPW + (t & 31) / N2 : t / N2;
+  const int r = GenCfg<N>::WARP_CELLS ? (t & 31) % N2 : t % N2, a = r % N, b = r / N;
   double * Uq = smem + (size_t)lc * (4 * SZ + FS);
   double * F0 = Uq + SZ, * F1 = F0 + SZ, * F2 = F1 + SZ;
   double * W = F2 + SZ; // [10][N2]
@@ -147,7 +155,8 @@ __global__ void __launch_bounds__(GenCfg<N>::THREADS, GenCfg<N>::MIN_BLOCKS) vmu
     // ---- P5: faces, one direction (two faces) at a time ----
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      double * Wvm = W, * Wv2 = W + 2 * N2, * Wd2 = W + 4 * N2, * Wv2t = W + 6 * N2, * Wd2t = W + 8 * N2;
+      double * Wvm = W, * Wv2 = W + 2 * N2, * Wd2 = W + 4 * N2, * Wx = W + 6 * N2, * Wy = W + 8 * N2;           // [2 sides][N2] each
+      double * Wm1 = W + 10 * N2, * Wm2 = W + 12 * N2, * Wp1 = W + 14 * N2, * Wp2 = W + 16 * N2;
       double vm[2], dm[2];
       int32_t nbc[2]; int32_t F[2]; int info[2];
       {
@@ -183,6 +192,112 @@ __global__ void __launch_bounds__(GenCfg<N>::THREADS, GenCfg<N>::MIN_BLOCKS) vmu
         }
         Wv2[s * N2 + r] = v2; Wd2[s * N2 + r] = d2;
       }
+      double zc[2], cgd[2];
+      if constexpr (GenCfg<N>::FACE_LINES) {
+      gen_sync<N>();
+      // The 2-D operations on the face fields (n x n values, two faces per direction) are done LINE BY LINE: an item is one line of one
+      // field, its owner loads the n values once and produces all n outputs (the first version gave every face point its own row:
+      // n loads per output, and five such loops made the face phase half of the kernel's shared-memory traffic).
+      // nodal -> collocation along t1: Wx = S Wv2, Wy = S Wd2   (4 n items: field f in {v2 s0, v2 s1, d2 s0, d2 s1}, line = fixed t2 index)
+      for (int it = r; it < 4 * N; it += N2) {
+        const int f = it / N, l = it % N;
+        const double * in = ((f < 2) ? Wv2 : Wd2) + (f & 1) * N2 + N * l;
+        double * out = ((f < 2) ? Wx : Wy) + (f & 1) * N2 + N * l;
+        double u[N];
+#pragma unroll
+        for (int p = 0; p < N; ++p) u[p] = in[p];
+#pragma unroll
+        for (int o = 0; o < N; ++o) {
+          double acc = 0.0;
+#pragma unroll
+          for (int p = 0; p < N; ++p) acc = fma(T.S[o * N + p], u[p], acc);
+          out[o] = acc;
+        }
+      }
+      gen_sync<N>();
+      // ... and along t2: Wv2 <- S Wx (= v+ at the face points), Wd2 <- S Wy (= reference normal derivative of u+)
+      for (int it = r; it < 4 * N; it += N2) {
+        const int f = it / N, l = it % N;
+        const double * in = ((f < 2) ? Wx : Wy) + (f & 1) * N2 + l;
+        double * out = ((f < 2) ? Wv2 : Wd2) + (f & 1) * N2 + l;
+        double u[N];
+#pragma unroll
+        for (int p = 0; p < N; ++p) u[p] = in[N * p];
+#pragma unroll
+        for (int o = 0; o < N; ++o) {
+          double acc = 0.0;
+#pragma unroll
+          for (int p = 0; p < N; ++p) acc = fma(T.S[o * N + p], u[p], acc);
+          out[N * o] = acc;
+        }
+      }
+      gen_sync<N>();
+      // tangential derivatives of v- and v+ (8 n items: field in {v- s0, v- s1, v+ s0, v+ s1} x direction in {t1, t2})
+      for (int it = r; it < 8 * N; it += N2) {
+        const int g = it / N, l = it % N, fld = g & 3, dir = g >> 2;
+        const double * in = ((fld < 2) ? Wvm : Wv2) + (fld & 1) * N2;
+        double * out = ((fld < 2) ? (dir ? Wm2 : Wm1) : (dir ? Wp2 : Wp1)) + (fld & 1) * N2;
+        const int base = dir ? l : N * l, st = dir ? N : 1;
+        double u[N];
+#pragma unroll
+        for (int p = 0; p < N; ++p) u[p] = in[base + p * st];
+#pragma unroll
+        for (int o = 0; o < N; ++o) {
+          double acc = 0.0;
+#pragma unroll
+          for (int p = 0; p < N; ++p) acc = fma(T.Dq[o * N + p], u[p], acc);
+          out[base + o * st] = acc;
+        }
+      }
+      gen_sync<N>();
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const double m1 = Wm1[s * N2 + r], m2 = Wm2[s * N2 + r], p1 = Wp1[s * N2 + r], p2 = Wp2[s * N2 + r];
+        const double vps = Wv2[s * N2 + r], dps = Wd2[s * N2 + r];
+        const bool plus = info[s] & 8; const int bt = (info[s] >> 4) & 3;
+        const double sgn = plus ? -1.0 : 1.0;
+        const double * fg = A.faceG + (size_t)F[s] * 7 * N2 + r;
+        const int om = plus ? 3 : 0, op = plus ? 0 : 3;
+        double am[3], ap[3];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) { am[e] = sgn * fg[(om + e) * N2]; ap[e] = sgn * fg[(op + e) * N2]; }
+        const double jxw = fg[6 * N2], tau = A.tau_f[F[s]];
+        const double dnm = am[d] * dm[s] + am[t1] * m1 + am[t2] * m2;
+        double dnp = ap[d] * dps + ap[t1] * p1 + ap[t2] * p2;
+        double vpl = vps;
+        if (bt == BT_DIRICHLET) { vpl = -vm[s]; dnp = dnm; }        // weak_boundary_conditions.h:44,118-121
+        else if (bt == BT_NEUMANN) { vpl = vm[s]; dnp = -dnm; }     // :45,124-127
+        else if (MODE == 1) { vpl = 0.0; dnp = 0.0; }               // exterior function zero
+        const double jump = vm[s] - vpl;
+        const double gf = A.lap * (-0.5 * jump);                    // laplace_operator.h:180-185 (viscous_operator.h:489-525 with nu)
+        const double vf = A.lap * (0.5 * (dnm + dnp) - tau * jump); // laplace_operator.h:187-197
+        zc[s] = -vf * jxw;                                          // submit_value(-value_flux)
+        cgd[s] = am[d] * gf * jxw;                                  // submit_normal_derivative(gradient_flux)
+        Wx[s * N2 + r] = am[t1] * gf * jxw;
+        Wy[s * N2 + r] = am[t2] * gf * jxw;
+      }
+      gen_sync<N>();
+      // tangential parts of submit_normal_derivative, tested with the derivatives of the collocation basis: Wm1 = Dq^T_t1 Wx, Wm2 = Dq^T_t2 Wy
+      for (int it = r; it < 4 * N; it += N2) {
+        const int f = it / N, l = it % N, dir = f >> 1;
+        const double * in = (dir ? Wy : Wx) + (f & 1) * N2;
+        double * out = (dir ? Wm2 : Wm1) + (f & 1) * N2;
+        const int base = dir ? l : N * l, st = dir ? N : 1;
+        double u[N];
+#pragma unroll
+        for (int p = 0; p < N; ++p) u[p] = in[base + p * st];
+#pragma unroll
+        for (int o = 0; o < N; ++o) {
+          double acc = 0.0;
+#pragma unroll
+          for (int p = 0; p < N; ++p) acc = fma(T.Dq[p * N + o], u[p], acc);
+          out[base + o * st] = acc;
+        }
+      }
+      gen_sync<N>();
+#pragma unroll
+      for (int s = 0; s < 2; ++s) zc[s] += Wm1[s * N2 + r] + Wm2[s * N2 + r];
+      } else {
       gen_sync<N>();
       // nodal -> collocation on the face, first tangential direction
 #pragma unroll
@@ -190,7 +305,7 @@ __global__ void __launch_bounds__(GenCfg<N>::THREADS, GenCfg<N>::MIN_BLOCKS) vmu
         double x = 0.0, y = 0.0;
 #pragma unroll
         for (int p = 0; p < N; ++p) { x = fma(T.S[a * N + p], Wv2[s * N2 + p + N * b], x); y = fma(T.S[a * N + p], Wd2[s * N2 + p + N * b], y); }
-        Wv2t[s * N2 + r] = x; Wd2t[s * N2 + r] = y;
+        Wx[s * N2 + r] = x; Wy[s * N2 + r] = y;
       }
       gen_sync<N>();
       double vp[2], dp[2];
@@ -198,12 +313,11 @@ __global__ void __launch_bounds__(GenCfg<N>::THREADS, GenCfg<N>::MIN_BLOCKS) vmu
       for (int s = 0; s < 2; ++s) {
         double x = 0.0, y = 0.0;
 #pragma unroll
-        for (int p = 0; p < N; ++p) { x = fma(T.S[b * N + p], Wv2t[s * N2 + a + N * p], x); y = fma(T.S[b * N + p], Wd2t[s * N2 + a + N * p], y); }
+        for (int p = 0; p < N; ++p) { x = fma(T.S[b * N + p], Wx[s * N2 + a + N * p], x); y = fma(T.S[b * N + p], Wy[s * N2 + a + N * p], y); }
         vp[s] = x; dp[s] = y;
         Wv2[s * N2 + r] = x;
       }
       gen_sync<N>();
-      double zc[2], cgd[2];
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         double m1 = 0.0, m2 = 0.0, p1 = 0.0, p2 = 0.0;
@@ -231,16 +345,17 @@ __global__ void __launch_bounds__(GenCfg<N>::THREADS, GenCfg<N>::MIN_BLOCKS) vmu
         const double vf = A.lap * (0.5 * (dnm + dnp) - tau * jump); // laplace_operator.h:187-197
         zc[s] = -vf * jxw;                                          // submit_value(-value_flux)
         cgd[s] = am[d] * gf * jxw;                                  // submit_normal_derivative(gradient_flux)
-        Wv2t[s * N2 + r] = am[t1] * gf * jxw;
-        Wd2t[s * N2 + r] = am[t2] * gf * jxw;
+        Wx[s * N2 + r] = am[t1] * gf * jxw;
+        Wy[s * N2 + r] = am[t2] * gf * jxw;
       }
       gen_sync<N>();
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         double z = zc[s];
 #pragma unroll
-        for (int p = 0; p < N; ++p) { z = fma(T.Dq[p * N + a], Wv2t[s * N2 + p + N * b], z); z = fma(T.Dq[p * N + b], Wd2t[s * N2 + a + N * p], z); }
+        for (int p = 0; p < N; ++p) { z = fma(T.Dq[p * N + a], Wx[s * N2 + p + N * b], z); z = fma(T.Dq[p * N + b], Wy[s * N2 + a + N * p], z); }
         zc[s] = z;
+      }
       }
 #pragma unroll
       for (int i = 0; i < N; ++i) {
@@ -289,7 +404,7 @@ void launch_n(const DeviceOperator & op, double * dst, const double * src, bool 
   constexpr int CPB = GenCfg<N>::CPB;
   constexpr int NP = N | 1;
   static const GenTables<N> T = make_tables<N>();
-  const size_t smem = (size_t)CPB * (4 * NP * N * N + 10 * N * N) * sizeof(double);
+  const size_t smem = (size_t)CPB * (4 * NP * N * N + (GenCfg<N>::FACE_LINES ? 18 : 10) * N * N) * sizeof(double);
   if (first_use_on_device((const void *)vmult_general_kernel<N, CPB, MODE>))
     CUDA_CHECK(cudaFuncSetAttribute(vmult_general_kernel<N, CPB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   GenArgs A;

@@ -48,7 +48,9 @@ if ROUND != "1":
     os.environ.pop("EXADG_B200_NO_PIPE", None)
     # every k=4 kernel variant on 4^3 and 6^3 cells (3 / 9 batches): 3 = default (four producer warps, setmaxnreg), 4 = warp-private,
     # 6 = staged (cp.async ring, single trace buffer, named barriers 3 / 4)
-    for variant in (3, 4, 6):
+    # (SANITIZER_SKIP_WP=1 leaves the warp-private kernel out: its hand-over between the warps is an mbarrier protocol, which racecheck does not
+    # model - it reports the producer's trace stores against the consumer's loads; the protocol is checked by ThreadSanitizer on the emulation)
+    for variant in ((3, 6) if os.environ.get("SANITIZER_SKIP_WP") else (3, 4, 6)):
         for (n_sub, refine) in ((1, 2), (3, 1)):
             op = exadg_b200.LaplaceOperator.hypercube(4, n_sub, refine)
             op.set_kernel_variant(variant)
@@ -91,7 +93,7 @@ if ROUND != "1":
     op.rhs(y)
     op.evaluate(y, x)
     op.integrate_source_add(y, np.ones(op.cell_quadrature_points(3).shape[:2]))
-    op.l2_error(x, np.zeros(op.cell_quadrature_points(5).shape[:2]))
+    op.l2_error(x, np.ones(op.cell_quadrature_points(5).shape[:2]))
     torch.cuda.synchronize()
     print("ok hybrid path=%d, rhs / evaluate / error" % op.is_cartesian_path, flush=True)
     # multigrid: p- and h-transfer kernels, Chebyshev smoothers, coarse CG (k = 2, 4^3 cells, curved, phMG)
