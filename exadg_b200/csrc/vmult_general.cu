@@ -62,6 +62,10 @@ __device__ __forceinline__ void sweep(const double * __restrict__ M, const doubl
 // N^2 <= 32: the lines of a cell live in ONE warp (32 / N^2 cells per warp; the spare lanes exit), so every barrier between the sweeps
 // is a __syncwarp of the participating lanes and the warps of a CTA run decoupled from each other; larger N: N^2 threads per cell and
 // block barriers
+#ifndef EXADG_B200_CELL_FUSED_ALL
+#define EXADG_B200_CELL_FUSED_ALL 0
+#endif
+constexpr bool CELL_FUSED_ALL = EXADG_B200_CELL_FUSED_ALL != 0;
 template<int N> struct GenCfg
 {
   static constexpr int MIN_BLOCKS = (N == 5 || N == 7) ? 2 : 4;
@@ -69,6 +73,10 @@ template<int N> struct GenCfg
   // face phase with line ownership (every 2-D operation on a face field line by line) or with a row per face point: measured per degree on
   // the curved box (scripts/r02_shot28.sh): k=2 13.3 -> 13.9, k=4 18.4 -> 21.5 GDoF/s, but k=3 24.9 -> 18.7, k=5 18.6 -> 12.9, k=6 17.2 -> 11.2
   static constexpr bool FACE_LINES = (N == 3 || N == 5);
+  // cell part with the z sweeps in registers and chained sweeps (see the kernel), per degree after measurement on the curved box
+  // (scripts/r02_shot28.sh, GDoF/s without -> with): k=2 13.9 -> 14.7, k=3 24.9 -> 26.9, k=5 18.6 -> 19.8, k=6 17.2 -> 17.3, k=7 22.2 -> 22.6,
+  // but k=4 21.5 -> 20.9 (the long fused column step costs more latency than its shared-memory accesses saved)
+  static constexpr bool CELL_FUSED = CELL_FUSED_ALL || (N != 5);
   static constexpr int CPW = WARP_CELLS ? 32 / (N * N) : 0;                      // cells per warp
   static constexpr int WARPS = (N == 5) ? 8 : 4;                                  // warps per CTA (warp-cell layout)
   static constexpr int CPB = WARP_CELLS ? CPW * WARPS : ((N * N >= 64) ? 2 : 4);  // cells per CTA
@@ -107,6 +115,93 @@ __global__ void __launch_bounds__(GenCfg<N>::THREADS, GenCfg<N>::MIN_BLOCKS) vmu
   const int nstr[3] = {1, N, N2}; // nodal (global) strides
 
   for (int col = 0; col < (MODE == 1 ? N3 : 1); ++col) {
+    double * R = F0;
+    if constexpr (GenCfg<N>::CELL_FUSED) {
+      // Fused cell part: every sweep along z is done by the thread that owns the column (x, y) = (a, b) in registers - the nodal values come
+      // straight from global memory, the z derivative, the metric terms and the tested z flux never see shared memory - and consecutive
+      // sweeps along the same line are chained (S_y with Dq_y).  35 % fewer shared-memory accesses than the phase-by-phase form below.
+      double uz[N], r2[N];
+      { // P0 + S_z
+        double u[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          const int nodal = a + N * (b + N * k);
+          u[k] = (MODE == 1) ? ((nodal == col) ? 1.0 : 0.0) : A.src[block * N3 + nodal];
+        }
+#pragma unroll
+        for (int q = 0; q < N; ++q) {
+          double acc = 0.0;
+#pragma unroll
+          for (int k = 0; k < N; ++k) acc = fma(T.S[q * N + k], u[k], acc);
+          Uq[a + NP * (b + N * q)] = acc;
+        }
+      }
+      gen_sync<N>();
+      sweep<N, false>(T.S, Uq, Uq, lbase[0], lstr[0]); gen_sync<N>();
+      { // S_y chained with Dq_y: the y line (x = a, z = b)
+        double u[N], v[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) u[i] = Uq[lbase[1] + i * lstr[1]];
+#pragma unroll
+        for (int q = 0; q < N; ++q) {
+          double acc = 0.0;
+#pragma unroll
+          for (int i = 0; i < N; ++i) acc = fma(T.S[q * N + i], u[i], acc);
+          v[q] = acc;
+          Uq[lbase[1] + q * lstr[1]] = acc;
+        }
+#pragma unroll
+        for (int q = 0; q < N; ++q) {
+          double acc = 0.0;
+#pragma unroll
+          for (int i = 0; i < N; ++i) acc = fma(T.Dq[q * N + i], v[i], acc);
+          F1[lbase[1] + q * lstr[1]] = acc;
+        }
+      }
+      gen_sync<N>();
+      sweep<N, false>(T.Dq, Uq, F0, lbase[0], lstr[0]);
+      gen_sync<N>();
+      { // column (a, b): Dq_z, flux = G grad (get_gradient + submit_gradient, laplace_operator.cpp:135), Dq_z^T, mass term
+        double d2[N], f2[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) uz[k] = Uq[a + NP * (b + N * k)];
+#pragma unroll
+        for (int q = 0; q < N; ++q) {
+          double acc = 0.0;
+#pragma unroll
+          for (int k = 0; k < N; ++k) acc = fma(T.Dq[q * N + k], uz[k], acc);
+          d2[q] = acc;
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          const int q = a + N * (b + N * k), s = a + NP * (b + N * k);
+          const double * g = A.cellG + (size_t)cell * 6 * N3 + q;
+          const double gxx = g[0], gyy = g[N3], gzz = g[2 * N3], gxy = g[3 * N3], gxz = g[4 * N3], gyz = g[5 * N3];
+          const double d0 = F0[s], d1 = F1[s];
+          F0[s] = A.lap * (gxx * d0 + gxy * d1 + gxz * d2[k]);
+          F1[s] = A.lap * (gxy * d0 + gyy * d1 + gyz * d2[k]);
+          f2[k] = A.lap * (gxz * d0 + gyz * d1 + gzz * d2[k]);
+        }
+#pragma unroll
+        for (int q = 0; q < N; ++q) {
+          double acc = 0.0;
+#pragma unroll
+          for (int k = 0; k < N; ++k) acc = fma(T.Dq[k * N + q], f2[k], acc);
+          r2[q] = acc;
+        }
+        if (A.cellJxW) { // MassKernel::get_volume_flux (mass_kernel.h:76-82): submit_value(scaling_factor * u)
+#pragma unroll
+          for (int k = 0; k < N; ++k) r2[k] = fma(A.mass * A.cellJxW[(size_t)cell * N3 + a + N * (b + N * k)], uz[k], r2[k]);
+        }
+      }
+      gen_sync<N>();
+      sweep<N, true>(T.Dq, F0, F0, lbase[0], lstr[0]);
+      sweep<N, true>(T.Dq, F1, F1, lbase[1], lstr[1]);
+      gen_sync<N>();
+#pragma unroll
+      for (int k = 0; k < N; ++k) { const int s = a + NP * (b + N * k); R[s] += F1[s] + r2[k]; }
+      gen_sync<N>();
+    } else {
     // ---- P0: nodal values into shared memory ----
 #pragma unroll
     for (int k = 0; k < N; ++k) {
@@ -143,7 +238,6 @@ __global__ void __launch_bounds__(GenCfg<N>::THREADS, GenCfg<N>::MIN_BLOCKS) vmu
     sweep<N, true>(T.Dq, F1, F1, lbase[1], lstr[1]);
     sweep<N, true>(T.Dq, F2, F2, lbase[2], lstr[2]);
     gen_sync<N>();
-    double * R = F0;
 #pragma unroll
     for (int k = 0; k < N; ++k) { const int s = a + NP * (b + N * k); R[s] += F1[s] + F2[s]; }
     if (A.cellJxW) { // MassKernel::get_volume_flux (mass_kernel.h:76-82): submit_value(scaling_factor * u)
@@ -152,6 +246,7 @@ __global__ void __launch_bounds__(GenCfg<N>::THREADS, GenCfg<N>::MIN_BLOCKS) vmu
     }
     gen_sync<N>();
 
+    }
     // ---- P5: faces, one direction (two faces) at a time ----
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -369,19 +464,38 @@ __global__ void __launch_bounds__(GenCfg<N>::THREADS, GenCfg<N>::MIN_BLOCKS) vmu
     // ---- P6: back to the nodal basis, write ----
     sweep<N, true>(T.S, R, R, lbase[0], lstr[0]); gen_sync<N>();
     sweep<N, true>(T.S, R, R, lbase[1], lstr[1]); gen_sync<N>();
-    sweep<N, true>(T.S, R, R, lbase[2], lstr[2]); gen_sync<N>();
-    if (MODE == 1) {
-      const int k = col / N2;
-      if (valid && r == col % N2) {
-        const double v = R[a + NP * (b + N * k)];
-        if (A.add) A.dst[block * N3 + col] += v; else A.dst[block * N3 + col] = v;
-      }
-    } else if (valid) {
+    if constexpr (GenCfg<N>::CELL_FUSED) {
+      // S_z^T by the owner of the column (a, b) in registers, straight to global memory
+      double rz[N];
 #pragma unroll
-      for (int k = 0; k < N; ++k) {
-        const int nodal = a + N * (b + N * k);
-        const double v = R[a + NP * (b + N * k)];
-        if (A.add) A.dst[block * N3 + nodal] += v; else A.dst[block * N3 + nodal] = v;
+      for (int k = 0; k < N; ++k) rz[k] = R[a + NP * (b + N * k)];
+#pragma unroll
+      for (int q = 0; q < N; ++q) {
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) v = fma(T.S[k * N + q], rz[k], v);
+        const int nodal = a + N * (b + N * q);
+        if (MODE == 1) {
+          if (valid && nodal == col) { if (A.add) A.dst[block * N3 + col] += v; else A.dst[block * N3 + col] = v; }
+        } else if (valid) {
+          if (A.add) A.dst[block * N3 + nodal] += v; else A.dst[block * N3 + nodal] = v;
+        }
+      }
+    } else {
+      sweep<N, true>(T.S, R, R, lbase[2], lstr[2]); gen_sync<N>();
+      if (MODE == 1) {
+        const int k = col / N2;
+        if (valid && r == col % N2) {
+          const double v = R[a + NP * (b + N * k)];
+          if (A.add) A.dst[block * N3 + col] += v; else A.dst[block * N3 + col] = v;
+        }
+      } else if (valid) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          const int nodal = a + N * (b + N * k);
+          const double v = R[a + NP * (b + N * k)];
+          if (A.add) A.dst[block * N3 + nodal] += v; else A.dst[block * N3 + nodal] = v;
+        }
       }
     }
     gen_sync<N>();
