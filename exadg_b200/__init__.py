@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "exadg_b200_set_stream", "exadg_b200_synchronize", "exadg_b200_n", "exadg_b200_local_size", "exadg_b200_n_cells_owned",
     "exadg_b200_n_cells_ghost", "exadg_b200_is_cartesian_path", "exadg_b200_kernel_launches", "exadg_b200_initialize_dof_vector",
     "exadg_b200_free_dof_vector", "exadg_b200_vmult", "exadg_b200_vmult_add", "exadg_b200_vmult_host",
-    "exadg_b200_vmult_host_pipelined", "exadg_b200_host_pipeline_plan",
+    "exadg_b200_vmult_host_pipelined", "exadg_b200_host_pipeline_plan", "exadg_b200_set_host_pipeline_mode", "exadg_b200_host_stream_plan",
     "exadg_b200_calculate_diagonal", "exadg_b200_add_diagonal", "exadg_b200_calculate_inverse_diagonal", "exadg_b200_jacobi_vmult",
     "exadg_b200_cg_solve", "exadg_b200_chebyshev_create", "exadg_b200_chebyshev_destroy", "exadg_b200_chebyshev_get",
     "exadg_b200_chebyshev_set_interval", "exadg_b200_chebyshev_vmult", "exadg_b200_chebyshev_step", "exadg_b200_set_nccl_comm",
@@ -115,6 +115,9 @@ def load_library():
     L.exadg_b200_vmult_host_pipelined.argtypes = [vp, vp, vp]
     L.exadg_b200_host_pipeline_plan.argtypes = [C.POINTER(HypercubeDesc), i64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                                 C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+    L.exadg_b200_set_host_pipeline_mode.argtypes = [vp, C.c_int]
+    L.exadg_b200_host_stream_plan.argtypes = [C.POINTER(HypercubeDesc), C.c_int, i64, C.POINTER(C.c_int32), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64),
+                                              C.POINTER(C.c_int32), C.POINTER(C.c_double)]
     L.exadg_b200_calculate_diagonal.argtypes = [vp, dp]
     L.exadg_b200_add_diagonal.argtypes = [vp, dp]
     L.exadg_b200_calculate_inverse_diagonal.argtypes = [vp, dp]
@@ -157,7 +160,7 @@ def load_library():
 
 
 from .laplace_operator import (ChebyshevSmoother, ExaDGError, JacobiPreconditioner, KrylovSolverCG, MultigridPreconditioner, PartitionPlan,  # noqa: E402
-                               LaplaceOperator, SolverData, cartesian_kernel, fp64_peak, host_pipeline_plan, multigrid_levels)
+                               LaplaceOperator, SolverData, cartesian_kernel, fp64_peak, host_pipeline_plan, host_stream_plan, multigrid_levels)
 
 __all__ = ["LaplaceOperator", "KrylovSolverCG", "ChebyshevSmoother", "JacobiPreconditioner", "SolverData", "ExaDGError",
-           "fp64_peak", "cartesian_kernel", "host_pipeline_plan", "load_library", "PERIODIC", "DIRICHLET", "NEUMANN"]
+           "fp64_peak", "cartesian_kernel", "host_pipeline_plan", "host_stream_plan", "load_library", "PERIODIC", "DIRICHLET", "NEUMANN"]

@@ -148,6 +148,9 @@ struct exadg_b200_operator
   HostPipelinePlan hp; bool hp_built = false;
   cudaStream_t hp_in = nullptr, hp_out = nullptr; cudaEvent_t hp_start = nullptr;
   std::vector<cudaEvent_t> hp_ev_in, hp_ev_cmp; int32_t * d_iota = nullptr;
+  // second plan: pieces in address order, per-unit readiness, dst stored by the kernels into the device-mapped host buffer
+  HostStreamPlan hs; bool hs_built = false; int32_t * d_hs_units = nullptr; std::vector<cudaEvent_t> hs_ev;
+  int hp_mode = 0; // 0 auto (direct on the affine path if dst_host is device-accessible), 1 staged (chunk plan, copy-engine download), 2 direct
 
   double * work(int i)
   {
@@ -754,6 +757,8 @@ int exadg_b200_destroy(exadg_b200_operator * op)
   for (int i = 0; i < 4; ++i) cudaFree(op->w[i]);
   cudaFree(op->d_stage_src); cudaFree(op->d_stage_dst);
   cudaFree(op->d_iota);
+  cudaFree(op->d_hs_units);
+  for (auto e : op->hs_ev) cudaEventDestroy(e);
   for (auto e : op->hp_ev_in) cudaEventDestroy(e);
   for (auto e : op->hp_ev_cmp) cudaEventDestroy(e);
   if (op->hp_start) cudaEventDestroy(op->hp_start);
@@ -841,7 +846,8 @@ int exadg_b200_vmult_host(exadg_b200_operator * op, double * dst_host, const dou
   return guarded([&]() {
     if (!op || !dst_host || !src_host) throw std::invalid_argument("null argument");
     const size_t bytes = (size_t)op->n_local * sizeof(double);
-    if (!op->d_stage_src) { CUDA_CHECK(cudaMalloc(&op->d_stage_src, std::max<size_t>(bytes, 16))); CUDA_CHECK(cudaMalloc(&op->d_stage_dst, std::max<size_t>(bytes, 16))); }
+    if (!op->d_stage_src) CUDA_CHECK(cudaMalloc(&op->d_stage_src, std::max<size_t>(bytes, 16)));
+    if (!op->d_stage_dst) CUDA_CHECK(cudaMalloc(&op->d_stage_dst, std::max<size_t>(bytes, 16)));
     CUDA_CHECK(cudaMemcpyAsync(op->d_stage_src, src_host, bytes, cudaMemcpyHostToDevice, op->stream));
     apply(op, op->d_stage_dst, op->d_stage_src, false);
     CUDA_CHECK(cudaMemcpyAsync(dst_host, op->d_stage_dst, bytes, cudaMemcpyDeviceToHost, op->stream));
@@ -863,12 +869,92 @@ static int64_t host_pipeline_cells_per_chunk(int batch)
   return per * batch;
 }
 
+// Direct variant (HostStreamPlan, host_pipeline.hpp): src is uploaded in pieces in address order; behind every piece ONE launch applies
+// the units (batches / cells) whose own cells and face neighbours are complete with it, and the kernels store dst straight into the
+// caller's pinned host buffer through its device mapping (bulk stores / coalesced stores over PCIe; every DoF of dst is written exactly
+// once, as on the device path).  No staging vector and no copy-engine download: the download has the granularity of a kernel unit.
+static int64_t host_stream_cells_per_piece(int unit)
+{
+  static const int64_t target = []() { const char * e = getenv("EXADG_B200_HS_CELLS"); const long v = e ? std::atol(e) : 12288; return (int64_t)(v > 0 ? v : 12288); }();
+  const int64_t per = std::max<int64_t>(1, (target + unit / 2) / unit);
+  return per * unit;
+}
+
+// device address of a host buffer the GPU can write (cudaHostAlloc / cudaHostRegister memory under unified addressing), else nullptr
+static double * device_view_of_host(double * host)
+{
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+  return static_cast<double *>(at.devicePointer);
+}
+
+static int vmult_host_direct(exadg_b200_operator * op, double * dst_dev, const double * src_host)
+{
+  HostMesh & M = op->mesh;
+  const int n3 = op->dev.n * op->dev.n * op->dev.n;
+  const bool cart = op->dev.cartesian;
+  const int B = cart ? cartesian_batch_size(op->dev) : 1;
+  const size_t bytes = (size_t)op->n_local * sizeof(double);
+  if (!op->hs_built) {
+    op->hs = build_host_stream_plan(M.nb.data(), M.n_owned, B, host_stream_cells_per_piece(B));
+    const HostStreamPlan & P = op->hs;
+    if (P.n_steps > 0) {
+      CUDA_CHECK(cudaMalloc(&op->d_hs_units, std::max<size_t>(P.units.size(), 1) * sizeof(int32_t)));
+      CUDA_CHECK(cudaMemcpy(op->d_hs_units, P.units.data(), P.units.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+      if (!op->hp_in) CUDA_CHECK(cudaStreamCreateWithFlags(&op->hp_in, cudaStreamNonBlocking));
+      if (!op->hp_start) CUDA_CHECK(cudaEventCreateWithFlags(&op->hp_start, cudaEventDisableTiming));
+      op->hs_ev.assign(P.n_steps, nullptr);
+      for (auto & e : op->hs_ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    op->hs_built = true;
+  }
+  const HostStreamPlan & P = op->hs;
+  if (P.n_steps == 0) { g_last_error = "the pipelined host-buffer vmult is for unpartitioned operators"; return (int)EXADG_B200_ERR_UNSUPPORTED; }
+  if (!op->d_stage_src) CUDA_CHECK(cudaMalloc(&op->d_stage_src, std::max<size_t>(bytes, 16)));
+  // the upload stream may not overtake earlier work of the operator's stream on the staging vector
+  CUDA_CHECK(cudaEventRecord(op->hp_start, op->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(op->hp_in, op->hp_start, 0));
+  for (int i = 0; i < P.n_steps; ++i) {
+    const int64_t c0 = P.piece_begin[i], c1 = P.piece_begin[i + 1];
+    CUDA_CHECK(cudaMemcpyAsync(op->d_stage_src + c0 * n3, src_host + c0 * n3, (size_t)(c1 - c0) * n3 * sizeof(double), cudaMemcpyHostToDevice, op->hp_in));
+    const int64_t u0 = P.step_begin[i], n_units = P.step_begin[i + 1] - u0;
+    if (n_units == 0) continue; // uploads complete in order: a later event covers this piece as well
+    CUDA_CHECK(cudaEventRecord(op->hs_ev[i], op->hp_in));
+    CUDA_CHECK(cudaStreamWaitEvent(op->stream, op->hs_ev[i], 0));
+    if (cart) launch_vmult_cartesian_list(op->dev, dst_dev, op->d_stage_src, false, op->d_hs_units + u0, (int)n_units, op->stream);
+    else launch_vmult_general(op->dev, dst_dev, op->d_stage_src, false, op->d_hs_units + u0, n_units, op->stream);
+    op->launches++;
+  }
+  CUDA_CHECK(cudaStreamSynchronize(op->stream)); // kernel completion makes the stores to host memory visible to the caller
+  return (int)EXADG_B200_OK;
+}
+
+int exadg_b200_set_host_pipeline_mode(exadg_b200_operator * op, int mode)
+{
+  if (!op) return -1;
+  const int prev = op->hp_mode;
+  if (mode >= 0 && mode <= 2) op->hp_mode = mode;
+  return prev;
+}
+
 int exadg_b200_vmult_host_pipelined(exadg_b200_operator * op, double * dst_host, const double * src_host)
 {
   return guarded([&]() {
     if (!op || !dst_host || !src_host) throw std::invalid_argument("null argument");
     HostMesh & M = op->mesh;
     if (M.world > 1 || M.n_ghost > 0) { g_last_error = "the pipelined host-buffer vmult is for unpartitioned operators"; return (int)EXADG_B200_ERR_UNSUPPORTED; }
+    {
+      static const int env_mode = []() { const char * e = getenv("EXADG_B200_HOST_PIPELINE"); return !e ? 0 : (!strcmp(e, "staged") ? 1 : (!strcmp(e, "direct") ? 2 : 0)); }();
+      const int mode = op->hp_mode ? op->hp_mode : env_mode;
+      // auto: the affine kernels store whole batches (bulk / coalesced stores), which PCIe takes at full rate; the general kernel stores line by
+      // line and keeps the staged download
+      if (mode == 2 || (mode == 0 && op->dev.cartesian)) {
+        double * const dst_dev = device_view_of_host(dst_host);
+        if (dst_dev) return vmult_host_direct(op, dst_dev, src_host);
+        if (mode == 2) throw std::invalid_argument("direct mode needs a dst_host the GPU can address (cudaHostAlloc / cudaHostRegister memory)");
+      }
+    }
     const int n3 = op->dev.n * op->dev.n * op->dev.n;
     const bool cart = op->dev.cartesian;
     const int B = cart ? cartesian_batch_size(op->dev) : 1;
@@ -892,7 +978,8 @@ int exadg_b200_vmult_host_pipelined(exadg_b200_operator * op, double * dst_host,
     }
     const HostPipelinePlan & P = op->hp;
     if (P.n_chunks == 0) { g_last_error = "the pipelined host-buffer vmult is for unpartitioned operators"; return (int)EXADG_B200_ERR_UNSUPPORTED; }
-    if (!op->d_stage_src) { CUDA_CHECK(cudaMalloc(&op->d_stage_src, std::max<size_t>(bytes, 16))); CUDA_CHECK(cudaMalloc(&op->d_stage_dst, std::max<size_t>(bytes, 16))); }
+    if (!op->d_stage_src) CUDA_CHECK(cudaMalloc(&op->d_stage_src, std::max<size_t>(bytes, 16)));
+    if (!op->d_stage_dst) CUDA_CHECK(cudaMalloc(&op->d_stage_dst, std::max<size_t>(bytes, 16)));
     // neither copy stream may overtake earlier work of the operator's stream on the staging vectors
     CUDA_CHECK(cudaEventRecord(op->hp_start, op->stream));
     CUDA_CHECK(cudaStreamWaitEvent(op->hp_in, op->hp_start, 0));
@@ -941,6 +1028,29 @@ int exadg_b200_host_pipeline_plan(const exadg_b200_hypercube_desc * desc, int64_
     if (compute_order) std::copy(P.compute_order.begin(), P.compute_order.end(), compute_order);
     if (ready_chunk) std::copy(P.ready_chunk.begin(), P.ready_chunk.end(), ready_chunk);
     if (model) *model = host_pipeline_model(P);
+    return (int)EXADG_B200_OK;
+  });
+}
+
+// host-only view of the stream plan of the direct variant (no CUDA call; CPU tests): sizes with null arrays, then the tables
+int exadg_b200_host_stream_plan(const exadg_b200_hypercube_desc * desc, int unit, int64_t cells_per_piece, int32_t * n_steps, int64_t * n_units, int64_t * piece_begin,
+                                int64_t * step_begin, int32_t * units, double * model)
+{
+  return guarded([&]() {
+    if (!desc || !n_steps || !n_units) throw std::invalid_argument("null argument");
+    if (unit <= 0) throw std::invalid_argument("unit must be positive");
+    HypercubeDesc hd;
+    hd.n_sub = desc->n_subdivisions; hd.refine = desc->n_refinements; hd.mapping_degree = 1;
+    hd.deformation = 0.0; hd.frequency = desc->frequency;
+    for (int f = 0; f < 6; ++f) hd.bc[f] = desc->boundary[f];
+    hd.rank = desc->rank; hd.world = desc->world < 1 ? 1 : desc->world;
+    const HostMesh mesh = make_hypercube(hd);
+    const HostStreamPlan P = build_host_stream_plan(mesh.nb.data(), mesh.n_owned, unit, cells_per_piece > 0 ? cells_per_piece : host_stream_cells_per_piece(unit));
+    *n_steps = P.n_steps; *n_units = (int64_t)P.units.size();
+    if (piece_begin) std::copy(P.piece_begin.begin(), P.piece_begin.end(), piece_begin);
+    if (step_begin) std::copy(P.step_begin.begin(), P.step_begin.end(), step_begin);
+    if (units) std::copy(P.units.begin(), P.units.end(), units);
+    if (model) *model = host_stream_model(P);
     return (int)EXADG_B200_OK;
   });
 }

@@ -89,6 +89,7 @@ struct WsArgs
   // CTAs that start late (those that export this rank's cells first) then simply process fewer items
   int * counter;
   int HA, HT; // staged variant: first trace slot of the z faces = maximum number of x and y entries of a batch; HT = HA + HB trace slots
+  int l2pf;   // producers prefetch the neighbour cells of the batch after next into L2 (measurement switch EXADG_B200_WS_L2PF; 0 = off)
 };
 
 // all peers have stored this vmult's ghost cells (every lane acquires every flag: its later loads are ordered behind them)
@@ -226,6 +227,19 @@ WS_FN void ws_prefetch(const WsArgs & A, int bt, int lane, WsPrefetch & pre)
   pre.h[1] = lane + 32 < n ? A.halo[(size_t)bt * A.HL + lane + 32] : zero;
 }
 
+// optional: the owned neighbour cells of the halo list just fetched (the batch after next) are requested into L2, one batch period before the
+// producers load them; the entries are dealt to the producer warps in groups of eight
+template<int N, int NP, class RT>
+WS_FN void ws_l2_prefetch(RT & rt, const WsArgs & A, const WsPrefetch & pre, int pw, int lane)
+{
+  constexpr int N3 = N * N * N;
+  if ((lane >> 3) % NP != pw % NP) return;
+  const int n = ws_count_total(pre.c);
+  WS_UNROLL
+  for (int q = 0; q < 2; ++q)
+    if (lane + 32 * q < n && pre.h[q].y < A.n_owned) rt.prefetch_l2(A.src + (size_t)pre.h[q].y * N3, N3 * (int)sizeof(double));
+}
+
 // one round: the lines (direction D) of the neighbour cells of entries e0 .. e0 + R - 1 -> registers -> traces.  All loads
 // are issued before the first use; both end derivatives are computed and the one facing us is selected (no branches).
 template<int N, int R, int D, bool GH>
@@ -284,7 +298,7 @@ WS_FN void ws_produce(RT & rt, const WsTables<N> & T, const WsArgs & A, int bt, 
   int nl[NL];
   WS_UNROLL
   for (int j = 0; j < NL; ++j) { const int i = pw * 32 + lane + 32 * NP * j; nl[j] = i < B * 6 ? A.nloc[(size_t)bt * (B * 6) + i] : 0; }
-  if (bt_next >= 0) ws_prefetch(A, bt_next, lane, pre);
+  if (bt_next >= 0) { ws_prefetch(A, bt_next, lane, pre); if (A.l2pf) ws_l2_prefetch<N, NP>(rt, A, pre, pw, lane); }
   rt.sync_producer(pw);
   const bool act = lane < N2;
   const int ab = act ? lane : 0; // line within the face; the spare lanes shadow line 0 and store nothing

@@ -97,6 +97,15 @@ struct DeviceRT
     long long v;
     do { asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); } while (v < epoch);
   }
+  // request the 128-byte lines of [p, p + bytes) into L2 (no register, no scoreboard entry)
+  __device__ __forceinline__ void prefetch_l2(const double * p, int bytes)
+  {
+    const char * c = reinterpret_cast<const char *>(p);
+#pragma unroll
+    for (int i = 0; i < 1024; i += 128)
+      if (i < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + i));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(c + bytes - 8));
+  }
   __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
   // shared -> global bulk copy (plain store, or FP64 add-reduction for vmult_add)
   __device__ __forceinline__ void store_issue(double * g, const double * s, uint32_t bytes, bool add)
@@ -294,6 +303,8 @@ void ws_launch(const DeviceOperator & op, const void * p, double * dst, const do
   A.src = src; A.ghost = op.ghost; A.dst = dst; A.n_owned = op.n_owned; A.n_items = n_items; A.HL = P->HL; A.add = add ? 1 : 0;
   A.flags = nullptr; A.epoch = 0; A.first_ghost_item = 0; A.n_peers = 0; A.counter = nullptr; A.HA = 0; A.HT = 0;
   for (int i = 0; i < 16; ++i) A.peer_rank[i] = 0;
+  static const int l2pf = []() { const char * e = std::getenv("EXADG_B200_WS_L2PF"); return e ? std::atoi(e) : 0; }(); // measurement switch
+  A.l2pf = l2pf;
   if (depth == 3 && P->smem_st == 0) depth = 4; // staged variant not applicable to this mesh: the same kernel with strided loads
   if (depth == 3) { A.HA = P->HA; A.HT = P->HA + P->HB; }
   PutDesc put;

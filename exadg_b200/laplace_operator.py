@@ -191,6 +191,12 @@ class LaplaceOperator:
                 raise ExaDGError("vmult_host_pipelined expects contiguous host tensors of the local size")
         _check(_lib().exadg_b200_vmult_host_pipelined(self._h, C.c_void_p(dst_host.data_ptr()), C.c_void_p(src_host.data_ptr())))
 
+    def set_host_pipeline_mode(self, mode):
+        """Variant of vmult_host_pipelined: 0 automatic, 1 / "staged" chunk plan with a copy-engine download per chunk, 2 / "direct"
+        piece-wise upload with the kernels storing dst straight into the pinned host tensor; returns the previous mode (an int)."""
+        mode = {"auto": 0, "staged": 1, "direct": 2}.get(mode, mode)
+        return _lib().exadg_b200_set_host_pipeline_mode(self._h, int(mode))
+
     def calculate_diagonal(self, diagonal):
         self._order_after_torch()
         _check(_lib().exadg_b200_calculate_diagonal(self._h, _ptr(diagonal, self._n_local)))
@@ -592,6 +598,23 @@ def host_pipeline_plan(n_subdivisions, n_refinements, cells_per_chunk=0, boundar
     _check(L.exadg_b200_host_pipeline_plan(C.byref(d), int(cells_per_chunk), C.byref(n), p(out["upload_order"]), p(out["compute_order"]), p(out["ready_chunk"]),
                                            C.byref(model)))
     out["n_chunks"], out["model"] = n.value, model.value
+    return out
+
+
+def host_stream_plan(n_subdivisions, n_refinements, unit=24, cells_per_piece=0, boundary=(0,) * 6, rank=0, world=1):
+    """Host-only view (no GPU needed) of the plan of the direct variant of vmult_host_pipelined on a hypercube grid: dict with n_steps,
+    piece_begin (cell ranges in upload order), step_begin / units (the kernel units of `unit` cells applied behind every upload) and
+    the modelled duration of one call in units of a one-direction transfer (1 = perfect overlap)."""
+    L = _lib()
+    d = _desc(1, n_subdivisions, n_refinements, 1, 0.0, 2, boundary, 1.0, rank, world, False)
+    n, nu, model = C.c_int32(), C.c_int64(), C.c_double()
+    _check(L.exadg_b200_host_stream_plan(C.byref(d), int(unit), C.c_int64(int(cells_per_piece)), C.byref(n), C.byref(nu), None, None, None, C.byref(model)))
+    out = {"piece_begin": np.zeros(n.value + 1, dtype=np.int64), "step_begin": np.zeros(n.value + 1, dtype=np.int64), "units": np.zeros(nu.value, dtype=np.int32)}
+    if n.value > 0:
+        _check(L.exadg_b200_host_stream_plan(C.byref(d), int(unit), C.c_int64(int(cells_per_piece)), C.byref(n), C.byref(nu),
+                                             out["piece_begin"].ctypes.data_as(C.POINTER(C.c_int64)), out["step_begin"].ctypes.data_as(C.POINTER(C.c_int64)),
+                                             out["units"].ctypes.data_as(C.POINTER(C.c_int32)), C.byref(model)))
+    out["n_steps"], out["unit"], out["model"] = n.value, int(unit), model.value
     return out
 
 

@@ -145,6 +145,20 @@ int exadg_b200_vmult_host_pipelined(exadg_b200_operator *op, double *dst_host, c
 int exadg_b200_host_pipeline_plan(const exadg_b200_hypercube_desc *desc, int64_t cells_per_chunk, int32_t *n_chunks, int32_t *upload_order,
                                   int32_t *compute_order, int32_t *ready_chunk, double *model);
 
+/* Variants of exadg_b200_vmult_host_pipelined (no reference counterpart; returns the previous mode, a value outside 0..2 only queries):
+ * 0 automatic, 1 "staged" - the chunk plan above with a copy-engine download per chunk, 2 "direct" - src is uploaded piece by piece in
+ * address order, behind every piece one launch applies the kernel units (cell batches) whose cells and face neighbours are complete,
+ * and the kernels store dst straight into dst_host through its device mapping (needs cudaHostAlloc / cudaHostRegister memory; every
+ * DoF of dst is written exactly once).  Automatic = direct on the affine fast path when dst_host is device-accessible, else staged.
+ * Environment override of the automatic choice: EXADG_B200_HOST_PIPELINE=staged|direct. */
+int exadg_b200_set_host_pipeline_mode(exadg_b200_operator *op, int mode);
+/* host-only view of the plan of the direct variant (no CUDA call; CPU tests): *n_steps pieces / launches and *n_units kernel units of
+ * `unit` cells with null arrays, then piece_begin[n_steps + 1] (cell ranges in upload order), step_begin[n_steps + 1] and units[n_units]
+ * (the units applied behind upload i are units[step_begin[i] .. step_begin[i + 1])); model as above (1 = perfect overlap).
+ * cells_per_piece <= 0 selects the library's default. */
+int exadg_b200_host_stream_plan(const exadg_b200_hypercube_desc *desc, int unit, int64_t cells_per_piece, int32_t *n_steps, int64_t *n_units,
+                                int64_t *piece_begin, int64_t *step_begin, int32_t *units, double *model);
+
 /* OperatorBase::calculate_diagonal / add_diagonal / calculate_inverse_diagonal
  * (operator_base.cpp:608-646, 249-262; invert_diagonal.h:35-46) */
 int exadg_b200_calculate_diagonal(exadg_b200_operator *op, double *diagonal);

@@ -156,7 +156,7 @@ int wse_vmult(void * h, const double * src, const double * ghost, double * dst, 
   A.batches = which == 0 ? nullptr : (which == 1 ? E->interior.data() : E->boundary.data());
   A.n_items = wse_n_batches(h, which);
   A.src = src; A.ghost = ghost; A.dst = dst; A.n_owned = E->mesh.n_owned; A.HL = E->plan.HL; A.add = add;
-  A.flags = nullptr; A.epoch = 0; A.first_ghost_item = 0; A.n_peers = 0; A.counter = nullptr;
+  A.flags = nullptr; A.epoch = 0; A.first_ghost_item = 0; A.n_peers = 0; A.counter = nullptr; A.HA = 0; A.HT = 0; A.l2pf = 0;
   if (E->plan.HL > Cfg::HLMAX || E->mesh.n_owned % 2 != 0) return -1; // the library falls back to the pipelined kernel
   if (A.n_items == 0) return 0;
   n_ctas = std::min(n_ctas, A.n_items);

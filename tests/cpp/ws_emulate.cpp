@@ -103,6 +103,7 @@ struct HostRT
     while (__atomic_load_n(p, __ATOMIC_ACQUIRE) < epoch) sched_yield();
   }
   int claim(int * counter) { return __atomic_fetch_add(counter, 1, __ATOMIC_RELAXED); }
+  void prefetch_l2(const double *, int) {}
   void fence_async() {}
   void check_store()
   {
@@ -183,6 +184,7 @@ int wse_vmult(void * h, const double * src, const double * ghost, double * dst, 
   A.n_items = wse_n_batches(h, which);
   A.src = src; A.ghost = ghost; A.dst = dst; A.n_owned = E->mesh.n_owned; A.HL = E->plan.HL; A.add = add;
   A.flags = nullptr; A.epoch = 0; A.first_ghost_item = 0; A.n_peers = 0; A.counter = nullptr; A.HA = 0; A.HT = 0;
+  A.l2pf = 1; // exercises the (no-op here) prefetch path: indexing only
   if (STAGED) { A.HA = E->plan.HA; A.HT = E->plan.HA + E->plan.HB; }
   if (g_dynamic) { g_counter = 0; A.counter = &g_counter; }
   if (A.n_items == 0) return 0;

@@ -1,6 +1,6 @@
-"""exadg_b200_vmult_host_pipelined (upload, operator and download overlapped chunk by chunk) must give the device vmult bit for bit -
-eagerly on the first call with a pair of host buffers, as one CUDA graph launch from the second call on, and again after the buffers
-change.  It runs in a child process (a fault in the stream / graph choreography cannot poison the CUDA context of the other tests); its
+"""exadg_b200_vmult_host_pipelined (upload, operator and download overlapped inside the call) must give the device vmult bit for bit in
+both of its variants - chunk by chunk with a copy-engine download ("staged"), and piece-wise upload with the kernels storing dst
+straight into the pinned host buffer ("direct") - on repeated calls and again after the buffers change.  It runs in a child process (a fault in the stream / graph choreography cannot poison the CUDA context of the other tests); its
 host-side plan is covered on the CPU by tests/test_host_pipeline.py."""
 import os
 import subprocess
@@ -24,10 +24,25 @@ for (degree, n_sub, refine, deformation) in [(4, 3, 3, 0.0), (4, 5, 2, 0.0), (3,
     op.vmult(dst, src)
     h_src = torch.empty(op.local_size(), dtype=torch.float64).pin_memory(); h_src.copy_(src.cpu())
     h_dst = torch.empty(op.local_size(), dtype=torch.float64).pin_memory()
-    for rep in range(4):   # eager, capture + graph launch, graph launch, graph launch
-        h_dst.fill_(float("nan"))
-        op.vmult_host_pipelined(h_dst, h_src)
-        assert (h_dst.cuda() - dst).abs().max().item() == 0.0, (degree, n_sub, refine, deformation, rep)
+    # both variants: "staged" (chunk plan, copy-engine download per chunk) and "direct" (piece-wise upload, the kernels store dst
+    # straight into the pinned host tensor); then the automatic choice, which the remaining checks run with
+    for mode in ("staged", "direct", "auto"):
+        op.set_host_pipeline_mode(mode)
+        for rep in range(3):   # plan and events are built by the first call and reused
+            h_dst.fill_(float("nan"))
+            op.vmult_host_pipelined(h_dst, h_src)
+            assert (h_dst.cuda() - dst).abs().max().item() == 0.0, (degree, n_sub, refine, deformation, mode, rep)
+    # direct mode needs a host buffer the GPU can address: pageable memory is refused there and takes the staged path in automatic mode
+    p_dst = torch.full((op.local_size(),), float("nan"), dtype=torch.float64)
+    op.vmult_host_pipelined(p_dst, h_src)
+    assert (p_dst.cuda() - dst).abs().max().item() == 0.0
+    op.set_host_pipeline_mode("direct")
+    try:
+        op.vmult_host_pipelined(p_dst, h_src)
+        raise SystemExit("direct mode accepted pageable memory")
+    except exadg_b200.ExaDGError:
+        pass
+    op.set_host_pipeline_mode("auto")
     # another pair of buffers and another vector: the graph of the first pair must not be reused
     src2 = torch.rand(op.local_size(), dtype=torch.float64, device="cuda") * 2 - 1
     op.vmult(dst, src2)

@@ -50,3 +50,47 @@ def test_benchmark_mesh_overlaps_most_of_the_two_transfers():
     P = exadg_b200.host_pipeline_plan(3, 5, 1536)  # finer chunks overlap more on paper (and cost more per chunk in practice)
     assert P["n_chunks"] == 576
     assert P["model"] < 1.3
+
+
+# ---- direct variant: pieces in address order, readiness per kernel unit (HostStreamPlan) ----
+def check_stream_plan(n_sub, refine, unit, cells_per_piece, boundary=(0,) * 6):
+    P = exadg_b200.host_stream_plan(n_sub, refine, unit, cells_per_piece, boundary)
+    nb = PartitionPlan(n_sub, refine, 0, 1, boundary).neighbors
+    n_cells = nb.shape[0]
+    K = P["n_steps"]
+    assert K == -(-n_cells // cells_per_piece)
+    assert P["piece_begin"][0] == 0 and P["piece_begin"][-1] == n_cells and np.all(np.diff(P["piece_begin"]) > 0)
+    n_units = -(-n_cells // unit)
+    assert sorted(P["units"].tolist()) == list(range(n_units)), "every unit is applied exactly once"
+    assert P["step_begin"][0] == 0 and P["step_begin"][-1] == n_units and np.all(np.diff(P["step_begin"]) >= 0)
+    piece = np.searchsorted(P["piece_begin"], np.arange(n_cells), side="right") - 1  # piece (= upload step) of every cell
+    for i in range(K):
+        us = P["units"][P["step_begin"][i]:P["step_begin"][i + 1]]
+        assert np.all(np.diff(us) > 0)
+        for u in us:
+            cells = np.arange(u * unit, min((u + 1) * unit, n_cells))
+            neigh = nb[cells].ravel()
+            need = max(piece[cells].max(), piece[neigh[neigh >= 0]].max(initial=0))
+            assert need == i, "unit %d is applied behind upload %d but is complete with upload %d" % (u, i, need)
+    return P
+
+
+@pytest.mark.parametrize("n_sub,refine,unit,cpp", [(3, 2, 24, 48), (1, 3, 24, 96), (5, 1, 16, 80), (3, 2, 1, 100), (3, 2, 32, 1536), (3, 1, 64, 64)])
+def test_units_are_applied_behind_the_upload_that_completes_them(n_sub, refine, unit, cpp):
+    check_stream_plan(n_sub, refine, unit, cpp)
+
+
+def test_stream_plan_with_boundaries_and_ragged_last_unit():
+    check_stream_plan(3, 1, 24, 48, (1, 2, 1, 1, 0, 0))  # 216 cells: 9 units
+    check_stream_plan(5, 0, 24, 48)                      # 125 cells: the last unit has 5 cells, the last piece 29
+
+
+def test_partitioned_operators_have_no_stream_plan():
+    assert exadg_b200.host_stream_plan(3, 2, 24, 48, rank=0, world=2)["n_steps"] == 0
+
+
+def test_benchmark_mesh_streams_with_little_more_than_one_transfer():
+    P = exadg_b200.host_stream_plan(3, 5)  # 96^3 cells, 24-cell batches, library default: 72 pieces of 12288 cells
+    assert P["n_steps"] == 72
+    assert P["model"] < 1.12               # chunk plan: 1.46
+    assert exadg_b200.host_stream_plan(3, 5, 24, 98304)["model"] < 1.21
