@@ -324,13 +324,14 @@ void launch_vmult(exadg_b200_operator * op, double * dst, const double * src, bo
 
 // dst (+)= A src including the ghost import of src (MatrixFree::loop's update_ghost_values, overlapped
 // with the cells that touch no ghost)
-void apply(exadg_b200_operator * op, double * dst, const double * src, bool add)
+// boundary_only (partitioned operators): ghost import + the cells (batches) that touch ghost cells; the others were applied by the caller
+void apply(exadg_b200_operator * op, double * dst, const double * src, bool add, bool boundary_only = false)
 {
   if (op->n_local == 0 && op->mesh.peers.empty()) return; // is_empty_locally: a rank without cells (and without neighbours) has nothing to do
   check_ptr(dst, "dst"); check_ptr(src, "src");
   if (dst == src) throw std::invalid_argument("dst and src must not alias");
   HostMesh & M = op->mesh;
-  if (M.world <= 1 || M.peers.empty()) { launch_vmult(op, dst, src, add, 0); return; }
+  if (M.world <= 1 || M.peers.empty()) { if (!boundary_only) launch_vmult(op, dst, src, add, 0); return; }
   const int n3 = op->dev.n * op->dev.n * op->dev.n;
   if (op->p2p) {
     const long long epoch = ++op->p2p_epoch;
@@ -351,7 +352,7 @@ void apply(exadg_b200_operator * op, double * dst, const double * src, bool add)
     // src must be complete (work queued on the compute stream) before it is read on the communication stream
     CUDA_CHECK(cudaEventRecord(op->ev_packed, op->stream));
     CUDA_CHECK(cudaStreamWaitEvent(op->comm_stream, op->ev_packed, 0));
-    if (op->dev.cartesian && op->d_put_done) {
+    if (!boundary_only && op->dev.cartesian && op->d_put_done) {
       // single launch: the operator kernel exports this rank's cells before its first batch (every CTA a slice, the last one per
       // peer publishes the epoch), runs the batches without ghost neighbours, and its producers acquire the peers' flags before
       // the first batch that reads ghost cells.  No communication stream, no events.
@@ -378,7 +379,7 @@ void apply(exadg_b200_operator * op, double * dst, const double * src, bool add)
     // overlap with the tail of the interior-cell kernel on the compute stream; the streams join at the end
     launch_vmult(op, dst, src, add, 2, op->comm_stream);
     CUDA_CHECK(cudaEventRecord(op->ev_halo, op->comm_stream));
-    launch_vmult(op, dst, src, add, 1);
+    if (!boundary_only) launch_vmult(op, dst, src, add, 1);
     CUDA_CHECK(cudaStreamWaitEvent(op->stream, op->ev_halo, 0));
     CUDA_CHECK(cudaGetLastError());
     return;
@@ -405,7 +406,7 @@ void apply(exadg_b200_operator * op, double * dst, const double * src, bool add)
   }
   launch_vmult(op, dst, src, add, 2, op->comm_stream);
   CUDA_CHECK(cudaEventRecord(op->ev_halo, op->comm_stream));
-  launch_vmult(op, dst, src, add, 1);
+  if (!boundary_only) launch_vmult(op, dst, src, add, 1);
   CUDA_CHECK(cudaStreamWaitEvent(op->stream, op->ev_halo, 0));
 }
 
@@ -875,7 +876,9 @@ static int64_t host_pipeline_cells_per_chunk(int batch)
 // once, as on the device path).  No staging vector and no copy-engine download: the download has the granularity of a kernel unit.
 static int64_t host_stream_cells_per_piece(int unit)
 {
-  static const int64_t target = []() { const char * e = getenv("EXADG_B200_HS_CELLS"); const long v = e ? std::atol(e) : 12288; return (int64_t)(v > 0 ? v : 12288); }();
+  // measured on the 96^3 box (k = 4, scripts/r02_shot40.sh): 3072 / 6144 / 12288 / 24576 / 49152 cells per piece -> 4.47 / 4.79 / 5.03 / 5.19 / 5.18 GDoF/s
+  // end to end (staged variant 4.34, sequential entry 3.25)
+  static const int64_t target = []() { const char * e = getenv("EXADG_B200_HS_CELLS"); const long v = e ? std::atol(e) : 24576; return (int64_t)(v > 0 ? v : 24576); }();
   const int64_t per = std::max<int64_t>(1, (target + unit / 2) / unit);
   return per * unit;
 }
@@ -897,24 +900,28 @@ static int vmult_host_direct(exadg_b200_operator * op, double * dst_dev, const d
   const int B = cart ? cartesian_batch_size(op->dev) : 1;
   const size_t bytes = (size_t)op->n_local * sizeof(double);
   if (!op->hs_built) {
-    op->hs = build_host_stream_plan(M.nb.data(), M.n_owned, B, host_stream_cells_per_piece(B));
+    op->hs = build_host_stream_plan(M.nb.data(), M.n_owned, B, host_stream_cells_per_piece(B), /*allow_ghosts=*/M.world > 1 && !M.peers.empty());
     const HostStreamPlan & P = op->hs;
     if (P.n_steps > 0) {
       CUDA_CHECK(cudaMalloc(&op->d_hs_units, std::max<size_t>(P.units.size(), 1) * sizeof(int32_t)));
       CUDA_CHECK(cudaMemcpy(op->d_hs_units, P.units.data(), P.units.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
       if (!op->hp_in) CUDA_CHECK(cudaStreamCreateWithFlags(&op->hp_in, cudaStreamNonBlocking));
       if (!op->hp_start) CUDA_CHECK(cudaEventCreateWithFlags(&op->hp_start, cudaEventDisableTiming));
-      op->hs_ev.assign(P.n_steps, nullptr);
+      op->hs_ev.assign(P.n_steps + 1, nullptr); // the last one: all uploads complete
       for (auto & e : op->hs_ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     op->hs_built = true;
   }
   const HostStreamPlan & P = op->hs;
-  if (P.n_steps == 0) { g_last_error = "the pipelined host-buffer vmult is for unpartitioned operators"; return (int)EXADG_B200_ERR_UNSUPPORTED; }
+  const bool import_ghosts = M.world > 1 && !M.peers.empty();
+  // (a rank of a partition that owns no cell has no plan but still takes part in the ghost import below)
+  if (P.n_steps == 0 && !(import_ghosts && M.n_owned == 0)) { g_last_error = "the pipelined host-buffer vmult does not apply to this operator"; return (int)EXADG_B200_ERR_UNSUPPORTED; }
   if (!op->d_stage_src) CUDA_CHECK(cudaMalloc(&op->d_stage_src, std::max<size_t>(bytes, 16)));
-  // the upload stream may not overtake earlier work of the operator's stream on the staging vector
-  CUDA_CHECK(cudaEventRecord(op->hp_start, op->stream));
-  CUDA_CHECK(cudaStreamWaitEvent(op->hp_in, op->hp_start, 0));
+  if (P.n_steps > 0) {
+    // the upload stream may not overtake earlier work of the operator's stream on the staging vector
+    CUDA_CHECK(cudaEventRecord(op->hp_start, op->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(op->hp_in, op->hp_start, 0));
+  }
   for (int i = 0; i < P.n_steps; ++i) {
     const int64_t c0 = P.piece_begin[i], c1 = P.piece_begin[i + 1];
     CUDA_CHECK(cudaMemcpyAsync(op->d_stage_src + c0 * n3, src_host + c0 * n3, (size_t)(c1 - c0) * n3 * sizeof(double), cudaMemcpyHostToDevice, op->hp_in));
@@ -925,6 +932,15 @@ static int vmult_host_direct(exadg_b200_operator * op, double * dst_dev, const d
     if (cart) launch_vmult_cartesian_list(op->dev, dst_dev, op->d_stage_src, false, op->d_hs_units + u0, (int)n_units, op->stream);
     else launch_vmult_general(op->dev, dst_dev, op->d_stage_src, false, op->d_hs_units + u0, n_units, op->stream);
     op->launches++;
+  }
+  if (import_ghosts) {
+    // partitioned operator: the units above touch no ghost cell; the others follow the ghost import of src (all ranks enter this call), which
+    // needs this rank's complete src on the device
+    if (P.n_steps > 0) {
+      CUDA_CHECK(cudaEventRecord(op->hs_ev[P.n_steps], op->hp_in));
+      CUDA_CHECK(cudaStreamWaitEvent(op->stream, op->hs_ev[P.n_steps], 0));
+    }
+    apply(op, dst_dev, op->d_stage_src, false, /*boundary_only=*/true);
   }
   CUDA_CHECK(cudaStreamSynchronize(op->stream)); // kernel completion makes the stores to host memory visible to the caller
   return (int)EXADG_B200_OK;
@@ -943,7 +959,8 @@ int exadg_b200_vmult_host_pipelined(exadg_b200_operator * op, double * dst_host,
   return guarded([&]() {
     if (!op || !dst_host || !src_host) throw std::invalid_argument("null argument");
     HostMesh & M = op->mesh;
-    if (M.world > 1 || M.n_ghost > 0) { g_last_error = "the pipelined host-buffer vmult is for unpartitioned operators"; return (int)EXADG_B200_ERR_UNSUPPORTED; }
+    const bool partitioned = M.world > 1 || M.n_ghost > 0;
+    if (partitioned && M.peers.empty() && M.n_ghost > 0) { g_last_error = "the pipelined host-buffer vmult cannot import ghost cells the caller owns"; return (int)EXADG_B200_ERR_UNSUPPORTED; }
     {
       static const int env_mode = []() { const char * e = getenv("EXADG_B200_HOST_PIPELINE"); return !e ? 0 : (!strcmp(e, "staged") ? 1 : (!strcmp(e, "direct") ? 2 : 0)); }();
       const int mode = op->hp_mode ? op->hp_mode : env_mode;
@@ -955,6 +972,7 @@ int exadg_b200_vmult_host_pipelined(exadg_b200_operator * op, double * dst_host,
         if (mode == 2) throw std::invalid_argument("direct mode needs a dst_host the GPU can address (cudaHostAlloc / cudaHostRegister memory)");
       }
     }
+    if (partitioned) { g_last_error = "the staged variant of the pipelined host-buffer vmult is for unpartitioned operators"; return (int)EXADG_B200_ERR_UNSUPPORTED; }
     const int n3 = op->dev.n * op->dev.n * op->dev.n;
     const bool cart = op->dev.cartesian;
     const int B = cart ? cartesian_batch_size(op->dev) : 1;
@@ -1045,7 +1063,7 @@ int exadg_b200_host_stream_plan(const exadg_b200_hypercube_desc * desc, int unit
     for (int f = 0; f < 6; ++f) hd.bc[f] = desc->boundary[f];
     hd.rank = desc->rank; hd.world = desc->world < 1 ? 1 : desc->world;
     const HostMesh mesh = make_hypercube(hd);
-    const HostStreamPlan P = build_host_stream_plan(mesh.nb.data(), mesh.n_owned, unit, cells_per_piece > 0 ? cells_per_piece : host_stream_cells_per_piece(unit));
+    const HostStreamPlan P = build_host_stream_plan(mesh.nb.data(), mesh.n_owned, unit, cells_per_piece > 0 ? cells_per_piece : host_stream_cells_per_piece(unit), hd.world > 1);
     *n_steps = P.n_steps; *n_units = (int64_t)P.units.size();
     if (piece_begin) std::copy(P.piece_begin.begin(), P.piece_begin.end(), piece_begin);
     if (step_begin) std::copy(P.step_begin.begin(), P.step_begin.end(), step_begin);

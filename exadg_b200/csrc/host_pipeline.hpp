@@ -6,6 +6,7 @@
 // exadg_b200_host_pipeline_plan), the stream / event choreography is in c_api.cu.
 #pragma once
 #include <algorithm>
+#include <climits>
 #include <cstdint>
 #include <vector>
 
@@ -89,42 +90,47 @@ inline double host_pipeline_model(const HostPipelinePlan & P)
 // box 1.11 transfer times per call with 72 pieces.
 struct HostStreamPlan
 {
-  int n_steps = 0;                  // 0: not applicable (ghost neighbours)
+  int n_steps = 0;                  // 0: not applicable
   int unit = 1;                     // cells per unit
   int64_t cells_per_piece = 0;
   std::vector<int64_t> piece_begin; // [n_steps + 1]: piece i = cells [piece_begin[i], piece_begin[i + 1]), uploaded in this order
   std::vector<int32_t> units;       // unit ids grouped by the step whose upload makes them computable, ascending within a step
   std::vector<int64_t> step_begin;  // [n_steps + 1]: units of step i = units[step_begin[i] .. step_begin[i + 1])
+  int64_t n_late = 0;               // partitioned operators: units with a ghost neighbour; they are not in `units` - the caller applies
+                                    // them behind the ghost import, after the last upload
 };
 
 // nb: [n_owned][6] neighbour cell (or < 0 on the boundary); unit u = cells [u * unit, (u + 1) * unit)
-inline HostStreamPlan build_host_stream_plan(const int32_t * nb, int64_t n_owned, int unit, int64_t cells_per_piece)
+// allow_ghosts: units with a neighbour >= n_owned are counted in n_late and left out of the steps (false: such a mesh has no plan)
+inline HostStreamPlan build_host_stream_plan(const int32_t * nb, int64_t n_owned, int unit, int64_t cells_per_piece, bool allow_ghosts = false)
 {
   HostStreamPlan P;
   if (n_owned <= 0 || unit <= 0 || cells_per_piece <= 0) return P;
   const int K = (int)((n_owned + cells_per_piece - 1) / cells_per_piece);
   const int64_t n_units = (n_owned + unit - 1) / unit;
+  constexpr int32_t LATE = INT32_MAX;
   std::vector<int32_t> ready((size_t)n_units, 0);
   for (int64_t c = 0; c < n_owned; ++c) {
     int32_t r = (int32_t)(c / cells_per_piece);
     for (int f = 0; f < 6; ++f) {
       const int32_t p = nb[c * 6 + f];
       if (p < 0) continue;
-      if (p >= n_owned) return P; // ghost cell
+      if (p >= n_owned) { if (!allow_ghosts) return P; r = LATE; continue; } // ghost cell
       r = std::max(r, (int32_t)(p / cells_per_piece));
     }
     int32_t & ru = ready[(size_t)(c / unit)];
     ru = std::max(ru, r);
   }
+  for (int64_t u = 0; u < n_units; ++u) if (ready[(size_t)u] == LATE) ++P.n_late;
   P.n_steps = K; P.unit = unit; P.cells_per_piece = cells_per_piece;
   P.piece_begin.resize((size_t)K + 1);
   for (int i = 0; i <= K; ++i) P.piece_begin[i] = std::min<int64_t>(n_owned, (int64_t)i * cells_per_piece);
   P.step_begin.assign((size_t)K + 1, 0);
-  for (int64_t u = 0; u < n_units; ++u) ++P.step_begin[(size_t)ready[(size_t)u] + 1];
+  for (int64_t u = 0; u < n_units; ++u) if (ready[(size_t)u] != LATE) ++P.step_begin[(size_t)ready[(size_t)u] + 1];
   for (int i = 0; i < K; ++i) P.step_begin[i + 1] += P.step_begin[i];
-  P.units.resize((size_t)n_units);
+  P.units.resize((size_t)(n_units - P.n_late));
   std::vector<int64_t> fill(P.step_begin.begin(), P.step_begin.end() - 1);
-  for (int64_t u = 0; u < n_units; ++u) P.units[(size_t)fill[(size_t)ready[(size_t)u]]++] = (int32_t)u;
+  for (int64_t u = 0; u < n_units; ++u) if (ready[(size_t)u] != LATE) P.units[(size_t)fill[(size_t)ready[(size_t)u]]++] = (int32_t)u;
   return P;
 }
 
@@ -134,7 +140,7 @@ inline double host_stream_model(const HostStreamPlan & P)
 {
   if (P.n_steps == 0) return 2.0;
   const double n = (double)P.piece_begin[P.n_steps];
-  const int64_t n_units = (int64_t)P.units.size();
+  const int64_t n_units = ((int64_t)n + P.unit - 1) / P.unit;
   double t = 0;
   for (int i = 0; i < P.n_steps; ++i) {
     double cells = 0;

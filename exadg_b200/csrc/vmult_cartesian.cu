@@ -1234,10 +1234,10 @@ void launch_vmult_cartesian_part(const DeviceOperator & op, double * dst, const 
   launch_cart(op, dst, src, add, which, nullptr, 0, stream);
 }
 
-// explicit list of batches of an operator without ghost cells (chunks of the pipelined host-buffer vmult)
+// explicit list of batches that read no ghost cell (steps of the pipelined host-buffer vmult; on a partitioned operator the batches with
+// ghost neighbours are not in these lists - they run behind the ghost import)
 void launch_vmult_cartesian_list(const DeviceOperator & op, double * dst, const double * src, bool add, const int32_t * list, int n_list, cudaStream_t stream)
 {
-  if (op.n_ghost > 0) throw std::runtime_error("batch-list launches are for operators without ghost cells");
   if (n_list > 0) launch_cart(op, dst, src, add, 1, list, n_list, stream);
 }
 

@@ -136,8 +136,8 @@ int exadg_b200_vmult_add(exadg_b200_operator *op, double *dst, const double *src
 int exadg_b200_vmult_host(exadg_b200_operator *op, double *dst_host, const double *src_host);
 
 /* same result, but upload, operator and download overlap chunk by chunk inside the call (PCIe is full duplex): a chunk of cells
- * is applied once the chunks holding its face neighbours have arrived.  Unpartitioned operators only (returns
- * EXADG_B200_ERR_UNSUPPORTED otherwise); the host buffers should be pinned. */
+ * is applied once the chunks holding its face neighbours have arrived.  The host buffers should be pinned.  Two variants, see
+ * exadg_b200_set_host_pipeline_mode; returns EXADG_B200_ERR_UNSUPPORTED where neither applies. */
 int exadg_b200_vmult_host_pipelined(exadg_b200_operator *op, double *dst_host, const double *src_host);
 /* host-only view of the chunk plan of exadg_b200_vmult_host_pipelined (no CUDA call; CPU tests): n_chunks with null arrays, then
  * upload order, compute order and, per chunk, the chunk whose upload makes it computable; model = duration of one call in units
@@ -150,11 +150,14 @@ int exadg_b200_host_pipeline_plan(const exadg_b200_hypercube_desc *desc, int64_t
  * address order, behind every piece one launch applies the kernel units (cell batches) whose cells and face neighbours are complete,
  * and the kernels store dst straight into dst_host through its device mapping (needs cudaHostAlloc / cudaHostRegister memory; every
  * DoF of dst is written exactly once).  Automatic = direct on the affine fast path when dst_host is device-accessible, else staged.
+ * The direct variant also serves partitioned operators whose ghost import the library owns (hypercube partitions; all ranks call
+ * it together like vmult): the units that touch ghost cells follow the ghost import behind the last upload.
  * Environment override of the automatic choice: EXADG_B200_HOST_PIPELINE=staged|direct. */
 int exadg_b200_set_host_pipeline_mode(exadg_b200_operator *op, int mode);
 /* host-only view of the plan of the direct variant (no CUDA call; CPU tests): *n_steps pieces / launches and *n_units kernel units of
  * `unit` cells with null arrays, then piece_begin[n_steps + 1] (cell ranges in upload order), step_begin[n_steps + 1] and units[n_units]
  * (the units applied behind upload i are units[step_begin[i] .. step_begin[i + 1])); model as above (1 = perfect overlap).
+ * On a partition (desc->world > 1) the units with a ghost neighbour are not listed: they follow the ghost import.
  * cells_per_piece <= 0 selects the library's default. */
 int exadg_b200_host_stream_plan(const exadg_b200_hypercube_desc *desc, int unit, int64_t cells_per_piece, int32_t *n_steps, int64_t *n_units,
                                 int64_t *piece_begin, int64_t *step_begin, int32_t *units, double *model);

@@ -68,6 +68,27 @@ def check_case(case, transport, rank, world):
     # vmult_add on top of the last result
     op.vmult_add(dst, src)
     worst = max(worst, ((dst - 6 * y_ref[lo:hi]).norm() / (6 * y_ref.norm())).item())
+    # host-buffer vmult, direct variant on the partition (piece-wise upload, interior units behind the uploads with dst stored straight into
+    # the pinned host buffer, units with ghost neighbours behind the ghost import): bit for bit the device vmult, repeatedly (epochs)
+    op.vmult(dst, src)
+    h_src = src.cpu().pin_memory()
+    h_dst = torch.empty_like(h_src).pin_memory()
+    op.set_host_pipeline_mode("direct")
+    pipe_diff = 0.0
+    for rep in range(3):
+        h_dst.fill_(float("nan"))
+        op.vmult_host_pipelined(h_dst, h_src)
+        d = (h_dst.cuda() - dst).abs().max().item()
+        pipe_diff = max(pipe_diff, d if d == d else float("inf"))
+    op.set_host_pipeline_mode("auto")
+    op.vmult_host(h_dst, h_src)  # the sequential entry point after it
+    pipe_diff = max(pipe_diff, (h_dst.cuda() - dst).abs().max().item())
+    pflag = torch.tensor([pipe_diff], device="cuda")
+    dist.all_reduce(pflag, op=dist.ReduceOp.MAX)
+    if pflag.item() != 0.0:
+        ok = False
+        if rank == 0:
+            print("host-buffer vmult (direct variant) differs from the device vmult: %g" % pflag.item(), flush=True)
     its = None
     if bc != P6:  # CG with Jacobi: iteration counts equal to the single-partition solve
         b = y_ref.clone()
