@@ -570,7 +570,7 @@ def run_gpu(args):
     # used for the e2e figure only if a child process has first reproduced the device result bit for bit with it, if it does so again
     # here, and if it is faster
     e2e_apis = {"staged": "exadg_b200_vmult_host_pipelined, staged variant (pinned host src/dst; upload, vmult and copy-engine download overlap chunk by chunk inside the call)",
-                "direct": "exadg_b200_vmult_host_pipelined, direct variant (pinned host src/dst; src uploaded in 12 MB pieces, behind every piece one launch applies the "
+                "direct": "exadg_b200_vmult_host_pipelined, direct variant (pinned host src/dst; src uploaded in 24 MB pieces, behind every piece one launch applies the "
                           "cell batches whose neighbours have arrived, the kernel's bulk stores write dst straight into the pinned host buffer over PCIe)"}
     if world == 1 and args.e2e_api != "plain":
         for mode in probe_pipelined_e2e(degree, n_sub, refine, deformation):
