@@ -857,9 +857,10 @@ int exadg_b200_vmult_host(exadg_b200_operator * op, double * dst_host, const dou
   });
 }
 
-// Same result as exadg_b200_vmult_host, but the upload of src, the operator and the download of dst overlap: the vector is cut into
-// contiguous chunks (host_pipeline.hpp), a chunk is applied as soon as the chunks holding its face neighbours have arrived and is
-// downloaded right behind its kernel on a third stream.  Unpartitioned operators only; host buffers should be pinned.
+// Same result as exadg_b200_vmult_host, but the upload of src, the operator and the download of dst overlap.  Staged variant: the vector is cut
+// into contiguous chunks (host_pipeline.hpp), a chunk is applied as soon as the chunks holding its face neighbours have arrived and is
+// downloaded right behind its kernel on a third stream (unpartitioned operators only).  Direct variant: vmult_host_direct below.  Host
+// buffers should be pinned.
 static int64_t host_pipeline_cells_per_chunk(int batch)
 {
   // about 12288 cells (24 blocks of 8^3 cells of the Morton curve on refined hypercubes; 12 MB per copy at k = 4), a multiple of the kernels'

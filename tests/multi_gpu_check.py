@@ -111,6 +111,44 @@ def check_case(case, transport, rank, world):
     return ok
 
 
+def check_multigrid(transport, rank, world):
+    """Config 3 on a partition: CG preconditioned by the p-multigrid V-cycle (DG levels k = 4, 2, 1 on the same cells - the p-transfer is
+    cell-local on any partition; Chebyshev smoothers, CG + point Jacobi on the coarsest level, all with global dot products) must
+    take the iteration count of the single-partition solve and give its solution."""
+    from exadg_b200.laplace_operator import MultigridPreconditioner, multigrid_levels
+    bc = (1, 2, 1, 1, 1, 1)
+    kw = dict(degree=4, n_subdivisions=1, n_refinements=2, mapping_degree=3, deformation=0.15, frequency=2, boundary=bc, ip_factor=1.0)
+    levels = multigrid_levels("pMG", "Bisect", 4, 3)
+    data = exadg_b200.SolverData(200, 1e-20, 1e-10)
+    ref_mg = MultigridPreconditioner.hypercube(kw, "pMG")
+    ref = ref_mg.op
+    g = torch.Generator().manual_seed(7)
+    x_global = torch.rand(ref.n(), dtype=torch.float64, generator=g) * 2 - 1
+    b = ref.initialize_dof_vector()
+    ref.vmult(b, x_global.cuda())
+    x1 = ref.initialize_dof_vector()
+    n1 = exadg_b200.KrylovSolverCG(ref, ref_mg, data).solve(x1, b)
+    ops = []
+    for (h, k) in levels:
+        op = exadg_b200.LaplaceOperator.hypercube(**dict(kw, degree=k, n_refinements=h, rank=rank, world=world))
+        op.init_nccl(fresh_nccl_id(rank))
+        if transport == "p2p":
+            op.enable_p2p(dist)
+        ops.append(op)
+    mg = MultigridPreconditioner(ops)
+    fine = ops[-1]
+    n3 = 125
+    lo = (fine.n() // n3) * rank // world * n3
+    hi = lo + fine.local_size()
+    x2 = fine.initialize_dof_vector()
+    n2 = exadg_b200.KrylovSolverCG(fine, mg, data).solve(x2, b[lo:hi].clone())
+    err = torch.tensor([((x2 - x1[lo:hi]).norm() / x1.norm()).item()], device="cuda")
+    dist.all_reduce(err, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print("%s CG + pMG %s: iterations single partition %d, %d ranks %d; solution difference %.2e" % (transport, levels, n1, world, n2, err.item()), flush=True)
+    return n1 == n2 and err.item() < 1e-8
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -119,6 +157,8 @@ def main():
     for case in CASES:
         for transport in ("nccl", "p2p"):
             ok &= check_case(case, transport, rank, world)
+    for transport in ("nccl", "p2p"):
+        ok &= check_multigrid(transport, rank, world)
     dist.barrier()
     if rank == 0:
         print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL", flush=True)
