@@ -93,6 +93,11 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
   constexpr int B = CartCfg<N>::B, NT = B * N;
   constexpr int N2 = N * N, N3 = N2 * N;
   constexpr int PS = N2 | 1, CS = N * PS; // odd plane stride: conflict-free plane- and line-wise access
+  // n^2 a multiple of 16 (n = 4): the trace arrays [cell][n^2] would put every cell on the same banks (8-way conflicts: ncu of the 64^3 box had
+  // 19.0 M conflict wavefronts out of 36.8 M).  Their in-face index is XOR-swizzled with the low bits of the cell that READS the entry (HV / HG)
+  // or owns it (GN): the lanes of a warp - 8 cells x 4 planes - then cover all 16 eight-byte banks twice.
+  constexpr bool SWZ = (N2 % 16 == 0);
+  auto sw = [](int idx, int cell) { return SWZ ? (idx ^ (cell & 15)) : idx; };
   extern __shared__ __align__(128) double smem[];
   double * U = smem;                 // [B][CS]  src values, later the staging buffer of the result
   double * Tt = U + B * CS;          // [B][CS]  partial results
@@ -168,9 +173,11 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
           double g = 0.0;
 #pragma unroll
           for (int i = 0; i < N; ++i) g = fma(sp[q] ? T.fd[1][i] : T.fd[0][i], x[q][i], g);
-          HV[e * N2 + ab] = sp[q] ? x[q][N - 1] : x[q][0];
-          HG[e * N2 + ab] = g;
-          if (ab == 0) { const int2 h = hlS[e]; slotS[(h.x >> 3) * 6 + (h.x & 7)] = e; }
+          const int2 h = hlS[e];
+          const int abs_ = sw(ab, h.x >> 3); // swizzled with the reading cell
+          HV[e * N2 + abs_] = sp[q] ? x[q][N - 1] : x[q][0];
+          HG[e * N2 + abs_] = g;
+          if (ab == 0) slotS[(h.x >> 3) * 6 + (h.x & 7)] = e;
         }
       }
     }
@@ -198,8 +205,8 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
           const double x = (d == 0) ? u[l][m] : u[m][l];
           g0 = fma(T.fd[0][m], x, g0); g1 = fma(T.fd[1][m], x, g1);
         }
-        GN[(0 * B + lc) * N2 + s * N + l] = g0;
-        GN[(1 * B + lc) * N2 + s * N + l] = g1;
+        GN[(0 * B + lc) * N2 + sw(s * N + l, lc)] = g0;
+        GN[(1 * B + lc) * N2 + sw(s * N + l, lc)] = g1;
       }
     }
     __syncthreads();
@@ -217,9 +224,9 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
           if (inb) {
             const int endn = side ? 0 : N - 1; // neighbour's end node facing us
             vn = (d == 0) ? U[nbl * CS + s * PS + endn + N * l] : U[nbl * CS + s * PS + l + N * endn];
-            gn = GN[((side ^ 1) * B + nbl) * N2 + s * N + l];
+            gn = GN[((side ^ 1) * B + nbl) * N2 + sw(s * N + l, nbl)];
           } else {
-            vn = HV[slot * N2 + l + N * s]; gn = HG[slot * N2 + l + N * s];
+            vn = HV[slot * N2 + sw(l + N * s, lc)]; gn = HG[slot * N2 + sw(l + N * s, lc)];
           }
           const double tt = fma(hs, gn, T.tau_hat[d] * vn);
 #pragma unroll
@@ -255,18 +262,22 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
   constexpr bool REMAP_Z = (N != 4); // measured: n = 4 (cell stride 68 doubles) is faster with the plane map
   const int lz = REMAP_Z ? t % B : lc, sz = REMAP_Z ? t / B : s;
   const bool validz = (sz < N) && (lz < nvalid);
+  // n = 4 keeps the plane map (lane = 4 lz + sz); with the slice along y its addresses 68 lz + 4 sz fall on four banks (8-way conflicts), with
+  // the slice along x (the thread owns the lines (x = sz, y = i)) they are 68 lz + sz: the conflict-free pattern of the plane sweeps
+  constexpr bool ZSWAP = (N == 4);
+  auto zo = [sz](int i) { return ZSWAP ? sz + N * i : i + N * sz; }; // in-plane offset = in-face index of line i of this thread
   if (validz) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       double g0 = 0.0, g1 = 0.0;
 #pragma unroll
       for (int k = 0; k < N; ++k) {
-        const double x = U[lz * CS + k * PS + i + N * sz];
+        const double x = U[lz * CS + k * PS + zo(i)];
         u[i][k] = x; // reuse the plane registers: u[i][k] = value of line i at height k
         g0 = fma(T.fd[0][k], x, g0); g1 = fma(T.fd[1][k], x, g1);
       }
-      GN[(0 * B + lz) * N2 + sz * N + i] = g0;
-      GN[(1 * B + lz) * N2 + sz * N + i] = g1;
+      GN[(0 * B + lz) * N2 + sw(zo(i), lz)] = g0;
+      GN[(1 * B + lz) * N2 + sw(zo(i), lz)] = g1;
     }
   }
   __syncthreads(); // Tt planes and z traces visible
@@ -282,16 +293,16 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
     for (int i = 0; i < N; ++i) {
       double w[N];
 #pragma unroll
-      for (int k = 0; k < N; ++k) w[k] = Tt[lz * CS + k * PS + i + N * sz];
+      for (int k = 0; k < N; ++k) w[k] = Tt[lz * CS + k * PS + zo(i)];
 #pragma unroll
       for (int side = 0; side < 2; ++side) {
         double vn, gn;
         if (inb[side]) {
           const int endn = side ? 0 : N - 1;
-          vn = U[nbl[side] * CS + endn * PS + i + N * sz];
-          gn = GN[((side ^ 1) * B + nbl[side]) * N2 + sz * N + i];
+          vn = U[nbl[side] * CS + endn * PS + zo(i)];
+          gn = GN[((side ^ 1) * B + nbl[side]) * N2 + sw(zo(i), nbl[side])];
         } else {
-          vn = HV[slot[side] * N2 + i + N * sz]; gn = HG[slot[side] * N2 + i + N * sz];
+          vn = HV[slot[side] * N2 + sw(zo(i), lz)]; gn = HG[slot[side] * N2 + sw(zo(i), lz)];
         }
         const double tt = fma(side ? 0.5 : -0.5, gn, T.tau_hat[2] * vn);
 #pragma unroll
@@ -307,7 +318,7 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
         double y = 0.0;
 #pragma unroll
         for (int c = 0; c < N; ++c) y = fma(T.M[r * N + c], w[c], y);
-        Tt[lz * CS + r * PS + i + N * sz] = y;
+        Tt[lz * CS + r * PS + zo(i)] = y;
       }
     }
   }
@@ -366,10 +377,13 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
 // =====================================================================================================
 // BB cells per CTA: 16 (two octets) or 8 (one octet: half the shared memory and threads per CTA, so two to four CTAs share an SM and
 // the load / trace / sweep / store phases of different batches overlap, at the price of 3.0 instead of 2.5 out-of-batch faces per cell)
-template<int N, int BB> struct LineCfg { static constexpr int B = BB; static constexpr int NT = B * N * N; static constexpr int RS = N | 1; static constexpr int CS = RS * N * N; };
+// MINB: resident CTAs the register budget is tuned for.  n = 6 with 16 cells: 576 threads x 92 registers left ONE CTA per SM (ncu: occupancy limited by
+// registers, 18 warps, load / trace / sweep / store phases strictly serial); 56 registers admit two (shared memory: 2 x 98 KB)
+template<int N, int BB> struct LineCfg { static constexpr int B = BB; static constexpr int NT = B * N * N; static constexpr int RS = N | 1; static constexpr int CS = RS * N * N;
+                                         static constexpr int MINB = (N == 6 && BB == 16) ? 2 : 1; };
 
 template<int N, int BB>
-__global__ void __launch_bounds__(LineCfg<N, BB>::NT, 1) vmult_cartesian_line_kernel(const __grid_constant__ CartTables<N> T, const CartArgs A)
+__global__ void __launch_bounds__(LineCfg<N, BB>::NT, LineCfg<N, BB>::MINB) vmult_cartesian_line_kernel(const __grid_constant__ CartTables<N> T, const CartArgs A)
 {
   constexpr int B = LineCfg<N, BB>::B, NT = LineCfg<N, BB>::NT, RS = LineCfg<N, BB>::RS, CS = LineCfg<N, BB>::CS;
   constexpr int N2 = N * N, N3 = N2 * N;
@@ -409,7 +423,7 @@ __global__ void __launch_bounds__(LineCfg<N, BB>::NT, 1) vmult_cartesian_line_ke
   __syncthreads();
   // ---- traces of the out-of-batch neighbours: one line per item, UNR items x n loads in flight per thread (register budget) ----
   {
-    constexpr int UNR = (N >= 8) ? 2 : (N == 7 ? 3 : 4);
+    constexpr int UNR = (N >= 8 || LineCfg<N, BB>::MINB > 1) ? 2 : (N == 7 ? 3 : 4);
     for (int it0 = t; it0 < cnt * N2; it0 += NT * UNR) {
       double x[UNR][N]; int sp[UNR];
 #pragma unroll
