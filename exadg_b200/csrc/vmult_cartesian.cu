@@ -378,9 +378,13 @@ __global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_car
 // BB cells per CTA: 16 (two octets) or 8 (one octet: half the shared memory and threads per CTA, so two to four CTAs share an SM and
 // the load / trace / sweep / store phases of different batches overlap, at the price of 3.0 instead of 2.5 out-of-batch faces per cell)
 // MINB: resident CTAs the register budget is tuned for.  n = 6 with 16 cells: 576 threads x 92 registers left ONE CTA per SM (ncu: occupancy limited by
-// registers, 18 warps, load / trace / sweep / store phases strictly serial); 56 registers admit two (shared memory: 2 x 98 KB)
+// registers, 18 warps, load / trace / sweep / store phases strictly serial); 56 registers admit two (shared memory: 2 x 98 KB).  8-cell batches:
+// 4 / 3 / 2 CTAs for n = 6 / 7 / 8 (56 / 48 / 60 registers).
+// Shared-memory layouts with fewer bank conflicts in the y / z sweeps (enumerated by scripts/line_layout_search.py: n = 8 rows of 8 rotated by y,
+// planes of 68: no conflicts at all; n = 7 planes of 51, lanes along the second coordinate) were measured SLOWER (scripts/r02_shot48.sh: k = 6
+// 84.4 -> 76.8, k = 7 89.3 -> 84.8 GDoF/s): the per-node address arithmetic costs more than the 1.3 - 1.5 x wavefronts of those sweeps.
 template<int N, int BB> struct LineCfg { static constexpr int B = BB; static constexpr int NT = B * N * N; static constexpr int RS = N | 1; static constexpr int CS = RS * N * N;
-                                         static constexpr int MINB = (N == 6 && BB == 16) ? 2 : 1; };
+                                         static constexpr int MINB = (BB == 16) ? (N == 6 ? 2 : 1) : (N == 6 ? 4 : (N == 7 ? 3 : 2)); };
 
 template<int N, int BB>
 __global__ void __launch_bounds__(LineCfg<N, BB>::NT, LineCfg<N, BB>::MINB) vmult_cartesian_line_kernel(const __grid_constant__ CartTables<N> T, const CartArgs A)
@@ -1099,7 +1103,9 @@ void store_tables(CartPlan & P, const DeviceOperator & op)
 }
 
 static size_t plan_create(DeviceOperator & op, const HostMesh & mesh, bool allow_pipe);
-static int line_batch_default(int n) { (void)n; return 16; }
+// measured (scripts/r02_shot46.sh, register budgets of LineCfg::MINB): 8-cell batches 91.5 / 84.4 / 89.3 GDoF/s at k = 5 / 6 / 7 against 84.6 / 62.6 / 71.8
+// with 16-cell batches (4 / 3 / 2 resident CTAs instead of 2 / 1 / 1)
+static int line_batch_default(int n) { (void)n; return 8; }
 
 // builds the batch plan (halo lists, interior/boundary batches, tables); returns the dynamic shared
 // memory per CTA, or 0 if the batch does not fit (caller falls back to the general kernel)
