@@ -87,10 +87,11 @@ __device__ __forceinline__ void tma_store_1d(void * gdst, const void * smem_src,
 // cells per batch = consecutive cells of the Morton curve: 4x4x4 bricks (1.5 out-of-batch faces per cell) while 2 CTAs of B n threads fit an SM
 template<int N> struct CartCfg { static constexpr int B = (N >= 6) ? 16 : ((N >= 5) ? 32 : 64); };
 
-template<int N>
-__global__ void __launch_bounds__(CartCfg<N>::B * N, (N == 5) ? 2 : 1) vmult_cartesian_kernel(const __grid_constant__ CartTables<N> T, const CartArgs A)
+// BB: cells per batch (default CartCfg; n = 4 also with 32-cell batches: EXADG_B200_PLANE_B=32, three CTAs per SM instead of two)
+template<int N, int BB = CartCfg<N>::B>
+__global__ void __launch_bounds__(BB * N, (N == 5) ? 2 : ((N == 4 && BB == 32) ? 3 : 1)) vmult_cartesian_kernel(const __grid_constant__ CartTables<N> T, const CartArgs A)
 {
-  constexpr int B = CartCfg<N>::B, NT = B * N;
+  constexpr int B = BB, NT = B * N;
   constexpr int N2 = N * N, N3 = N2 * N;
   constexpr int PS = N2 | 1, CS = N * PS; // odd plane stride: conflict-free plane- and line-wise access
   // n^2 a multiple of 16 (n = 4): the trace arrays [cell][n^2] would put every cell on the same banks (8-way conflicts: ncu of the 64^3 box had
@@ -1027,6 +1028,8 @@ void launch_n(const DeviceOperator & op, const CartPlan & plan, double * dst, co
   const CartTables<N> & T = *reinterpret_cast<const CartTables<N> *>(plan.tables.data());
   if (first_use_on_device((const void *)vmult_cartesian_kernel<N>))
     CUDA_CHECK(cudaFuncSetAttribute(vmult_cartesian_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+  if (N == 4 && first_use_on_device((const void *)vmult_cartesian_kernel<4, 32>))
+    CUDA_CHECK(cudaFuncSetAttribute(vmult_cartesian_kernel<4, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
   CartArgs A;
   A.nb = op.nb; A.halo = plan.d_halo; A.halo_cnt = plan.d_cnt; A.src = src; A.ghost = op.ghost; A.dst = dst;
   A.n_owned = op.n_owned; A.H = plan.H; A.add = add ? 1 : 0;
@@ -1034,7 +1037,8 @@ void launch_n(const DeviceOperator & op, const CartPlan & plan, double * dst, co
   A.n_items = which == 0 ? plan.n_batches : (which == 1 ? plan.n_interior : plan.n_boundary);
   if (list) { A.batches = list; A.n_items = n_list; }
   if (A.n_items == 0) return;
-  vmult_cartesian_kernel<N><<<A.n_items, B * N, plan.smem, stream>>>(T, A);
+  if (N == 4 && plan.B == 32) vmult_cartesian_kernel<4, 32><<<A.n_items, 32 * 4, plan.smem, stream>>>(*reinterpret_cast<const CartTables<4> *>(plan.tables.data()), A);
+  else vmult_cartesian_kernel<N><<<A.n_items, B * N, plan.smem, stream>>>(T, A);
   CUDA_CHECK(cudaGetLastError());
 }
 template<int N, int BB>
@@ -1118,6 +1122,7 @@ static size_t plan_create(DeviceOperator & op, const HostMesh & mesh, bool allow
   P.n = op.n;
   const int N = op.n;
   P.B = (N >= 6) ? 16 : ((N >= 5) ? 32 : 64);
+  if (N == 4) { const char * e = getenv("EXADG_B200_PLANE_B"); if (e && std::atoi(e) == 32) P.B = 32; }
   if (N >= 6 && !getenv("EXADG_B200_NO_LINE")) { // line kernel: 8 or 16 cells per CTA (EXADG_B200_LINE_B; default per degree from the measurements)
     const char * e = getenv("EXADG_B200_LINE_B");
     const int want = e ? std::atoi(e) : line_batch_default(N);
