@@ -87,7 +87,8 @@ __device__ __forceinline__ void tma_store_1d(void * gdst, const void * smem_src,
 // cells per batch = consecutive cells of the Morton curve: 4x4x4 bricks (1.5 out-of-batch faces per cell) while 2 CTAs of B n threads fit an SM
 template<int N> struct CartCfg { static constexpr int B = (N >= 6) ? 16 : ((N >= 5) ? 32 : 64); };
 
-// BB: cells per batch (default CartCfg; n = 4 also with 32-cell batches: EXADG_B200_PLANE_B=32, three CTAs per SM instead of two)
+// BB: cells per batch (default CartCfg; n = 4 also with 32-cell batches: measurement switch EXADG_B200_PLANE_B=32, three CTAs per SM instead of two but
+// 2.0 instead of 1.5 out-of-batch faces per cell - measured slower, 91.8 against 99.8 GDoF/s, scripts/r02_shot50.sh)
 template<int N, int BB = CartCfg<N>::B>
 __global__ void __launch_bounds__(BB * N, (N == 5) ? 2 : ((N == 4 && BB == 32) ? 3 : 1)) vmult_cartesian_kernel(const __grid_constant__ CartTables<N> T, const CartArgs A)
 {
