@@ -23,7 +23,9 @@ P6 = (0,) * 6
 # (4, 1, 3), (4, 1, 4), (4, 3, 3): octet-aligned partitions (the warp-specialised k=4 kernel applies on every rank);
 # (4, 5, 0), (5, 3, 0), (2, 5, 0): partitions that end inside a cell batch (ghost indices directly follow a ragged last batch)
 CASES = [(4, 1, 3, 0.0, P6), (4, 1, 4, 0.0, P6), (4, 3, 3, 0.0, P6), (4, 5, 0, 0.0, P6), (5, 3, 0, 0.0, P6), (2, 5, 0, 0.0, P6), (4, 3, 2, 0.0, P6), (3, 1, 3, 0.1, P6),
-         (2, 2, 2, 0.15, (1, 2, 1, 1, 1, 1)), (5, 1, 2, 0.0, P6)]
+         (2, 2, 2, 0.15, (1, 2, 1, 1, 1, 1)), (5, 1, 2, 0.0, P6),
+         # k=3 plane kernel with the swizzled trace arrays and k=6 / k=7 line kernels with 8-cell batches on a partition (ghost reads in the trace phase)
+         (3, 1, 3, 0.0, P6), (6, 1, 2, 0.0, P6), (7, 1, 2, 0.0, P6)]
 
 
 def fresh_nccl_id(rank):
