@@ -133,6 +133,10 @@ struct exadg_b200_operator
   // uniform box with Dirichlet / Neumann faces: batches of cells that see the interior penalty on all their faces run the affine fast
   // kernel, the two cell layers next to the boundary (and the batches they share) the general kernel
   bool hybrid = false; int32_t * d_hyb_batches = nullptr, * d_hyb_cells = nullptr; int64_t n_hyb_batches = 0, n_hyb_cells = 0;
+  // Helmholtz / viscous operator on a uniform periodic box (the Taylor-Green setup): vmult on the affine fast kernels.  Every block
+  // (cell, component) of the vector is a "cell" of a virtual mesh whose neighbours are the same component of the neighbour cells;
+  // dev_helm holds that mesh's batch plan.  The diagonal and everything else stay with dev (general kernel).
+  bool helm_fast = false; DeviceOperator dev_helm;
   // peer-memory halo (NVLink): one region [ghost A | ghost B | flags[world]] mapped by all peers
   bool p2p = false; char * p2p_region = nullptr; size_t p2p_ghost_bytes = 0; long long p2p_epoch = 0;
   unsigned long long * d_put_done = nullptr; long long put_seq = 0; int put_grid = 0; int * d_work_counter = nullptr; // ticket counters of the in-launch export (GhostSync)
@@ -270,6 +274,30 @@ void finish_setup(exadg_b200_operator * op, double ip_factor, bool force_general
       } else cartesian_plan_destroy(D);
     }
   }
+  if (D.helmholtz && M.n_owned > 0 && M.cartesian_uniform && M.all_interior() && !force_general && M.world <= 1 && M.n_ghost == 0 && cartesian_supported(D.n)
+      && !getenv("EXADG_B200_NO_HELMHOLTZ_FAST")) {
+    const int nc = D.n_components;
+    HostMesh V;
+    V.n_owned = M.n_owned * nc; V.n_global_cells = V.n_owned; V.cartesian_uniform = true; V.world = 1;
+    for (int e = 0; e < 3; ++e) V.h[e] = M.h[e];
+    V.nb.resize((size_t)V.n_owned * 6);
+    for (int64_t c = 0; c < M.n_owned; ++c)
+      for (int comp = 0; comp < nc; ++comp)
+        for (int f = 0; f < 6; ++f) V.nb[((size_t)c * nc + comp) * 6 + f] = M.nb[c * 6 + f] * nc + comp;
+    DeviceOperator & H = op->dev_helm;
+    H = DeviceOperator();
+    H.degree = D.degree; H.n = D.n; H.n_owned = V.n_owned; H.n_global_dofs = D.n_global_dofs;
+    H.helmholtz = true; H.n_components = nc; H.mass_coeff = D.mass_coeff; H.laplace_coeff = D.laplace_coeff;
+    for (int e = 0; e < 3; ++e) H.h[e] = M.h[e];
+    double tk = 0.0;
+    for (int e = 0; e < 3; ++e) tk += 1.0 / M.h[e];
+    H.tau_hat = tk * ip_factor * (D.degree + 1.0) * (D.degree + 1.0);
+    H.cartesian = true;
+    CUDA_CHECK(cudaMalloc(&H.nb, V.nb.size() * sizeof(int32_t)));
+    CUDA_CHECK(cudaMemcpy(H.nb, V.nb.data(), V.nb.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (cartesian_plan_create(H, V) != 0) op->helm_fast = true;
+    else { cudaFree(H.nb); H.nb = nullptr; }
+  }
   CUDA_CHECK(cudaStreamCreateWithFlags(&op->stream, cudaStreamNonBlocking));
   {
     // the halo exchange must not queue behind the interior-cell kernel: highest priority for its stream
@@ -308,7 +336,8 @@ void finish_setup(exadg_b200_operator * op, double ip_factor, bool force_general
 void launch_vmult(exadg_b200_operator * op, double * dst, const double * src, bool add, int which, cudaStream_t stream = nullptr)
 {
   if (!stream) stream = op->stream;
-  if (op->dev.cartesian) launch_vmult_cartesian_part(op->dev, dst, src, add, which, stream);
+  if (op->helm_fast && which == 0) launch_vmult_cartesian_part(op->dev_helm, dst, src, add, 0, stream);
+  else if (op->dev.cartesian) launch_vmult_cartesian_part(op->dev, dst, src, add, which, stream);
   else if (op->hybrid && which == 0) {
     launch_vmult_cartesian_list(op->dev, dst, src, add, op->d_hyb_batches, (int)op->n_hyb_batches, stream);
     if (op->n_hyb_cells > 0) { launch_vmult_general(op->dev, dst, src, add, op->d_hyb_cells, op->n_hyb_cells, stream); op->launches++; }
@@ -724,7 +753,7 @@ int exadg_b200_set_scaling_factor_mass(exadg_b200_operator * op, double scaling_
   return guarded([&]() {
     if (!op) throw std::invalid_argument("null operator");
     if (!op->dev.helmholtz) throw std::runtime_error("exadg_b200_set_scaling_factor_mass: not a Helmholtz operator (create it with exadg_b200_create_*_helmholtz)");
-    op->dev.mass_coeff = scaling_factor_mass;
+    op->dev.mass_coeff = scaling_factor_mass; op->dev_helm.mass_coeff = scaling_factor_mass;
     return EXADG_B200_OK;
   });
 }
@@ -745,6 +774,7 @@ int exadg_b200_destroy(exadg_b200_operator * op)
   cudaDeviceSynchronize();
   DeviceOperator & D = op->dev;
   cartesian_plan_destroy(D);
+  cartesian_plan_destroy(op->dev_helm); cudaFree(op->dev_helm.nb);
   if (op->p2p) D.ghost = op->ghost_alloc;
   cudaFree(D.cellJxW); cudaFree(op->d_hyb_batches); cudaFree(op->d_hyb_cells);
   cudaFree(D.nb); cudaFree(D.face_id); cudaFree(D.face_info); cudaFree(D.cellG); cudaFree(D.faceG); cudaFree(D.tau_f); cudaFree(D.tau_cell); cudaFree(D.ghost);

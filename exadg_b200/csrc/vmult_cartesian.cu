@@ -50,6 +50,7 @@ struct CartArgs
   const int32_t * batches;   // optional list of batch ids
   const double * src; const double * ghost; double * dst;
   int64_t n_owned; int n_items; int H; int add;
+  double mass; // Helmholtz / viscous operator on a uniform box: scaling_factor_mass x cell volume, added before the mass sweeps (0: Laplace)
 };
 
 // ---- TMA (bulk async copy) + mbarrier helpers, sm_90+/sm_100a PTX ----
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(BB * N, (N == 5) ? 2 : ((N == 4 && BB == 32) ?
 #pragma unroll
     for (int j = 0; j < N; ++j)
 #pragma unroll
-      for (int i = 0; i < N; ++i) { u[j][i] = U[lc * CS + s * PS + i + N * j]; acc[j][i] = 0.0; }
+      for (int i = 0; i < N; ++i) { u[j][i] = U[lc * CS + s * PS + i + N * j]; acc[j][i] = A.mass * u[j][i]; }
   }
 
   // ---- x and y sweeps on the register plane z = s ----
@@ -484,7 +485,7 @@ __global__ void __launch_bounds__(LineCfg<N, BB>::NT, LineCfg<N, BB>::MINB) vmul
       GN[(1 * B + c) * N2 + ab] = g1;
 #pragma unroll
       for (int r = 0; r < N; ++r) {
-        double v = 0.0;
+        double v = (d == 0) ? A.mass * x[r] : 0.0; // mass term of the Helmholtz operator (in front of the mass sweeps like the rest)
 #pragma unroll
         for (int m = 0; m < N; ++m) v = fma(T.G[d][r * N + m], x[m], v);
         y[r] = v;
@@ -990,7 +991,7 @@ CartTables<N> make_cart_tables(const DeviceOperator & op)
   CartTables<N> T;
   for (int d = 0; d < 3; ++d) {
     const int e = (d + 1) % 3, f = (d + 2) % 3;
-    const real_t cd = (real_t)op.h[e] * op.h[f] / op.h[d];
+    const real_t cd = (real_t)op.laplace_coeff * op.h[e] * op.h[f] / op.h[d]; // laplace_coeff: viscosity of the Helmholtz operator (1 otherwise)
     const real_t tau_hat = (real_t)op.tau_hat * op.h[d];
     T.tau_hat[d] = (double)tau_hat;
     // own-side 1-D operator K + sum_s [ -1/2 sigma (d e^T + e d^T) + tau_hat e e^T ]
@@ -1033,7 +1034,7 @@ void launch_n(const DeviceOperator & op, const CartPlan & plan, double * dst, co
     CUDA_CHECK(cudaFuncSetAttribute(vmult_cartesian_kernel<4, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
   CartArgs A;
   A.nb = op.nb; A.halo = plan.d_halo; A.halo_cnt = plan.d_cnt; A.src = src; A.ghost = op.ghost; A.dst = dst;
-  A.n_owned = op.n_owned; A.H = plan.H; A.add = add ? 1 : 0;
+  A.n_owned = op.n_owned; A.H = plan.H; A.add = add ? 1 : 0; A.mass = op.helmholtz ? op.mass_coeff * op.h[0] * op.h[1] * op.h[2] : 0.0;
   A.batches = which == 0 ? nullptr : (which == 1 ? plan.d_interior : plan.d_boundary);
   A.n_items = which == 0 ? plan.n_batches : (which == 1 ? plan.n_interior : plan.n_boundary);
   if (list) { A.batches = list; A.n_items = n_list; }
@@ -1051,7 +1052,7 @@ void launch_line_b(const DeviceOperator & op, const CartPlan & plan, double * ds
     CUDA_CHECK(cudaFuncSetAttribute(vmult_cartesian_line_kernel<N, BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
   CartArgs A;
   A.nb = op.nb; A.halo = plan.d_halo; A.halo_cnt = plan.d_cnt; A.src = src; A.ghost = op.ghost; A.dst = dst;
-  A.n_owned = op.n_owned; A.H = plan.H; A.add = add ? 1 : 0;
+  A.n_owned = op.n_owned; A.H = plan.H; A.add = add ? 1 : 0; A.mass = op.helmholtz ? op.mass_coeff * op.h[0] * op.h[1] * op.h[2] : 0.0;
   A.batches = which == 0 ? nullptr : (which == 1 ? plan.d_interior : plan.d_boundary);
   A.n_items = which == 0 ? plan.n_batches : (which == 1 ? plan.n_interior : plan.n_boundary);
   if (list) { A.batches = list; A.n_items = n_list; }
@@ -1129,7 +1130,7 @@ static size_t plan_create(DeviceOperator & op, const HostMesh & mesh, bool allow
     const int want = e ? std::atoi(e) : line_batch_default(N);
     P.B = (want == 8) ? 8 : 16;
   }
-  P.pipe = allow_pipe && (N == 5) && !getenv("EXADG_B200_NO_PIPE"); // n = 3 measured slower than the 64-cell kernel (0.99 vs 0.86 ms) // pipelined 4-warp kernel (EXADG_B200_NO_PIPE=1: the 5-warp kernel)
+  P.pipe = allow_pipe && (N == 5) && !op.helmholtz && !getenv("EXADG_B200_NO_PIPE"); // (the mass term lives in the plane and line kernels only) // n = 3 measured slower than the 64-cell kernel (0.99 vs 0.86 ms) // pipelined 4-warp kernel (EXADG_B200_NO_PIPE=1: the 5-warp kernel)
   if (P.pipe) P.B = (N == 3) ? PipeCfg<3>::B : PipeCfg<5>::B;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&P.n_sm, cudaDevAttrMultiProcessorCount, dev); if (P.n_sm < 1) P.n_sm = 148; }
   P.n_batches = (int)((mesh.n_owned + P.B - 1) / P.B);
