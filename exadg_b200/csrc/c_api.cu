@@ -229,7 +229,6 @@ void finish_setup(exadg_b200_operator * op, double ip_factor, bool force_general
   D.n_global_dofs = M.n_global_cells * n3 * D.n_components;
   op->n_local = M.n_owned * n3 * D.n_components;
   for (int e = 0; e < 3; ++e) D.h[e] = M.h[e];
-  if (D.helmholtz && M.world > 1) throw std::runtime_error("the Helmholtz / viscous operator is not partitioned yet (world must be 1)");
   // the mass term and the component blocks live in the general kernel only
   D.cartesian = M.n_owned > 0 && M.cartesian_uniform && M.all_interior() && !force_general && !D.helmholtz && cartesian_supported(D.n);
   if (D.cartesian) {
@@ -316,7 +315,7 @@ void finish_setup(exadg_b200_operator * op, double ip_factor, bool force_general
       int32_t * l = nullptr; double * b = nullptr;
       CUDA_CHECK(cudaMalloc(&l, p.send_cells.size() * sizeof(int32_t)));
       CUDA_CHECK(cudaMemcpy(l, p.send_cells.data(), p.send_cells.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-      CUDA_CHECK(cudaMalloc(&b, p.send_cells.size() * n3 * sizeof(double)));
+      CUDA_CHECK(cudaMalloc(&b, p.send_cells.size() * n3 * D.n_components * sizeof(double))); // whole cell blocks: all components
       op->d_send_lists.push_back(l); op->d_send_bufs.push_back(b);
     }
     std::vector<int32_t> interior, boundary;
@@ -324,6 +323,10 @@ void finish_setup(exadg_b200_operator * op, double ip_factor, bool force_general
       bool touches = false;
       for (int f = 0; f < 6; ++f) touches |= (M.nb[c * 6 + f] >= M.n_owned);
       (touches ? boundary : interior).push_back((int32_t)c);
+    }
+    if (D.n_components > 1) { // the general kernel's items are (cell, component) blocks
+      auto blocks = [&](std::vector<int32_t> & v) { std::vector<int32_t> b; b.reserve(v.size() * D.n_components); for (int32_t c : v) for (int k = 0; k < D.n_components; ++k) b.push_back(c * D.n_components + k); v.swap(b); };
+      blocks(interior); blocks(boundary);
     }
     op->n_interior = (int64_t)interior.size(); op->n_boundary = (int64_t)boundary.size();
     if (!interior.empty()) { CUDA_CHECK(cudaMalloc(&op->d_interior, interior.size() * 4)); CUDA_CHECK(cudaMemcpy(op->d_interior, interior.data(), interior.size() * 4, cudaMemcpyHostToDevice)); }
@@ -361,7 +364,7 @@ void apply(exadg_b200_operator * op, double * dst, const double * src, bool add,
   if (dst == src) throw std::invalid_argument("dst and src must not alias");
   HostMesh & M = op->mesh;
   if (M.world <= 1 || M.peers.empty()) { if (!boundary_only) launch_vmult(op, dst, src, add, 0); return; }
-  const int n3 = op->dev.n * op->dev.n * op->dev.n;
+  const int n3 = op->dev.n * op->dev.n * op->dev.n * op->dev.n_components; // doubles per cell block (all components of a cell travel together)
   if (op->p2p) {
     const long long epoch = ++op->p2p_epoch;
     const int buf = (int)(epoch & 1);
@@ -732,7 +735,6 @@ static int create_from_mesh(const exadg_b200_mesh_desc * desc, const exadg_b200_
     M.cartesian_uniform = detect_cartesian_uniform(M, h);
     if (M.cartesian_uniform) for (int e = 0; e < 3; ++e) M.h[e] = h[e];
     M.build_faces();
-    if (op->dev.helmholtz && M.n_ghost > 0) throw std::runtime_error("the Helmholtz / viscous operator is not partitioned yet (n_cells_ghost must be 0)");
     finish_setup(op.get(), desc->ip_factor, desc->force_general != 0);
     *out = op.release();
     return EXADG_B200_OK;
@@ -991,6 +993,7 @@ int exadg_b200_vmult_host_pipelined(exadg_b200_operator * op, double * dst_host,
     if (!op || !dst_host || !src_host) throw std::invalid_argument("null argument");
     HostMesh & M = op->mesh;
     const bool partitioned = M.world > 1 || M.n_ghost > 0;
+    if (op->dev.helmholtz) { g_last_error = "the pipelined host-buffer vmult is implemented for the scalar Laplace operator (use exadg_b200_vmult_host)"; return (int)EXADG_B200_ERR_UNSUPPORTED; }
     if (partitioned && M.peers.empty() && M.n_ghost > 0) { g_last_error = "the pipelined host-buffer vmult cannot import ghost cells the caller owns"; return (int)EXADG_B200_ERR_UNSUPPORTED; }
     {
       static const int env_mode = []() { const char * e = getenv("EXADG_B200_HOST_PIPELINE"); return !e ? 0 : (!strcmp(e, "staged") ? 1 : (!strcmp(e, "direct") ? 2 : 0)); }();
@@ -1535,7 +1538,7 @@ int exadg_b200_p2p_export(exadg_b200_operator * op, char * handle64, int64_t * r
     if (!op || !handle64 || !recv_begin_by_rank) throw std::invalid_argument("null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     const HostMesh & M = op->mesh;
-    const size_t n3 = (size_t)op->dev.n * op->dev.n * op->dev.n;
+    const size_t n3 = (size_t)op->dev.n * op->dev.n * op->dev.n * op->dev.n_components;
     if (!op->p2p_region) {
       op->p2p_ghost_bytes = ((size_t)std::max<int64_t>(M.n_ghost, 1) * n3 * sizeof(double) + 255) / 256 * 256;
       const size_t bytes = 2 * op->p2p_ghost_bytes + (size_t)M.world * sizeof(long long);
@@ -1614,7 +1617,7 @@ int exadg_b200_halo_pack(exadg_b200_operator * op, int i, const double * src, do
 {
   return guarded([&]() {
     if (!op || i < 0 || i >= (int)op->mesh.peers.size()) throw std::invalid_argument("bad peer index");
-    const int n3 = op->dev.n * op->dev.n * op->dev.n;
+    const int n3 = op->dev.n * op->dev.n * op->dev.n * op->dev.n_components;
     const int64_t nc = (int64_t)op->mesh.peers[i].send_cells.size();
     pack_cells_kernel<<<(unsigned)std::min<int64_t>((nc * n3 + 255) / 256, 148 * 8), 256, 0, op->stream>>>(src, op->d_send_lists[i], nc, n3, send_buffer);
     op->launches++;

@@ -202,7 +202,7 @@ void setup_geometry(DeviceOperator & op, const HostMesh & mesh, double ip_factor
   op.nb = to_device(mesh.nb);
   op.face_id = to_device(mesh.face_id);
   op.face_info = to_device(mesh.face_info);
-  if (mesh.n_ghost > 0) CUDA_CHECK(cudaMalloc(&op.ghost, (size_t)mesh.n_ghost * n * n * n * sizeof(double)));
+  if (mesh.n_ghost > 0) CUDA_CHECK(cudaMalloc(&op.ghost, (size_t)mesh.n_ghost * n * n * n * op.n_components * sizeof(double))); // [ghost cell][component][n^3]
 
   if (op.cartesian) {
     // uniform box: tau_K = sum_d 1/h_d (all faces weighted 1/2), same for every cell

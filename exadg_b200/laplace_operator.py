@@ -74,12 +74,13 @@ class LaplaceOperator:
 
     @classmethod
     def hypercube_helmholtz(cls, degree, n_components=3, scaling_factor_mass=1.0, viscosity=1.0, n_subdivisions=1, n_refinements=0, mapping_degree=1,
-                            deformation=0.0, frequency=2, boundary=(0,) * 6, ip_factor=1.0):
+                            deformation=0.0, frequency=2, boundary=(0,) * 6, ip_factor=1.0, rank=0, world=1):
         """IncNS::MomentumOperator with the viscous term in Laplace formulation and constant viscosity (momentum_operator.cpp:376-480,
-        viscous_operator.h:365-560): scaling_factor_mass * M + viscosity * A_SIPG on every component."""
+        viscous_operator.h:365-560): scaling_factor_mass * M + viscosity * A_SIPG on every component.  rank / world: partition
+        of the grid as for LaplaceOperator.hypercube (whole cell blocks - all components - travel in the ghost import)."""
         from . import HelmholtzData
         _torch()
-        d = _desc(degree, n_subdivisions, n_refinements, mapping_degree, deformation, frequency, boundary, ip_factor, 0, 1, False)
+        d = _desc(degree, n_subdivisions, n_refinements, mapping_degree, deformation, frequency, boundary, ip_factor, rank, world, False)
         hd = HelmholtzData(n_components, scaling_factor_mass, viscosity)
         h = C.c_void_p()
         _check(_lib().exadg_b200_create_hypercube_helmholtz(C.byref(d), C.byref(hd), C.byref(h)))

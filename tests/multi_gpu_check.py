@@ -113,6 +113,48 @@ def check_case(case, transport, rank, world):
     return ok
 
 
+def check_helmholtz(transport, rank, world):
+    """Config 4 on a partition: the viscous / Helmholtz operator (three velocity components; whole cell blocks travel in the ghost import) must
+    match the single-partition operator - on the curved walled box (general kernel on both sides) and on the uniform periodic box, where the
+    single-partition operator runs the affine fast kernels and the partition the general kernel - and CG must take the same number of
+    iterations."""
+    ok = True
+    for (k, n_sub, refine, deformation, bc) in [(3, 1, 2, 0.1, (1, 1, 1, 1, 2, 2)), (2, 3, 1, 0.0, P6), (5, 1, 2, 0.0, P6)]:
+        args = (k, 3, 40.0, 0.05, n_sub, refine, 1, deformation, 2, bc)
+        ref = exadg_b200.LaplaceOperator.hypercube_helmholtz(*args)
+        op = exadg_b200.LaplaceOperator.hypercube_helmholtz(*args, rank=rank, world=world)
+        op.init_nccl(fresh_nccl_id(rank))
+        if transport == "p2p":
+            op.enable_p2p(dist)
+        blk = 3 * (k + 1) ** 3
+        g = torch.Generator().manual_seed(11)
+        x_global = torch.rand(ref.local_size(), dtype=torch.float64, generator=g) * 2 - 1
+        lo = (ref.local_size() // blk) * rank // world * blk
+        hi = lo + op.local_size()
+        y_ref = ref.initialize_dof_vector()
+        ref.vmult(y_ref, x_global.cuda())
+        dst = op.initialize_dof_vector()
+        worst = 0.0
+        for rep in range(3):
+            op.vmult(dst, (x_global[lo:hi] * (rep + 1)).cuda())
+            worst = max(worst, ((dst - (rep + 1) * y_ref[lo:hi]).norm() / ((rep + 1) * y_ref.norm())).item())
+        d_ref, d = ref.initialize_dof_vector(), op.initialize_dof_vector()
+        ref.calculate_diagonal(d_ref); op.calculate_diagonal(d)
+        worst = max(worst, ((d - d_ref[lo:hi]).norm() / d_ref.norm()).item())
+        data = exadg_b200.SolverData(500, 1e-20, 1e-9)
+        x1, x2 = ref.initialize_dof_vector(), op.initialize_dof_vector()
+        n1 = exadg_b200.KrylovSolverCG(ref, exadg_b200.JacobiPreconditioner(ref), data).solve(x1, y_ref)
+        n2 = exadg_b200.KrylovSolverCG(op, exadg_b200.JacobiPreconditioner(op), data).solve(x2, y_ref[lo:hi].clone())
+        worst_t = torch.tensor([worst, ((x2 - x1[lo:hi]).norm() / x1.norm()).item()], device="cuda")
+        dist.all_reduce(worst_t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print("%s Helmholtz k=%d cells=%d^3 deformation=%g: vmult / diagonal rel err %.2e, CG its %d / %d, solution diff %.2e"
+                  % (transport, k, n_sub << refine, deformation, worst_t[0].item(), n1, n2, worst_t[1].item()), flush=True)
+        ok &= worst_t[0].item() < 1e-12 and n1 == n2 and worst_t[1].item() < 1e-7
+        del op, ref
+    return ok
+
+
 def check_multigrid(transport, rank, world):
     """Config 3 on a partition: CG preconditioned by the p-multigrid V-cycle (DG levels k = 4, 2, 1 on the same cells - the p-transfer is
     cell-local on any partition; Chebyshev smoothers, CG + point Jacobi on the coarsest level, all with global dot products) must
@@ -161,6 +203,7 @@ def main():
             ok &= check_case(case, transport, rank, world)
     for transport in ("nccl", "p2p"):
         ok &= check_multigrid(transport, rank, world)
+        ok &= check_helmholtz(transport, rank, world)
     dist.barrier()
     if rank == 0:
         print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL", flush=True)
