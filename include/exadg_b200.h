@@ -89,8 +89,9 @@ int exadg_b200_destroy(exadg_b200_operator *op);
  * viscous_operator.h:365-386 volume flux nu grad u, :489-560 gradient flux -1/2 nu [u] n and value flux nu ({dn u} - tau [u]),
  * I/operators/mass_kernel.h:32-93; penalty as for the Laplace operator, interior_penalty_parameter.h:43-128).  Vectors hold
  * FESystem(FE_DGQ(k)^n_components) DoFs: cell by cell, component blocks of (k+1)^3 values inside a cell.  Boundary types apply to
- * every component (velocity Dirichlet walls / Neumann outflow / periodic).  These operators run the general kernel on one GPU
- * (world = 1); vmult, vmult_add, calculate_(inverse_)diagonal, the Jacobi / Chebyshev / CG entry points and the multigrid apply. */
+ * every component (velocity Dirichlet walls / Neumann outflow / periodic).  vmult, vmult_add, calculate_(inverse_)diagonal, the
+ * Jacobi / Chebyshev / CG entry points and the multigrid apply.  Kernels: the general kernel; on a uniform periodic box (one GPU) the
+ * affine fast kernels on the (cell, component) blocks.  Partitions (world > 1): the ghost import moves whole cell blocks. */
 typedef struct { int n_components; double scaling_factor_mass; double viscosity; } exadg_b200_helmholtz_data;
 int exadg_b200_create_hypercube_helmholtz(const exadg_b200_hypercube_desc *desc, const exadg_b200_helmholtz_data *data, exadg_b200_operator **op);
 int exadg_b200_create_helmholtz(const exadg_b200_mesh_desc *desc, const exadg_b200_helmholtz_data *data, exadg_b200_operator **op);
