@@ -1018,9 +1018,9 @@ int exadg_b200_vmult_host_pipelined(exadg_b200_operator * op, double * dst_host,
       for (size_t i = 0; i < iota.size(); ++i) iota[i] = (int32_t)i;
       CUDA_CHECK(cudaMalloc(&op->d_iota, iota.size() * sizeof(int32_t)));
       CUDA_CHECK(cudaMemcpy(op->d_iota, iota.data(), iota.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-      CUDA_CHECK(cudaStreamCreateWithFlags(&op->hp_in, cudaStreamNonBlocking));
+      if (!op->hp_in) CUDA_CHECK(cudaStreamCreateWithFlags(&op->hp_in, cudaStreamNonBlocking)); // (shared with the direct variant)
       CUDA_CHECK(cudaStreamCreateWithFlags(&op->hp_out, cudaStreamNonBlocking));
-      CUDA_CHECK(cudaEventCreateWithFlags(&op->hp_start, cudaEventDisableTiming));
+      if (!op->hp_start) CUDA_CHECK(cudaEventCreateWithFlags(&op->hp_start, cudaEventDisableTiming));
       op->hp_ev_in.assign(op->hp.n_chunks, nullptr); op->hp_ev_cmp.assign(op->hp.n_chunks, nullptr);
       for (int c = 0; c < op->hp.n_chunks; ++c) {
         CUDA_CHECK(cudaEventCreateWithFlags(&op->hp_ev_in[c], cudaEventDisableTiming));
