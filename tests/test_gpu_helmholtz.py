@@ -12,7 +12,11 @@ WALLS = (1, 1, 1, 1, 2, 2)   # velocity Dirichlet on four sides, Neumann (outflo
 
 
 @pytest.mark.parametrize("case", [(2, 3, 1, 2, 1, 0.0, (0,) * 6, 30.0, 0.01), (3, 3, 2, 1, 2, 0.1, WALLS, 2.5, 0.3), (5, 3, 1, 1, 1, 0.0, (0,) * 6, 100.0, 1e-3),
-                                  (4, 1, 1, 2, 3, 0.15, WALLS, 1.0, 1.0), (1, 2, 2, 1, 1, 0.05, WALLS, 0.0, 2.0)])
+                                  (4, 1, 1, 2, 3, 0.15, WALLS, 1.0, 1.0), (1, 2, 2, 1, 1, 0.05, WALLS, 0.0, 2.0),
+                                  # uniform periodic boxes: the affine fast kernels on the (cell, component) blocks, every kernel family
+                                  # (plane kernel n = 2, 4, 5; line kernel n = 7, 8), ragged last batches included
+                                  (1, 3, 3, 1, 1, 0.0, (0,) * 6, 7.0, 0.5), (3, 3, 3, 1, 1, 0.0, (0,) * 6, 12.0, 0.02), (4, 2, 1, 2, 1, 0.0, (0,) * 6, 3.0, 1.0),
+                                  (6, 3, 1, 1, 1, 0.0, (0,) * 6, 50.0, 0.1), (7, 1, 1, 1, 1, 0.0, (0,) * 6, 0.5, 2.0)])
 def test_helmholtz_vmult_diagonal_and_inverse_mass_match_the_restatement(case):
     import exadg_b200
     degree, ncomp, n_sub, refine, m, deformation, bc, alpha, nu = case
