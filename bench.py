@@ -424,9 +424,9 @@ def applications_block():
     tv = timed(lambda: visc.vmult_async(yv, uv), 5)
     out["ins_operators"] = {"cells": 48 ** 3, "pressure_poisson": {"degree": 4, "dofs": pres.n(), "vmult_ms": tp * 1e3, "dofs_per_s": pres.n() / tp, "singular": bool(pres.operator_is_singular())},
                             "viscous_helmholtz": {"degree": 5, "components": 3, "dofs": visc.n(), "vmult_ms": tv * 1e3, "dofs_per_s": visc.n() / tv,
-                                                  "kernel": "affine line kernel on the (cell, component) blocks, mass term in front of the mass sweeps (uniform periodic box; general kernel elsewhere)"},
+                                                  "kernel": "affine line kernel, one component of a cell batch per CTA, mass term in front of the mass sweeps (uniform periodic box; general kernel elsewhere)"},
                             "what": "operators of the dual-splitting scheme on the Taylor-Green box (periodic, 48^3 cells): pressure Poisson = the SIPG Laplace fast path at k=4; "
-                                    "viscous step = gamma0/dt M + nu A_SIPG on 3 velocity components at k=5 (affine fast path on the (cell, component) blocks)"}
+                                    "viscous step = gamma0/dt M + nu A_SIPG on 3 velocity components at k=5 (affine fast path, one component of a cell batch per CTA)"}
     del pres, visc, u, y, uv, yv
     torch.cuda.empty_cache()
     return out

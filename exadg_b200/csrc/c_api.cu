@@ -133,9 +133,8 @@ struct exadg_b200_operator
   // uniform box with Dirichlet / Neumann faces: batches of cells that see the interior penalty on all their faces run the affine fast
   // kernel, the two cell layers next to the boundary (and the batches they share) the general kernel
   bool hybrid = false; int32_t * d_hyb_batches = nullptr, * d_hyb_cells = nullptr; int64_t n_hyb_batches = 0, n_hyb_cells = 0;
-  // Helmholtz / viscous operator on a uniform periodic box (the Taylor-Green setup): vmult on the affine fast kernels.  Every block
-  // (cell, component) of the vector is a "cell" of a virtual mesh whose neighbours are the same component of the neighbour cells;
-  // dev_helm holds that mesh's batch plan.  The diagonal and everything else stay with dev (general kernel).
+  // Helmholtz / viscous operator on a uniform periodic box (the Taylor-Green setup): vmult on the affine fast kernels, one component of a
+  // cell batch per CTA (CartArgs::ncomp); dev_helm holds the batch plan.  The diagonal and everything else stay with dev (general kernel).
   bool helm_fast = false; DeviceOperator dev_helm;
   // peer-memory halo (NVLink): one region [ghost A | ghost B | flags[world]] mapped by all peers
   bool p2p = false; char * p2p_region = nullptr; size_t p2p_ghost_bytes = 0; long long p2p_epoch = 0;
@@ -273,30 +272,6 @@ void finish_setup(exadg_b200_operator * op, double ip_factor, bool force_general
       } else cartesian_plan_destroy(D);
     }
   }
-  if (D.helmholtz && M.n_owned > 0 && M.cartesian_uniform && M.all_interior() && !force_general && M.world <= 1 && M.n_ghost == 0 && cartesian_supported(D.n)
-      && !getenv("EXADG_B200_NO_HELMHOLTZ_FAST")) {
-    const int nc = D.n_components;
-    HostMesh V;
-    V.n_owned = M.n_owned * nc; V.n_global_cells = V.n_owned; V.cartesian_uniform = true; V.world = 1;
-    for (int e = 0; e < 3; ++e) V.h[e] = M.h[e];
-    V.nb.resize((size_t)V.n_owned * 6);
-    for (int64_t c = 0; c < M.n_owned; ++c)
-      for (int comp = 0; comp < nc; ++comp)
-        for (int f = 0; f < 6; ++f) V.nb[((size_t)c * nc + comp) * 6 + f] = M.nb[c * 6 + f] * nc + comp;
-    DeviceOperator & H = op->dev_helm;
-    H = DeviceOperator();
-    H.degree = D.degree; H.n = D.n; H.n_owned = V.n_owned; H.n_global_dofs = D.n_global_dofs;
-    H.helmholtz = true; H.n_components = nc; H.mass_coeff = D.mass_coeff; H.laplace_coeff = D.laplace_coeff;
-    for (int e = 0; e < 3; ++e) H.h[e] = M.h[e];
-    double tk = 0.0;
-    for (int e = 0; e < 3; ++e) tk += 1.0 / M.h[e];
-    H.tau_hat = tk * ip_factor * (D.degree + 1.0) * (D.degree + 1.0);
-    H.cartesian = true;
-    CUDA_CHECK(cudaMalloc(&H.nb, V.nb.size() * sizeof(int32_t)));
-    CUDA_CHECK(cudaMemcpy(H.nb, V.nb.data(), V.nb.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    if (cartesian_plan_create(H, V) != 0) op->helm_fast = true;
-    else { cudaFree(H.nb); H.nb = nullptr; }
-  }
   CUDA_CHECK(cudaStreamCreateWithFlags(&op->stream, cudaStreamNonBlocking));
   {
     // the halo exchange must not queue behind the interior-cell kernel: highest priority for its stream
@@ -309,6 +284,21 @@ void finish_setup(exadg_b200_operator * op, double ip_factor, bool force_general
   CUDA_CHECK(cudaEventCreateWithFlags(&op->ev_order, cudaEventDisableTiming));
   reducer_init(op->red);
   setup_geometry(D, M, ip_factor, op->stream);
+  if (D.helmholtz && M.n_owned > 0 && M.cartesian_uniform && M.all_interior() && !force_general && M.world <= 1 && M.n_ghost == 0 && cartesian_supported(D.n)
+      && !getenv("EXADG_B200_NO_HELMHOLTZ_FAST")) {
+    // Helmholtz / viscous operator on a uniform periodic box: the affine fast kernels, one component of a cell batch per CTA.  The batch plan
+    // is that of the scalar operator on this mesh (dev_helm shares the neighbour table of dev and owns only the plan)
+    DeviceOperator & H = op->dev_helm;
+    H = DeviceOperator();
+    H.degree = D.degree; H.n = D.n; H.n_owned = D.n_owned; H.n_global_dofs = D.n_global_dofs; H.nb = D.nb;
+    H.helmholtz = true; H.n_components = D.n_components; H.mass_coeff = D.mass_coeff; H.laplace_coeff = D.laplace_coeff;
+    for (int e = 0; e < 3; ++e) H.h[e] = M.h[e];
+    double tk = 0.0;
+    for (int e = 0; e < 3; ++e) tk += 1.0 / M.h[e];
+    H.tau_hat = tk * ip_factor * (D.degree + 1.0) * (D.degree + 1.0);
+    H.cartesian = true;
+    if (cartesian_plan_create(H, M) != 0) op->helm_fast = true;
+  }
   // halo plan on the device + interior/boundary split for overlap
   if (M.world > 1) {
     for (auto & p : M.peers) {
@@ -776,7 +766,7 @@ int exadg_b200_destroy(exadg_b200_operator * op)
   cudaDeviceSynchronize();
   DeviceOperator & D = op->dev;
   cartesian_plan_destroy(D);
-  cartesian_plan_destroy(op->dev_helm); cudaFree(op->dev_helm.nb);
+  cartesian_plan_destroy(op->dev_helm); // (its neighbour table is dev's)
   if (op->p2p) D.ghost = op->ghost_alloc;
   cudaFree(D.cellJxW); cudaFree(op->d_hyb_batches); cudaFree(op->d_hyb_cells);
   cudaFree(D.nb); cudaFree(D.face_id); cudaFree(D.face_info); cudaFree(D.cellG); cudaFree(D.faceG); cudaFree(D.tau_f); cudaFree(D.tau_cell); cudaFree(D.ghost);

@@ -51,6 +51,8 @@ struct CartArgs
   const double * src; const double * ghost; double * dst;
   int64_t n_owned; int n_items; int H; int add;
   double mass; // Helmholtz / viscous operator on a uniform box: scaling_factor_mass x cell volume, added before the mass sweeps (0: Laplace)
+  int ncomp;   // components of the Helmholtz operator (1: scalar).  Vectors are cell-major with component blocks of n^3 values inside a cell; a CTA
+               // applies the operator to ONE component of its batch of cells (blockIdx = item * ncomp + component): the batch plan is that of the scalar mesh
 };
 
 // ---- TMA (bulk async copy) + mbarrier helpers, sm_90+/sm_100a PTX ----
@@ -90,7 +92,8 @@ template<int N> struct CartCfg { static constexpr int B = (N >= 6) ? 16 : ((N >=
 
 // BB: cells per batch (default CartCfg; n = 4 also with 32-cell batches: measurement switch EXADG_B200_PLANE_B=32, three CTAs per SM instead of two but
 // 2.0 instead of 1.5 out-of-batch faces per cell - measured slower, 91.8 against 99.8 GDoF/s, scripts/r02_shot50.sh)
-template<int N, int BB = CartCfg<N>::B>
+// COMP: component blocks (Helmholtz operator with ncomp > 1); the scalar instantiation is the code it was before the blocks existed
+template<int N, int BB = CartCfg<N>::B, bool COMP = false>
 __global__ void __launch_bounds__(BB * N, (N == 5) ? 2 : ((N == 4 && BB == 32) ? 3 : 1)) vmult_cartesian_kernel(const __grid_constant__ CartTables<N> T, const CartArgs A)
 {
   constexpr int B = BB, NT = B * N;
@@ -113,13 +116,17 @@ __global__ void __launch_bounds__(BB * N, (N == 5) ? 2 : ((N == 4 && BB == 32) ?
   uint64_t * bar = reinterpret_cast<uint64_t *>(slotS + B * 6);
 
   const int t = threadIdx.x, lc = t / N, s = t % N;
-  const int batch = A.batches ? A.batches[blockIdx.x] : (int)blockIdx.x;
+  const int ncomp = COMP ? A.ncomp : 1;
+  const int bitem = COMP ? (int)blockIdx.x / ncomp : (int)blockIdx.x, comp = COMP ? (int)blockIdx.x % ncomp : 0;
+  const int batch = A.batches ? A.batches[bitem] : bitem;
   const int64_t b0 = (int64_t)batch * B;
+  // offset of value i of the batch (cell i / n^3 of the batch, component comp) in src / dst
+  auto goff = [&](int i) { return COMP ? ((b0 + i / N3) * ncomp + comp) * N3 + i % N3 : b0 * N3 + i; };
   const int nvalid = (int)min((int64_t)B, A.n_owned - b0);
   const bool valid = lc < nvalid;
   // contiguous cell data (odd n: no padding) goes through one TMA bulk copy; 16-byte granularity
   const uint32_t bytes = (uint32_t)(nvalid * N3 * sizeof(double));
-  const bool use_tma = (PS == N2) && (bytes % 16 == 0);
+  const bool use_tma = (PS == N2) && (bytes % 16 == 0) && !COMP; // (component blocks of a batch are not contiguous)
 
   // ---- phase L: stage the batch, its neighbour table and the traces of out-of-batch neighbours ----
   if (use_tma) {
@@ -135,7 +142,7 @@ __global__ void __launch_bounds__(BB * N, (N == 5) ? 2 : ((N == 4 && BB == 32) ?
     for (int i0 = t; i0 < nvalid * N3; i0 += NT * UNR) {
       double v[UNR];
 #pragma unroll
-      for (int q = 0; q < UNR; ++q) { const int i = i0 + q * NT; v[q] = (i < nvalid * N3) ? A.src[b0 * N3 + i] : 0.0; }
+      for (int q = 0; q < UNR; ++q) { const int i = i0 + q * NT; v[q] = (i < nvalid * N3) ? A.src[goff(i)] : 0.0; }
 #pragma unroll
       for (int q = 0; q < UNR; ++q) {
         const int i = i0 + q * NT;
@@ -157,7 +164,7 @@ __global__ void __launch_bounds__(BB * N, (N == 5) ? 2 : ((N == 4 && BB == 32) ?
           const int2 h = hlS[e];
           const int f = h.x & 7, d = f >> 1;
           sp[q] = (f & 1) ^ 1; // neighbour is entered through its face (d, sp)
-          const double * un = (h.y < A.n_owned) ? A.src + (size_t)h.y * N3 : A.ghost + (size_t)(h.y - A.n_owned) * N3;
+          const double * un = (h.y < A.n_owned) ? A.src + ((size_t)h.y * ncomp + comp) * N3 : A.ghost + ((size_t)(h.y - A.n_owned) * ncomp + comp) * N3;
           const int sd = (d == 0) ? 1 : (d == 1 ? N : N2);
           const int s1 = (d == 0) ? N : 1, s2 = (d == 2) ? N : N2;
           const double * line = un + a * s1 + b * s2;
@@ -363,7 +370,7 @@ __global__ void __launch_bounds__(BB * N, (N == 5) ? 2 : ((N == 4 && BB == 32) ?
   for (int i = t; i < nvalid * N3; i += NT) {
     const int c = i / N3, rem = i % N3, k = rem / N2, e = rem % N2;
     const double v = U[c * CS + k * PS + e];
-    if (A.add) A.dst[b0 * N3 + i] += v; else A.dst[b0 * N3 + i] = v;
+    if (A.add) A.dst[goff(i)] += v; else A.dst[goff(i)] = v;
   }
 }
 
@@ -389,7 +396,7 @@ __global__ void __launch_bounds__(BB * N, (N == 5) ? 2 : ((N == 4 && BB == 32) ?
 template<int N, int BB> struct LineCfg { static constexpr int B = BB; static constexpr int NT = B * N * N; static constexpr int RS = N | 1; static constexpr int CS = RS * N * N;
                                          static constexpr int MINB = (BB == 16) ? (N == 6 ? 2 : 1) : (N == 6 ? 4 : (N == 7 ? 3 : 2)); };
 
-template<int N, int BB>
+template<int N, int BB, bool COMP = false>
 __global__ void __launch_bounds__(LineCfg<N, BB>::NT, LineCfg<N, BB>::MINB) vmult_cartesian_line_kernel(const __grid_constant__ CartTables<N> T, const CartArgs A)
 {
   constexpr int B = LineCfg<N, BB>::B, NT = LineCfg<N, BB>::NT, RS = LineCfg<N, BB>::RS, CS = LineCfg<N, BB>::CS;
@@ -405,8 +412,12 @@ __global__ void __launch_bounds__(LineCfg<N, BB>::NT, LineCfg<N, BB>::MINB) vmul
   int * slotS = nbS + B * 6;                                     // [B][6]
 
   const int t = threadIdx.x, c = t / N2, ab = t % N2, a = ab % N, b = ab / N;
-  const int batch = A.batches ? A.batches[blockIdx.x] : (int)blockIdx.x;
+  const int ncomp = COMP ? A.ncomp : 1;
+  const int bitem = COMP ? (int)blockIdx.x / ncomp : (int)blockIdx.x, comp = COMP ? (int)blockIdx.x % ncomp : 0;
+  const int batch = A.batches ? A.batches[bitem] : bitem;
   const int64_t b0 = (int64_t)batch * B;
+  // offset of value i of the batch (cell i / n^3 of the batch, component comp) in src / dst
+  auto goff = [&](int i) { return COMP ? ((b0 + i / N3) * ncomp + comp) * N3 + i % N3 : b0 * N3 + i; };
   const int nvalid = (int)min((int64_t)B, A.n_owned - b0);
   const bool valid = c < nvalid;
 
@@ -419,7 +430,7 @@ __global__ void __launch_bounds__(LineCfg<N, BB>::NT, LineCfg<N, BB>::MINB) vmul
     for (int i0 = t; i0 < nvalid * N3; i0 += NT * UNR) {
       double v[UNR];
 #pragma unroll
-      for (int q = 0; q < UNR; ++q) { const int i = i0 + q * NT; v[q] = (i < nvalid * N3) ? A.src[b0 * N3 + i] : 0.0; }
+      for (int q = 0; q < UNR; ++q) { const int i = i0 + q * NT; v[q] = (i < nvalid * N3) ? A.src[goff(i)] : 0.0; }
 #pragma unroll
       for (int q = 0; q < UNR; ++q) {
         const int i = i0 + q * NT;
@@ -442,7 +453,7 @@ __global__ void __launch_bounds__(LineCfg<N, BB>::NT, LineCfg<N, BB>::MINB) vmul
           const int2 h = hlS[e];
           const int f = h.x & 7, d = f >> 1;
           sp[q] = (f & 1) ^ 1; // the neighbour is entered through its face (d, sp)
-          const double * un = (h.y < A.n_owned) ? A.src + (size_t)h.y * N3 : A.ghost + (size_t)(h.y - A.n_owned) * N3;
+          const double * un = (h.y < A.n_owned) ? A.src + ((size_t)h.y * ncomp + comp) * N3 : A.ghost + ((size_t)(h.y - A.n_owned) * ncomp + comp) * N3;
           const int sd = (d == 0) ? 1 : (d == 1 ? N : N2);
           const int s1 = (d == 0) ? N : 1, s2 = (d == 2) ? N : N2;
           const double * line = un + la * s1 + lb * s2;
@@ -555,7 +566,7 @@ __global__ void __launch_bounds__(LineCfg<N, BB>::NT, LineCfg<N, BB>::MINB) vmul
   for (int i = t; i < nvalid * N3; i += NT) {
     const int cc = i / N3, rem = i % N3;
     const double v = Tt[cc * CS + (rem / N) * RS + rem % N];
-    if (A.add & 1) A.dst[b0 * N3 + i] += v; else A.dst[b0 * N3 + i] = v;
+    if (A.add & 1) A.dst[goff(i)] += v; else A.dst[goff(i)] = v;
   }
 }
 
@@ -1035,11 +1046,17 @@ void launch_n(const DeviceOperator & op, const CartPlan & plan, double * dst, co
   CartArgs A;
   A.nb = op.nb; A.halo = plan.d_halo; A.halo_cnt = plan.d_cnt; A.src = src; A.ghost = op.ghost; A.dst = dst;
   A.n_owned = op.n_owned; A.H = plan.H; A.add = add ? 1 : 0; A.mass = op.helmholtz ? op.mass_coeff * op.h[0] * op.h[1] * op.h[2] : 0.0;
+  A.ncomp = op.helmholtz ? op.n_components : 1;
   A.batches = which == 0 ? nullptr : (which == 1 ? plan.d_interior : plan.d_boundary);
   A.n_items = which == 0 ? plan.n_batches : (which == 1 ? plan.n_interior : plan.n_boundary);
   if (list) { A.batches = list; A.n_items = n_list; }
   if (A.n_items == 0) return;
-  if (N == 4 && plan.B == 32) vmult_cartesian_kernel<4, 32><<<A.n_items, 32 * 4, plan.smem, stream>>>(*reinterpret_cast<const CartTables<4> *>(plan.tables.data()), A);
+  if (A.ncomp > 1) { // Helmholtz operator: one component of a batch per CTA
+    if (first_use_on_device((const void *)vmult_cartesian_kernel<N, CartCfg<N>::B, true>))
+      CUDA_CHECK(cudaFuncSetAttribute(vmult_cartesian_kernel<N, CartCfg<N>::B, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    vmult_cartesian_kernel<N, CartCfg<N>::B, true><<<A.n_items * A.ncomp, B * N, plan.smem, stream>>>(T, A);
+  }
+  else if (N == 4 && plan.B == 32) vmult_cartesian_kernel<4, 32><<<A.n_items, 32 * 4, plan.smem, stream>>>(*reinterpret_cast<const CartTables<4> *>(plan.tables.data()), A);
   else vmult_cartesian_kernel<N><<<A.n_items, B * N, plan.smem, stream>>>(T, A);
   CUDA_CHECK(cudaGetLastError());
 }
@@ -1053,13 +1070,19 @@ void launch_line_b(const DeviceOperator & op, const CartPlan & plan, double * ds
   CartArgs A;
   A.nb = op.nb; A.halo = plan.d_halo; A.halo_cnt = plan.d_cnt; A.src = src; A.ghost = op.ghost; A.dst = dst;
   A.n_owned = op.n_owned; A.H = plan.H; A.add = add ? 1 : 0; A.mass = op.helmholtz ? op.mass_coeff * op.h[0] * op.h[1] * op.h[2] : 0.0;
+  A.ncomp = op.helmholtz ? op.n_components : 1;
   A.batches = which == 0 ? nullptr : (which == 1 ? plan.d_interior : plan.d_boundary);
   A.n_items = which == 0 ? plan.n_batches : (which == 1 ? plan.n_interior : plan.n_boundary);
   if (list) { A.batches = list; A.n_items = n_list; }
   if (A.n_items == 0) return;
   static const bool skip_halo = getenv("EXADG_B200_LINE_SKIP_HALO") != nullptr; // timing experiment only (results wrong)
   if (skip_halo) A.add |= 2;
-  vmult_cartesian_line_kernel<N, BB><<<A.n_items, LineCfg<N, BB>::NT, plan.smem_line, stream>>>(T, A);
+  if (A.ncomp > 1) {
+    if (first_use_on_device((const void *)vmult_cartesian_line_kernel<N, BB, true>))
+      CUDA_CHECK(cudaFuncSetAttribute(vmult_cartesian_line_kernel<N, BB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    vmult_cartesian_line_kernel<N, BB, true><<<A.n_items * A.ncomp, LineCfg<N, BB>::NT, plan.smem_line, stream>>>(T, A);
+  }
+  else vmult_cartesian_line_kernel<N, BB><<<A.n_items, LineCfg<N, BB>::NT, plan.smem_line, stream>>>(T, A);
   CUDA_CHECK(cudaGetLastError());
 }
 template<int N>
